@@ -1,0 +1,202 @@
+// C ABI of libb200mcmc.so (declared in include/b200mcmc.h): model handle, validation, dispatch.
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "model.cuh"
+
+namespace b2m {
+
+static thread_local std::string tl_error;
+int64_t g_launches = 0;
+void set_error(const std::string &msg) { tl_error = msg; }
+
+int pick_lanes(const KModel &km, int64_t n_chains, int requested);
+int launch_logp_grad(const KModel &km, const float *theta, int64_t C, float *logp, float *grad, int lanes,
+                     cudaStream_t st);
+int launch_hmc(const KModel &km, b2m_hmc_args a, cudaStream_t st);
+int launch_mh(const KModel &km, b2m_mh_args a, cudaStream_t st);
+int launch_nuts(const KModel &km, b2m_nuts_args a, cudaStream_t st);
+
+}  // namespace b2m
+
+struct b2m_model {
+  b2m::KModel km{};
+  int model_class = 0;
+  void *dev_terms = nullptr, *dev_lin = nullptr, *dev_arrays = nullptr;
+  std::vector<b2m_term> terms;
+  std::vector<b2m_lin_entry> lin;
+  std::vector<b2m_array> arrays;
+};
+
+using b2m::set_error;
+
+static bool valid_lanes(int l) { return l == 0 || l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32; }
+
+static int check_operand(const b2m_operand &o, int length, int D, int n_lin, const b2m_array *arrays, int n_arrays,
+                         const char *slot, int t) {
+  auto fail = [&](const std::string &why) {
+    set_error("term " + std::to_string(t) + " operand " + slot + ": " + why);
+    return 1;
+  };
+  switch (o.kind) {
+    case B2M_OP_CONST: return 0;
+    case B2M_OP_PARAM:
+      if (o.a < 0 || o.a >= D) return fail("parameter index out of range");
+      return 0;
+    case B2M_OP_DATA:
+      if (o.a < 0 || o.a >= n_arrays) return fail("array index out of range");
+      if (arrays[o.a].cols != 1 || arrays[o.a].rows < length) return fail("observed array shorter than the term");
+      return 0;
+    case B2M_OP_PARAMVEC:
+      if (o.a < 0 || o.a + length > D) return fail("parameter slice out of range");
+      return 0;
+    case B2M_OP_LIN:
+      if (o.a < 0 || o.b < 0 || o.a + o.b > n_lin) return fail("linear-entry range out of range");
+      return 0;
+    case B2M_OP_MATVEC:
+      if (o.a < 0 || o.a >= n_arrays) return fail("matrix index out of range");
+      if (arrays[o.a].rows < length) return fail("matrix has fewer rows than the term");
+      if (o.b < 0 || o.b + arrays[o.a].cols > D) return fail("matvec parameter slice out of range");
+      return 0;
+    default: return fail("unknown operand kind " + std::to_string(o.kind));
+  }
+}
+
+extern "C" {
+
+const char *b2m_last_error(void) { return b2m::tl_error.c_str(); }
+int b2m_abi_version(void) { return B2M_ABI_VERSION; }
+int64_t b2m_launch_count(void) { return b2m::g_launches; }
+
+int b2m_struct_sizes(int32_t *out6) {
+  out6[0] = (int32_t)sizeof(b2m_term);
+  out6[1] = (int32_t)sizeof(b2m_operand);
+  out6[2] = (int32_t)sizeof(b2m_lin_entry);
+  out6[3] = (int32_t)sizeof(b2m_hmc_args);
+  out6[4] = (int32_t)sizeof(b2m_mh_args);
+  out6[5] = (int32_t)sizeof(b2m_nuts_args);
+  return 0;
+}
+
+int b2m_model_create(const b2m_term *terms, int32_t n_terms, const b2m_lin_entry *lin, int32_t n_lin,
+                     const b2m_array *arrays, int32_t n_arrays, int32_t D, b2m_model **out) {
+  B2M_REQUIRE(out != nullptr, "b2m_model_create: out is NULL");
+  *out = nullptr;
+  B2M_REQUIRE(n_terms > 0 && n_terms <= 256, "b2m_model_create: need 1..256 terms");
+  B2M_REQUIRE(D > 0, "b2m_model_create: D must be positive");
+  B2M_REQUIRE(n_lin >= 0 && n_arrays >= 0, "b2m_model_create: negative table size");
+  int n_matvec = 0, max_len = 1;
+  for (int e = 0; e < n_lin; ++e) {
+    B2M_REQUIRE(lin[e].param < D, "linear entry: parameter index out of range");
+    B2M_REQUIRE(lin[e].array < n_arrays, "linear entry: array index out of range");
+  }
+  for (int t = 0; t < n_terms; ++t) {
+    const b2m_term &T = terms[t];
+    if (T.dist < B2M_NORMAL || T.dist > B2M_CONSTANT) {
+      set_error("term " + std::to_string(t) + ": unknown distribution tag " + std::to_string(T.dist));
+      return 1;
+    }
+    B2M_REQUIRE(T.length >= 0, "term length must be non-negative");
+    if (check_operand(T.x, T.length, D, n_lin, arrays, n_arrays, "x", t)) return 1;
+    if (check_operand(T.p0, T.length, D, n_lin, arrays, n_arrays, "p0", t)) return 1;
+    if (check_operand(T.p1, T.length, D, n_lin, arrays, n_arrays, "p1", t)) return 1;
+    n_matvec += (T.x.kind == B2M_OP_MATVEC) + (T.p0.kind == B2M_OP_MATVEC) + (T.p1.kind == B2M_OP_MATVEC);
+    if (T.length > max_len) max_len = T.length;
+  }
+  b2m_model *m = new b2m_model();
+  m->terms.assign(terms, terms + n_terms);
+  if (n_lin) m->lin.assign(lin, lin + n_lin);
+  if (n_arrays) m->arrays.assign(arrays, arrays + n_arrays);
+  m->model_class = n_matvec > 0 ? 1 : 0;
+
+  std::vector<b2m::DevArray> da(n_arrays > 0 ? n_arrays : 1);
+  int64_t stage = 0;
+  for (int a = 0; a < n_arrays; ++a) {
+    da[a].ptr = arrays[a].data;
+    da[a].rows = arrays[a].rows;
+    da[a].cols = arrays[a].cols;
+    if (arrays[a].cols == 1) stage += (arrays[a].rows + 3) & ~int64_t(3);
+  }
+  auto up = [&](void **dst, const void *src, size_t bytes) -> int {
+    if (bytes == 0) bytes = 16;
+    B2M_CHECK_CUDA(cudaMalloc(dst, bytes));
+    if (src) B2M_CHECK_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+  };
+  if (up(&m->dev_terms, terms, sizeof(b2m_term) * n_terms) ||
+      up(&m->dev_lin, n_lin ? lin : nullptr, sizeof(b2m_lin_entry) * n_lin) ||
+      up(&m->dev_arrays, n_arrays ? da.data() : nullptr, sizeof(b2m::DevArray) * n_arrays)) {
+    b2m_model_destroy(m);
+    return 2;
+  }
+  m->km.terms = static_cast<const b2m_term *>(m->dev_terms);
+  m->km.lin = static_cast<const b2m_lin_entry *>(m->dev_lin);
+  m->km.arrays = static_cast<const b2m::DevArray *>(m->dev_arrays);
+  m->km.n_terms = n_terms;
+  m->km.n_lin = n_lin;
+  m->km.n_arrays = n_arrays;
+  m->km.D = D;
+  m->km.max_len = max_len;
+  // observation vectors are staged in shared memory when they fit beside the mailboxes
+  m->km.stage_floats = (stage * 4 <= 96 * 1024) ? (int32_t)stage : 0;
+  *out = m;
+  return 0;
+}
+
+void b2m_model_destroy(b2m_model *m) {
+  if (!m) return;
+  if (m->dev_terms) cudaFree(m->dev_terms);
+  if (m->dev_lin) cudaFree(m->dev_lin);
+  if (m->dev_arrays) cudaFree(m->dev_arrays);
+  delete m;
+}
+
+int b2m_model_dim(const b2m_model *m) { return m ? m->km.D : -1; }
+int b2m_model_class(const b2m_model *m) { return m ? m->model_class : -1; }
+
+int b2m_logp_grad(b2m_model *m, const float *theta, int64_t n_chains, float *logp, float *grad, int32_t lanes,
+                  void *stream) {
+  B2M_REQUIRE(m && theta && logp, "b2m_logp_grad: NULL argument");
+  B2M_REQUIRE(n_chains > 0, "b2m_logp_grad: n_chains must be positive");
+  B2M_REQUIRE(valid_lanes(lanes), "b2m_logp_grad: lanes must be 0 or a power of two <= 32");
+  B2M_REQUIRE(m->model_class == 0, "b2m_logp_grad: GLM-class models are not built in this library version");
+  return b2m::launch_logp_grad(m->km, theta, n_chains, logp, grad, lanes, static_cast<cudaStream_t>(stream));
+}
+
+int b2m_hmc_run(b2m_model *m, const b2m_hmc_args *a, void *stream) {
+  B2M_REQUIRE(m && a, "b2m_hmc_run: NULL argument");
+  B2M_REQUIRE(a->n_chains > 0 && a->n_iter >= 0 && a->n_leapfrog > 0, "b2m_hmc_run: bad sizes");
+  B2M_REQUIRE(a->theta && a->step_size && a->n_accept && a->n_total, "b2m_hmc_run: NULL state pointer");
+  B2M_REQUIRE(valid_lanes(a->lanes), "b2m_hmc_run: lanes must be 0 or a power of two <= 32");
+  B2M_REQUIRE(a->adapt >= B2M_ADAPT_NONE && a->adapt <= B2M_ADAPT_DUAL_AVERAGING, "b2m_hmc_run: bad adapt mode");
+  B2M_REQUIRE(a->adapt != B2M_ADAPT_DUAL_AVERAGING || a->da_state, "b2m_hmc_run: dual averaging needs da_state");
+  B2M_REQUIRE(m->model_class == 0, "b2m_hmc_run: GLM-class models are not built in this library version");
+  if (a->n_iter == 0) return 0;
+  return b2m::launch_hmc(m->km, *a, static_cast<cudaStream_t>(stream));
+}
+
+int b2m_mh_run(b2m_model *m, const b2m_mh_args *a, void *stream) {
+  B2M_REQUIRE(m && a, "b2m_mh_run: NULL argument");
+  B2M_REQUIRE(a->n_chains > 0 && a->n_iter >= 0, "b2m_mh_run: bad sizes");
+  B2M_REQUIRE(a->theta && a->logp && a->n_accept, "b2m_mh_run: NULL state pointer");
+  B2M_REQUIRE(valid_lanes(a->lanes), "b2m_mh_run: lanes must be 0 or a power of two <= 32");
+  B2M_REQUIRE(m->model_class == 0, "b2m_mh_run: GLM-class models are not built in this library version");
+  if (a->n_iter == 0) return 0;
+  return b2m::launch_mh(m->km, *a, static_cast<cudaStream_t>(stream));
+}
+
+int b2m_nuts_run(b2m_model *m, const b2m_nuts_args *a, void *stream) {
+  B2M_REQUIRE(m && a, "b2m_nuts_run: NULL argument");
+  B2M_REQUIRE(a->n_chains > 0 && a->n_iter >= 0, "b2m_nuts_run: bad sizes");
+  B2M_REQUIRE(a->max_tree_depth >= 1 && a->max_tree_depth <= B2M_MAX_TREE_DEPTH, "b2m_nuts_run: max_tree_depth out of range");
+  B2M_REQUIRE(a->theta && a->step_size && a->da_state && a->n_accept && a->n_leaves && a->n_diverge,
+              "b2m_nuts_run: NULL state pointer");
+  B2M_REQUIRE(valid_lanes(a->lanes), "b2m_nuts_run: lanes must be 0 or a power of two <= 32");
+  B2M_REQUIRE(m->model_class == 0, "b2m_nuts_run: GLM-class models are not built in this library version");
+  if (a->n_iter == 0) return 0;
+  return b2m::launch_nuts(m->km, *a, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

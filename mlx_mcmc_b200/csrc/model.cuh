@@ -1,0 +1,309 @@
+// Device-side model: the traced term table, staged in shared memory, and the fused
+// log-density + analytic gradient evaluation used by every pointwise-class kernel.
+//
+// Replaces: the user's log_prob + Distribution.log_prob bodies (mlx_mcmc/distributions/*.py) and
+// MLX's reverse-mode pass over them (mx.grad in kernels/hmc.py:53-67, kernels/nuts.py:76-87).
+// Value and gradient follow SURVEY.md 8(a2'): outside a distribution's support the term is -inf
+// with zero gradient (VJP of `where`); log of a negative scale gives a NaN value with the finite
+// analytic gradient.
+#pragma once
+#include "common.cuh"
+
+namespace b2m {
+
+struct DevArray {
+  const float *ptr;
+  int64_t rows;
+  int64_t cols;
+};
+
+// What the host passes by value to every kernel.
+struct KModel {
+  const b2m_term *terms;
+  const b2m_lin_entry *lin;
+  const DevArray *arrays;
+  int32_t n_terms, n_lin, n_arrays, D;
+  int32_t stage_floats;  // total floats of the 1-D arrays staged in shared memory (0 = no staging)
+  int32_t max_len;       // longest term
+};
+
+// Per-CTA copy in shared memory.
+struct SModel {
+  const b2m_term *terms;
+  const b2m_lin_entry *lin;
+  const DevArray *arrays;  // ptr fields point at the staged shared-memory copies when staged
+  int32_t n_terms, D;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+__host__ inline size_t model_smem_bytes(const KModel &km) {
+  return align16(sizeof(b2m_term) * km.n_terms) + align16(sizeof(b2m_lin_entry) * (km.n_lin > 0 ? km.n_lin : 1)) +
+         align16(sizeof(DevArray) * (km.n_arrays > 0 ? km.n_arrays : 1)) + align16(sizeof(float) * km.stage_floats);
+}
+
+// Cooperative copy of the term table (+ float4-staged observation vectors) into shared memory.
+// Returns the first free byte after the model region.
+__device__ inline unsigned char *model_to_smem(const KModel &km, unsigned char *smem, SModel &sm) {
+  b2m_term *terms = reinterpret_cast<b2m_term *>(smem);
+  smem += align16(sizeof(b2m_term) * km.n_terms);
+  b2m_lin_entry *lin = reinterpret_cast<b2m_lin_entry *>(smem);
+  smem += align16(sizeof(b2m_lin_entry) * (km.n_lin > 0 ? km.n_lin : 1));
+  DevArray *arrays = reinterpret_cast<DevArray *>(smem);
+  smem += align16(sizeof(DevArray) * (km.n_arrays > 0 ? km.n_arrays : 1));
+  float *stage = reinterpret_cast<float *>(smem);
+  smem += align16(sizeof(float) * km.stage_floats);
+
+  const int tid = threadIdx.x, nt = blockDim.x;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(km.terms);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(terms);
+    for (int i = tid; i < int(sizeof(b2m_term) / 4) * km.n_terms; i += nt) dst[i] = src[i];
+    const uint32_t *ls = reinterpret_cast<const uint32_t *>(km.lin);
+    uint32_t *ld = reinterpret_cast<uint32_t *>(lin);
+    for (int i = tid; i < int(sizeof(b2m_lin_entry) / 4) * km.n_lin; i += nt) ld[i] = ls[i];
+  }
+  if (tid == 0) {
+    int off = 0;  // in floats, each array padded to a multiple of 4 so float4 copies stay aligned
+    for (int a = 0; a < km.n_arrays; ++a) {
+      DevArray d = km.arrays[a];
+      if (km.stage_floats > 0 && d.cols == 1) {
+        arrays[a].ptr = stage + off;
+        off += int((d.rows + 3) & ~int64_t(3));
+      } else {
+        arrays[a].ptr = d.ptr;
+      }
+      arrays[a].rows = d.rows;
+      arrays[a].cols = d.cols;
+    }
+  }
+  __syncthreads();
+  if (km.stage_floats > 0) {
+    for (int a = 0; a < km.n_arrays; ++a) {
+      DevArray d = km.arrays[a];
+      if (d.cols != 1) continue;
+      float *dst = const_cast<float *>(arrays[a].ptr);
+      const int n4 = int(d.rows >> 2);
+      if ((reinterpret_cast<uintptr_t>(d.ptr) & 15) == 0) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(d.ptr);
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+        for (int i = tid; i < n4; i += nt) d4[i] = __ldg(s4 + i);  // coalesced 16-byte loads
+        for (int i = (n4 << 2) + tid; i < d.rows; i += nt) dst[i] = __ldg(d.ptr + i);
+      } else {
+        for (int i = tid; i < d.rows; i += nt) dst[i] = __ldg(d.ptr + i);
+      }
+    }
+  }
+  __syncthreads();
+  sm.terms = terms;
+  sm.lin = lin;
+  sm.arrays = arrays;
+  sm.n_terms = km.n_terms;
+  sm.D = km.D;
+  return smem;
+}
+
+// ---------------------------------------------------------------- operands
+// `th` / `gr` are this lane's private columns of the shared-memory mailboxes: element d lives at
+// [d * TS], TS = blockDim.x, so consecutive threads hit consecutive banks.
+__device__ __forceinline__ bool op_varies(const b2m_operand &o) {
+  return o.kind == B2M_OP_DATA || o.kind == B2M_OP_PARAMVEC || o.kind == B2M_OP_LIN;
+}
+
+__device__ __forceinline__ float op_fetch(const b2m_operand &o, int n, const float *th, int TS, const SModel &sm) {
+  switch (o.kind) {
+    case B2M_OP_PARAM: return th[o.a * TS];
+    case B2M_OP_DATA: return sm.arrays[o.a].ptr[n];
+    case B2M_OP_PARAMVEC: return th[(o.a + n) * TS];
+    case B2M_OP_LIN: {
+      float v = o.c;
+      for (int e = o.a; e < o.a + o.b; ++e) {
+        b2m_lin_entry le = sm.lin[e];
+        float t = le.coef;
+        if (le.array >= 0) t *= sm.arrays[le.array].ptr[n];
+        if (le.param >= 0) t *= th[le.param * TS];
+        v += t;
+      }
+      return v;
+    }
+    default: return o.c;
+  }
+}
+
+__device__ __forceinline__ void op_scatter(const b2m_operand &o, int n, float adj, float *gr, int TS,
+                                           const SModel &sm) {
+  switch (o.kind) {
+    case B2M_OP_PARAM: gr[o.a * TS] += adj; break;
+    case B2M_OP_PARAMVEC: gr[(o.a + n) * TS] += adj; break;
+    case B2M_OP_LIN:
+      for (int e = o.a; e < o.a + o.b; ++e) {
+        b2m_lin_entry le = sm.lin[e];
+        if (le.param < 0) continue;
+        float t = le.coef;
+        if (le.array >= 0) t *= sm.arrays[le.array].ptr[n];
+        gr[le.param * TS] += adj * t;
+      }
+      break;
+    default: break;
+  }
+}
+
+// ---------------------------------------------------------------- densities
+constexpr float kHalfLog2Pi = 0.91893853320467274178f;
+constexpr float kLog2 = 0.69314718055994530942f;
+
+struct Elem {
+  float lp, dx, d0, d1;
+};
+
+template <bool GRAD>
+__device__ __forceinline__ Elem dist_eval(int dist, float x, float p0, float p1, float k0, float k1, float k2) {
+  Elem e;
+  e.lp = 0.f; e.dx = 0.f; e.d0 = 0.f; e.d1 = 0.f;
+  const float ninf = -INFINITY;
+  switch (dist) {
+    case B2M_NORMAL: {  // normal.py:49-56
+      float z = x - p0, var = p1 * p1;
+      e.lp = (-kHalfLog2Pi - logf(p1)) - (0.5f * (z * z)) / var;
+      if (GRAD) {
+        float t = z / var;
+        e.dx = -t; e.d0 = t; e.d1 = z * t / p1 - 1.0f / p1;
+      }
+    } break;
+    case B2M_HALFNORMAL: {  // halfnormal.py:55-63
+      if (x >= 0.f) {
+        float var = p0 * p0;
+        e.lp = ((kLog2 + -kHalfLog2Pi) - logf(p0)) - (0.5f * (x * x)) / var;
+        if (GRAD) {
+          float t = x / var;
+          e.dx = -t; e.d0 = x * t / p0 - 1.0f / p0;
+        }
+      } else {
+        e.lp = ninf;
+      }
+    } break;
+    case B2M_EXPONENTIAL: {  // exponential.py:61-71
+      if (x >= 0.f) {
+        e.lp = logf(p0) - p0 * x;
+        if (GRAD) { e.dx = -p0; e.d0 = 1.0f / p0 - x; }
+      } else {
+        e.lp = ninf;
+      }
+    } break;
+    case B2M_GAMMA: {  // gamma.py:53-88 ; p0 = rate, k0 = alpha, k1 = lgamma(alpha)
+      if (x > 0.f) {
+        e.lp = (k0 * logf(p0) - k1) + (k0 - 1.0f) * logf(x) - p0 * x;
+        if (GRAD) { e.dx = (k0 - 1.0f) / x - p0; e.d0 = k0 / p0 - x; }
+      } else {
+        e.lp = ninf;
+      }
+    } break;
+    case B2M_BETA: {  // beta.py:53-91 ; k0 = a, k1 = b, k2 = log B(a, b)
+      if (x > 0.f && x < 1.f) {
+        e.lp = (k0 - 1.0f) * logf(x) + (k1 - 1.0f) * logf(1.0f - x) - k2;
+        if (GRAD) e.dx = (k0 - 1.0f) / x - (k1 - 1.0f) / (1.0f - x);
+      } else {
+        e.lp = ninf;
+      }
+    } break;
+    default: e.lp = k0; break;  // B2M_CONSTANT
+  }
+  return e;
+}
+
+// ---------------------------------------------------------------- fused value + gradient
+// One chain is served by G lanes (G in {1,2,..,32}, a power of two, lanes contiguous in the warp).
+// Each lane walks elements n = lane, lane+G, ... of every term; the G partial sums are combined
+// with xor shuffles so every lane ends with the identical total.
+//   th : this lane's theta mailbox column (read)      -- all G lanes hold the same values
+//   gr : this lane's gradient mailbox column (written) -- after the call every lane holds d logp/d theta
+template <bool GRAD>
+__device__ inline float eval_model(const SModel &sm, const float *th, float *gr, int TS, int lane, int G,
+                                   unsigned gmask) {
+  float total = 0.f;
+  if (GRAD)
+    for (int d = 0; d < sm.D; ++d) gr[d * TS] = 0.f;
+
+  for (int t = 0; t < sm.n_terms; ++t) {
+    const b2m_term &T = sm.terms[t];
+    const b2m_operand ox = T.x, o0 = T.p0, o1 = T.p1;
+    const int dist = T.dist, len = T.length;
+    const float k0 = T.k0, k1 = T.k1, k2 = T.k2, w = T.weight;
+    float acc = 0.f, ax = 0.f, a0 = 0.f, a1 = 0.f;
+
+    const bool params_fixed = !op_varies(o0) && !op_varies(o1);
+    if (params_fixed && ox.kind == B2M_OP_DATA && dist == B2M_NORMAL) {
+      // Hot pattern (C1 likelihood): Normal(mu, sigma) over an observation vector.
+      const float mu = op_fetch(o0, 0, th, TS, sm), sg = op_fetch(o1, 0, th, TS, sm);
+      const float inv_var = 1.0f / (sg * sg), base = -kHalfLog2Pi - logf(sg);
+      const float *y = sm.arrays[ox.a].ptr;
+      float s1 = 0.f, s2 = 0.f;
+      int cnt = 0;
+      for (int n = lane; n < len; n += G) {
+        float z = y[n] - mu;
+        s1 += z;
+        s2 = fmaf(z, z, s2);
+        ++cnt;
+      }
+      acc = cnt * base - 0.5f * s2 * inv_var;
+      a0 = s1 * inv_var;
+      a1 = (s2 * inv_var - (float)cnt) / sg;
+    } else if (params_fixed && ox.kind == B2M_OP_DATA && dist == B2M_EXPONENTIAL) {
+      // Hot pattern (C2 likelihood): Exponential(rate) over an observation vector.
+      const float rate = op_fetch(o0, 0, th, TS, sm);
+      const float lr = logf(rate), ir = 1.0f / rate;
+      const float *y = sm.arrays[ox.a].ptr;
+      float s1 = 0.f;
+      int cnt = 0;
+      bool bad = false;
+      for (int n = lane; n < len; n += G) {
+        float v = y[n];
+        bad |= !(v >= 0.f);
+        s1 += v;
+        ++cnt;
+      }
+      acc = bad ? -INFINITY : cnt * lr - rate * s1;
+      a0 = bad ? 0.f : cnt * ir - s1;  // any out-of-support datum: -inf value; its own cotangent is 0
+      if (bad) {                        // exact masked gradient needs the per-element path
+        a0 = 0.f;
+        for (int n = lane; n < len; n += G) {
+          float v = y[n];
+          if (v >= 0.f) a0 += ir - v;
+        }
+      }
+    } else {
+      for (int n = lane; n < len; n += G) {
+        const float x = op_fetch(ox, n, th, TS, sm);
+        const float p0 = op_fetch(o0, n, th, TS, sm);
+        const float p1 = op_fetch(o1, n, th, TS, sm);
+        Elem e = dist_eval<GRAD>(dist, x, p0, p1, k0, k1, k2);
+        acc += e.lp;
+        if (GRAD) {
+          if (ox.kind == B2M_OP_PARAM) ax += e.dx; else op_scatter(ox, n, w * e.dx, gr, TS, sm);
+          if (o0.kind == B2M_OP_PARAM) a0 += e.d0; else op_scatter(o0, n, w * e.d0, gr, TS, sm);
+          if (o1.kind == B2M_OP_PARAM) a1 += e.d1; else op_scatter(o1, n, w * e.d1, gr, TS, sm);
+        }
+      }
+    }
+    total += w * acc;
+    if (GRAD) {
+      if (ox.kind == B2M_OP_PARAM) gr[ox.a * TS] += w * ax;
+      if (o0.kind == B2M_OP_PARAM) gr[o0.a * TS] += w * a0;
+      if (o1.kind == B2M_OP_PARAM) gr[o1.a * TS] += w * a1;
+    }
+  }
+
+  // combine the G lanes of the chain; gmask names exactly those lanes, so chains sharing a warp may
+  // diverge from each other (NUTS tree depth) without breaking the shuffles
+  for (int o = G >> 1; o > 0; o >>= 1) total += __shfl_xor_sync(gmask, total, o);
+  if (GRAD && G > 1) {
+    for (int d = 0; d < sm.D; ++d) {
+      float v = gr[d * TS];
+      for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+      gr[d * TS] = v;
+    }
+  }
+  return total;
+}
+
+}  // namespace b2m

@@ -1,0 +1,251 @@
+// Pointwise-class kernels: many independent chains in lock-step inside persistent kernels.
+// One launch covers `n_iter` whole iterations (an HMC trajectory of L leapfrog steps + accept +
+// step-size adaptation; a Metropolis step; a NUTS transition) for every local chain.
+//
+// Mapping: a chain is served by G lanes (G = 1 for >= 32K chains: thread per chain, observations
+// broadcast from shared memory; G up to 32 for few chains x many observations: lanes stride the
+// observation vector and combine with xor shuffles).  Chain state (q, p, grad) lives in registers
+// (template DMAX); a shared-memory mailbox per lane carries theta / grad through the term loop.
+#include "pointwise.cuh"
+
+namespace b2m {
+
+// ---------------------------------------------------------------- K1: log p and gradient
+template <int DMAX>
+__global__ void __launch_bounds__(128) logp_grad_kernel(KModel km, const float *__restrict__ theta, int64_t C,
+                                                         float *__restrict__ logp, float *__restrict__ grad, int G) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SModel sm;
+  unsigned char *mail = model_to_smem(km, smem, sm);
+  Lane L = make_lane(C, G, mail, DMAX);
+  const int D = sm.D;
+  float q[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) q[d] = (d < D) ? theta[L.chain * D + d] : 0.f;
+  to_mailbox<DMAX>(q, L.th, L.TS, D);
+  float lp;
+  if (grad)
+    lp = eval_model<true>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
+  else
+    lp = eval_model<false>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
+  if (L.writer) {
+    logp[L.chain] = lp;
+    if (grad)
+      for (int d = 0; d < D; ++d) grad[L.chain * D + d] = L.gr[d * L.TS];
+  }
+}
+
+// ---------------------------------------------------------------- K2: HMC
+// hmc_step (hmc.py:113-153): momentum ~ N(0,I); H_init; L x leapfrog_step (:69-100, two half kicks,
+// separate multiply and add as MLX evaluates them); H_prop; accept iff log U < -(H_prop - H_init).
+// The gradient at the trajectory start is the cached gradient of the current state (the reference
+// recomputes it: same number).  Warm-up rule (:164-170): for i > 10, eps *= 0.95 if the cumulative
+// acceptance rate is below target else 1.05, per chain, in float64 like the python float it replaces.
+template <int DMAX>
+__global__ void __launch_bounds__(128) hmc_kernel(KModel km, b2m_hmc_args A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SModel sm;
+  unsigned char *mail = model_to_smem(km, smem, sm);
+  const int G = A.lanes;
+  Lane L = make_lane(A.n_chains, G, mail, DMAX);
+  const int D = sm.D;
+  const int64_t C = A.n_chains, c = L.chain;
+  const uint64_t gchain = (uint64_t)(A.chain_offset + c);
+
+  float q[DMAX], g[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) q[d] = (d < D) ? A.theta[c * D + d] : 0.f;
+  double eps = A.step_size[c];
+  int64_t n_acc = A.n_accept[c], n_tot = A.n_total[c];
+  double h_bar = 0.0, log_eps_bar = 0.0, da_mu = 0.0;
+  if (A.adapt == B2M_ADAPT_DUAL_AVERAGING) {
+    h_bar = A.da_state[c * 3 + 0];
+    log_eps_bar = A.da_state[c * 3 + 1];
+    da_mu = A.da_state[c * 3 + 2];
+  }
+
+  to_mailbox<DMAX>(q, L.th, L.TS, D);
+  float lp = eval_model<true>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
+  from_mailbox<DMAX>(g, L.gr, L.TS, D);
+
+  for (int it = 0; it < A.n_iter; ++it) {
+    const uint32_t giter = (uint32_t)(A.iter_offset + it);
+    const size_t row = (size_t)it * C + c;
+    uint4 w0 = make_uint4(0, 0, 0, 0);
+    if (!A.inj_normal || !A.inj_uniform) w0 = Philox::draw(A.seed, gchain, giter, 0u);
+
+    float p[DMAX];
+    draw_normals<DMAX>(p, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0);
+    const float h_init = __fadd_rn(-lp, kinetic<DMAX>(p, D));
+
+    float qn[DMAX], gn[DMAX];
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) { qn[d] = q[d]; gn[d] = g[d]; }
+    float lpn = lp;
+    const float half_eps = (float)(0.5 * eps), feps = (float)eps;
+    for (int l = 0; l < A.n_leapfrog; ++l) {
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) {
+        p[d] = __fadd_rn(p[d], __fmul_rn(half_eps, gn[d]));
+        qn[d] = __fadd_rn(qn[d], __fmul_rn(feps, p[d]));
+      }
+      to_mailbox<DMAX>(qn, L.th, L.TS, D);
+      lpn = eval_model<true>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
+      from_mailbox<DMAX>(gn, L.gr, L.TS, D);
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) p[d] = __fadd_rn(p[d], __fmul_rn(half_eps, gn[d]));
+    }
+    const float h_prop = __fadd_rn(-lpn, kinetic<DMAX>(p, D));
+    const float u = A.inj_uniform ? A.inj_uniform[row] : u01(w0.z);
+    const float log_ratio = -(__fsub_rn(h_prop, h_init));
+    const bool accept = logf(u) < log_ratio;  // NaN => false => reject
+    if (accept) {
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) { q[d] = qn[d]; g[d] = gn[d]; }
+      lp = lpn;
+      ++n_acc;
+    }
+    ++n_tot;
+
+    if (A.adapt == B2M_ADAPT_REFERENCE) {
+      if ((int64_t)giter > 10) eps *= ((double)n_acc / (double)n_tot < A.target_accept) ? 0.95 : 1.05;
+    } else if (A.adapt == B2M_ADAPT_DUAL_AVERAGING) {
+      // Hoffman & Gelman Alg. 5 recurrences with the constants the reference uses in nuts.py:62-68
+      float a = expf(fminf(log_ratio, 0.f));
+      if (!(a == a)) a = 0.f;
+      const double m = (double)giter + 1.0, eta = 1.0 / (m + 10.0);
+      h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - (double)a);
+      double log_eps = da_mu - sqrt(m) / 0.05 * h_bar;
+      log_eps = fmin(fmax(log_eps, -10.0), 10.0);
+      const double wt = pow(m, -0.75);
+      log_eps_bar = wt * log_eps + (1.0 - wt) * log_eps_bar;
+      eps = exp(log_eps);
+    }
+
+    if (L.writer) {
+      if (A.draws)
+        store_vec<DMAX>(A.draws + row * D, q, D);
+      if (A.trace_energy) { A.trace_energy[row * 2] = h_init; A.trace_energy[row * 2 + 1] = h_prop; }
+      if (A.trace_accept) A.trace_accept[row] = accept ? 1 : 0;
+    }
+  }
+
+  if (L.writer) {
+    store_vec<DMAX>(A.theta + c * D, q, D);
+    A.step_size[c] = eps;
+    A.n_accept[c] = n_acc;
+    A.n_total[c] = n_tot;
+    if (A.adapt == B2M_ADAPT_DUAL_AVERAGING) {
+      A.da_state[c * 3 + 0] = h_bar;
+      A.da_state[c * 3 + 1] = log_eps_bar;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- K3: random-walk Metropolis
+// metropolis.py:64-92: theta' = theta + scale * N(0,I) (multiply, then add); accept iff
+// log U < lp' - lp with the current log-prob cached; NaN => reject.
+template <int DMAX>
+__global__ void __launch_bounds__(128) mh_kernel(KModel km, b2m_mh_args A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SModel sm;
+  unsigned char *mail = model_to_smem(km, smem, sm);
+  const int G = A.lanes;
+  Lane L = make_lane(A.n_chains, G, mail, DMAX);
+  const int D = sm.D;
+  const int64_t C = A.n_chains, c = L.chain;
+  const uint64_t gchain = (uint64_t)(A.chain_offset + c);
+
+  float q[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) q[d] = (d < D) ? A.theta[c * D + d] : 0.f;
+  float lp = A.logp[c];
+  if (lp != lp) {
+    to_mailbox<DMAX>(q, L.th, L.TS, D);
+    lp = eval_model<false>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
+  }
+  int64_t n_acc = A.n_accept[c];
+
+  for (int it = 0; it < A.n_iter; ++it) {
+    const uint32_t giter = (uint32_t)(A.iter_offset + it);
+    const size_t row = (size_t)it * C + c;
+    uint4 w0 = make_uint4(0, 0, 0, 0);
+    if (!A.inj_normal || !A.inj_uniform) w0 = Philox::draw(A.seed, gchain, giter, 0u);
+    float z[DMAX], qn[DMAX];
+    draw_normals<DMAX>(z, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0);
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) qn[d] = __fadd_rn(q[d], __fmul_rn(z[d], A.proposal_scale));
+    to_mailbox<DMAX>(qn, L.th, L.TS, D);
+    const float lpn = eval_model<false>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
+    const float u = A.inj_uniform ? A.inj_uniform[row] : u01(w0.z);
+    const bool accept = logf(u) < __fsub_rn(lpn, lp);
+    if (accept) {
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) q[d] = qn[d];
+      lp = lpn;
+      ++n_acc;
+    }
+    if (L.writer) {
+      if (A.draws)
+        store_vec<DMAX>(A.draws + row * D, q, D);
+      if (A.trace_accept) A.trace_accept[row] = accept ? 1 : 0;
+    }
+  }
+  if (L.writer) {
+    store_vec<DMAX>(A.theta + c * D, q, D);
+    A.logp[c] = lp;
+    A.n_accept[c] = n_acc;
+  }
+}
+
+// ---------------------------------------------------------------- host-side launchers
+int pick_lanes(const KModel &km, int64_t n_chains, int requested) {
+  if (requested > 0) return requested;
+  if (n_chains >= 32768) return 1;
+  int g = 1;
+  // enough lanes to put ~64K threads in flight, never more lanes than the longest term has elements
+  while (g < 32 && (int64_t)n_chains * g < 65536 && g * 2 <= km.max_len) g <<= 1;
+  return g;
+}
+
+int launch_logp_grad(const KModel &km, const float *theta, int64_t C, float *logp, float *grad, int lanes,
+                     cudaStream_t st) {
+  const int dmax = pick_dmax(km.D);
+  const int G = pick_lanes(km, C, lanes);
+  Geometry ge = geometry(km, C, G, dmax ? dmax : 2);
+  B2M_DISPATCH_DMAX(dmax, {
+    if (int rc = prep(logp_grad_kernel<DM>, ge.smem)) return rc;
+    logp_grad_kernel<DM><<<ge.grid, ge.block, ge.smem, st>>>(km, theta, C, logp, grad, G);
+  });
+  ++g_launches;
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_hmc(const KModel &km, b2m_hmc_args a, cudaStream_t st) {
+  const int dmax = pick_dmax(km.D);
+  a.lanes = pick_lanes(km, a.n_chains, a.lanes);
+  Geometry ge = geometry(km, a.n_chains, a.lanes, dmax ? dmax : 2);
+  B2M_DISPATCH_DMAX(dmax, {
+    if (int rc = prep(hmc_kernel<DM>, ge.smem)) return rc;
+    hmc_kernel<DM><<<ge.grid, ge.block, ge.smem, st>>>(km, a);
+  });
+  ++g_launches;
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_mh(const KModel &km, b2m_mh_args a, cudaStream_t st) {
+  const int dmax = pick_dmax(km.D);
+  a.lanes = pick_lanes(km, a.n_chains, a.lanes);
+  Geometry ge = geometry(km, a.n_chains, a.lanes, dmax ? dmax : 2);
+  B2M_DISPATCH_DMAX(dmax, {
+    if (int rc = prep(mh_kernel<DM>, ge.smem)) return rc;
+    mh_kernel<DM><<<ge.grid, ge.block, ge.smem, st>>>(km, a);
+  });
+  ++g_launches;
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b2m

@@ -1,0 +1,134 @@
+// Helpers shared by the pointwise-class kernels (pointwise.cu, nuts_pointwise.cu).
+#pragma once
+#include <math.h>
+
+#include "model.cuh"
+
+namespace b2m {
+
+// ---------------------------------------------------------------- small helpers
+template <int DMAX>
+struct Vec {
+  float v[DMAX];
+};
+
+template <int DMAX>
+__device__ __forceinline__ void to_mailbox(const float (&q)[DMAX], float *th, int TS, int D) {
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d)
+    if (d < D) th[d * TS] = q[d];
+}
+template <int DMAX>
+__device__ __forceinline__ void from_mailbox(float (&g)[DMAX], const float *gr, int TS, int D) {
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) g[d] = (d < D) ? gr[d * TS] : 0.f;
+}
+
+template <int DMAX>
+__device__ __forceinline__ void store_vec(float *dst, const float (&q)[DMAX], int D) {
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d)
+    if (d < D) dst[d] = q[d];
+}
+
+// kinetic energy exactly as the reference sums it: 0.5 * (p_0^2 + p_1^2 + ...) left to right
+// (hmc.py:110, nuts.py:116)
+template <int DMAX>
+__device__ __forceinline__ float kinetic(const float (&p)[DMAX], int D) {
+  float s = 0.f;
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d)
+    if (d < D) s = __fadd_rn(s, __fmul_rn(p[d], p[d]));
+  return __fmul_rn(0.5f, s);
+}
+
+// momentum / proposal normals for one (chain, iteration): injected or Philox (slot map in common.cuh)
+template <int DMAX>
+__device__ __forceinline__ void draw_normals(float (&z)[DMAX], int D, const float *inj, uint64_t seed,
+                                             uint64_t gchain, uint32_t giter, uint4 first) {
+  if (inj) {
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) z[d] = (d < D) ? inj[d] : 0.f;
+    return;
+  }
+  float a, b;
+  box_muller(first.x, first.y, a, b);
+  z[0] = a;
+  if (DMAX > 1) z[1] = b;
+#pragma unroll
+  for (int k = 0; k < (DMAX + 1) / 4; ++k) {
+    if (2 + 4 * k < D) {
+      uint4 w = Philox::draw(seed, gchain, giter, 1u + k);
+      float n0, n1, n2, n3;
+      box_muller(w.x, w.y, n0, n1);
+      box_muller(w.z, w.w, n2, n3);
+      if (2 + 4 * k + 0 < DMAX) z[2 + 4 * k + 0] = n0;
+      if (2 + 4 * k + 1 < DMAX) z[2 + 4 * k + 1] = n1;
+      if (2 + 4 * k + 2 < DMAX) z[2 + 4 * k + 2] = n2;
+      if (2 + 4 * k + 3 < DMAX) z[2 + 4 * k + 3] = n3;
+    }
+  }
+}
+
+struct Lane {
+  int64_t chain;   // clamped local chain index
+  bool writer;     // lane 0 of an in-range chain
+  int lane, G, TS;
+  unsigned gmask;  // warp lanes serving this chain
+  float *th, *gr;  // mailbox columns
+};
+
+__device__ __forceinline__ Lane make_lane(int64_t n_chains, int G, unsigned char *mail, int dmax) {
+  Lane L;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c = t / G;
+  L.lane = int(t % G);
+  L.G = G;
+  L.TS = blockDim.x;
+  L.gmask = G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  L.writer = (c < n_chains) && (L.lane == 0);
+  L.chain = c < n_chains ? c : n_chains - 1;
+  float *m = reinterpret_cast<float *>(mail);
+  L.th = m + threadIdx.x;
+  L.gr = m + (size_t)dmax * blockDim.x + threadIdx.x;
+  return L;
+}
+
+// ---------------------------------------------------------------- host-side launchers
+inline int pick_dmax(int D) { return D <= 2 ? 2 : D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 0; }
+
+int pick_lanes(const KModel &km, int64_t n_chains, int requested);
+
+struct Geometry {
+  dim3 grid, block;
+  size_t smem;
+};
+
+inline Geometry geometry(const KModel &km, int64_t n_chains, int G, int dmax) {
+  Geometry ge;
+  int threads = 64;
+  if (threads < G) threads = G;
+  const int64_t total = n_chains * G;
+  ge.block = dim3(threads);
+  ge.grid = dim3((unsigned)((total + threads - 1) / threads));
+  ge.smem = model_smem_bytes(km) + sizeof(float) * 2 * (size_t)dmax * threads;
+  return ge;
+}
+
+template <typename K>
+static int prep(K kernel, size_t smem) {
+  if (smem > 48 * 1024) B2M_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
+#define B2M_DISPATCH_DMAX(dmax, ...)                       \
+  switch (dmax) {                                           \
+    case 2: { constexpr int DM = 2; __VA_ARGS__; } break;          \
+    case 4: { constexpr int DM = 4; __VA_ARGS__; } break;          \
+    case 8: { constexpr int DM = 8; __VA_ARGS__; } break;          \
+    case 16: { constexpr int DM = 16; __VA_ARGS__; } break;        \
+    default: b2m::set_error("pointwise models support at most 16 scalar parameters"); return 1; \
+  }
+
+
+}  // namespace b2m

@@ -1,0 +1,206 @@
+"""Host-side engine: device model handle + thin launch wrappers around the C ABI.
+
+torch is used for device memory, streams and (in dist.py) torch.distributed -- plumbing only.  Every
+number on the sampling path is produced by the kernels in csrc/ through libb200mcmc.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .tracer import OP_LIN, TracedModel, trace
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("mlx_mcmc_b200: no CUDA device visible -- the sampling path runs only on the GPU "
+                           "(there is deliberately no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DeviceModel:
+    """A traced model resident on one GPU (observed arrays in HBM, term table inside the C handle)."""
+
+    def __init__(self, traced: TracedModel, device: Optional[torch.device] = None):
+        self.lib = _cabi.load()
+        self.device = device or _require_cuda()
+        self.traced = traced
+        self.D = traced.D
+        self.layout = traced.layout
+        # observed arrays: uploaded once, kept alive by this object (the library never owns them)
+        self._arrays = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device) for a in traced.arrays]
+        n_t, n_a, n_l = len(traced.terms), len(traced.arrays), len(traced.lin)
+        terms = (_cabi.Term * n_t)()
+        for i, t in enumerate(traced.terms):
+            terms[i].dist, terms[i].length, terms[i].weight = t.dist, t.length, t.weight
+            terms[i].k0, terms[i].k1, terms[i].k2 = t.k
+            for slot, o in (("x", t.x), ("p0", t.p0), ("p1", t.p1)):
+                dst = getattr(terms[i], slot)
+                dst.kind, dst.a, dst.b, dst.c = o.kind, o.a, o.b, o.c
+        lin = (_cabi.LinEntry * max(n_l, 1))()
+        for i, (p, a, c) in enumerate(traced.lin):
+            lin[i].param, lin[i].array, lin[i].coef = p, a, c
+        arrays = (_cabi.Array * max(n_a, 1))()
+        for i, a in enumerate(self._arrays):
+            arrays[i].data = a.data_ptr()
+            arrays[i].rows = a.shape[0]
+            arrays[i].cols = a.shape[1] if a.dim() == 2 else 1
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b2m_model_create(terms, n_t, lin, n_l, arrays, n_a, self.D, C.byref(handle)))
+        self.handle = handle
+        self.model_class = self.lib.b2m_model_class(handle)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                self.lib.b2m_model_destroy(h)
+            except Exception:
+                pass
+
+    # -- parameter packing ----------------------------------------------------------------
+    def pack(self, params: Dict[str, object], n_chains: int) -> torch.Tensor:
+        """dict of initial values -> theta [n_chains, D] float32 on the device.  A value with a leading
+        axis of length n_chains gives per-chain starting points; otherwise every chain starts at it."""
+        flat = np.zeros((n_chains, self.D), dtype=np.float32)
+        for name, (off, n, shp) in self.layout.items():
+            v = np.asarray(params[name], dtype=np.float32)
+            if v.shape == tuple(shp):
+                flat[:, off:off + n] = v.reshape(1, n)
+            elif v.shape == (n_chains,) + tuple(shp):
+                flat[:, off:off + n] = v.reshape(n_chains, n)
+            else:
+                raise ValueError(f"initial value of {name!r} has shape {v.shape}, expected {shp} or ({n_chains},)+{shp}")
+        return torch.from_numpy(flat).to(self.device)
+
+    def unpack(self, draws: torch.Tensor, squeeze_chain: bool, to_numpy: bool = True):
+        """draws [S, C, D] -> {name: (S,) | (S, n) | (C, S) | (C, S, n)} in the reference's shapes."""
+        out = {}
+        host = None
+        if to_numpy:
+            pinned = torch.empty(draws.shape, dtype=draws.dtype, pin_memory=True)
+            pinned.copy_(draws, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            host = pinned.numpy()
+        for name, (off, n, shp) in self.layout.items():
+            src = host if to_numpy else draws
+            part = src[:, :, off:off + n]
+            part = part.transpose(1, 0, 2) if to_numpy else part.permute(1, 0, 2)
+            if not shp:
+                part = part[:, :, 0]
+            if squeeze_chain:
+                part = part[0]
+            out[name] = np.ascontiguousarray(part) if to_numpy else part
+        return out
+
+    # -- K1 -------------------------------------------------------------------------------
+    def logp_grad(self, theta: torch.Tensor, want_grad: bool = True, lanes: int = 0):
+        """log p and gradient for theta [C, D] (device float32).  Parity-check-1 entry point."""
+        assert theta.is_cuda and theta.dtype == torch.float32 and theta.dim() == 2 and theta.shape[1] == self.D
+        theta = theta.contiguous()
+        Cn = theta.shape[0]
+        logp = torch.empty(Cn, dtype=torch.float32, device=self.device)
+        grad = torch.empty(Cn, self.D, dtype=torch.float32, device=self.device) if want_grad else None
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b2m_logp_grad(self.handle, _ptr(theta), Cn, _ptr(logp), _ptr(grad), lanes, _stream()))
+        return logp, grad
+
+
+class ChainState:
+    """Per-chain sampler state in HBM (positions, step sizes, counters)."""
+
+    def __init__(self, model: DeviceModel, theta: torch.Tensor, step_size: float, chain_offset: int = 0):
+        dev = model.device
+        self.model = model
+        self.n_chains = theta.shape[0]
+        self.chain_offset = int(chain_offset)
+        self.theta = theta.contiguous()
+        self.step_size = torch.full((self.n_chains,), float(step_size), dtype=torch.float64, device=dev)
+        self.n_accept = torch.zeros(self.n_chains, dtype=torch.int64, device=dev)
+        self.n_total = torch.zeros(self.n_chains, dtype=torch.int64, device=dev)
+        self.n_leaves = torch.zeros(self.n_chains, dtype=torch.int64, device=dev)
+        self.n_diverge = torch.zeros(self.n_chains, dtype=torch.int64, device=dev)
+        self.da_state = torch.zeros(self.n_chains, 3, dtype=torch.float64, device=dev)
+        self.logp = torch.full((self.n_chains,), float("nan"), dtype=torch.float32, device=dev)
+
+    def reset_counters(self):
+        self.n_accept.zero_()
+        self.n_total.zero_()
+
+
+def launch_hmc(st: ChainState, n_iter: int, n_leapfrog: int, adapt: int, target_accept: float, seed: int,
+               iter_offset: int, draws: Optional[torch.Tensor] = None, lanes: int = 0, inj_normal=None,
+               inj_uniform=None, trace_energy=None, trace_accept=None):
+    m = st.model
+    a = _cabi.HmcArgs()
+    a.n_chains, a.chain_offset, a.iter_offset = st.n_chains, st.chain_offset, iter_offset
+    a.n_iter, a.n_leapfrog, a.adapt, a.lanes = n_iter, n_leapfrog, adapt, lanes
+    a.target_accept, a.seed = target_accept, seed & 0xFFFFFFFFFFFFFFFF
+    a.theta, a.step_size, a.n_accept, a.n_total = _ptr(st.theta), _ptr(st.step_size), _ptr(st.n_accept), _ptr(st.n_total)
+    a.da_state, a.draws = _ptr(st.da_state), _ptr(draws)
+    a.inj_normal, a.inj_uniform = _ptr(inj_normal), _ptr(inj_uniform)
+    a.trace_energy, a.trace_accept = _ptr(trace_energy), _ptr(trace_accept)
+    with torch.cuda.device(m.device):
+        _cabi.check(m.lib.b2m_hmc_run(m.handle, C.byref(a), _stream()))
+
+
+def launch_mh(st: ChainState, n_iter: int, proposal_scale: float, seed: int, iter_offset: int,
+              draws: Optional[torch.Tensor] = None, lanes: int = 0, inj_normal=None, inj_uniform=None,
+              trace_accept=None):
+    m = st.model
+    a = _cabi.MhArgs()
+    a.n_chains, a.chain_offset, a.iter_offset = st.n_chains, st.chain_offset, iter_offset
+    a.n_iter, a.lanes, a.proposal_scale, a.seed = n_iter, lanes, proposal_scale, seed & 0xFFFFFFFFFFFFFFFF
+    a.theta, a.logp, a.n_accept, a.draws = _ptr(st.theta), _ptr(st.logp), _ptr(st.n_accept), _ptr(draws)
+    a.inj_normal, a.inj_uniform, a.trace_accept = _ptr(inj_normal), _ptr(inj_uniform), _ptr(trace_accept)
+    with torch.cuda.device(m.device):
+        _cabi.check(m.lib.b2m_mh_run(m.handle, C.byref(a), _stream()))
+
+
+def launch_nuts(st: ChainState, n_iter: int, max_tree_depth: int, adapt: int, compat: int, target_accept: float,
+                seed: int, iter_offset: int, draws=None, depths=None, alphas=None, lanes: int = 0, inj=None,
+                trace_doubling=None, trace_energy=None):
+    m = st.model
+    inj = inj or {}
+    a = _cabi.NutsArgs()
+    a.n_chains, a.chain_offset, a.iter_offset = st.n_chains, st.chain_offset, iter_offset
+    a.n_iter, a.max_tree_depth, a.adapt, a.compat, a.lanes = n_iter, max_tree_depth, adapt, compat, lanes
+    a.target_accept, a.seed = target_accept, seed & 0xFFFFFFFFFFFFFFFF
+    a.theta, a.step_size, a.da_state = _ptr(st.theta), _ptr(st.step_size), _ptr(st.da_state)
+    a.n_accept, a.n_leaves, a.n_diverge = _ptr(st.n_accept), _ptr(st.n_leaves), _ptr(st.n_diverge)
+    a.draws, a.depths, a.alphas = _ptr(draws), _ptr(depths), _ptr(alphas)
+    a.inj_normal, a.inj_slice = _ptr(inj.get("normal")), _ptr(inj.get("slice"))
+    a.inj_dir, a.inj_take, a.inj_merge = _ptr(inj.get("dir")), _ptr(inj.get("take")), _ptr(inj.get("merge"))
+    a.trace_doubling, a.trace_energy = _ptr(trace_doubling), _ptr(trace_energy)
+    with torch.cuda.device(m.device):
+        _cabi.check(m.lib.b2m_nuts_run(m.handle, C.byref(a), _stream()))
+
+
+_MODEL_CACHE: Dict[tuple, DeviceModel] = {}
+
+
+def compile_model(log_prob_fn, initial_params, cache: bool = True) -> DeviceModel:
+    """Trace `log_prob_fn` once and build its device model.  Cached per (function object, parameter
+    shapes, device) so repeated run() calls do not re-trace or re-upload the observations."""
+    dev = _require_cuda()
+    key = (id(log_prob_fn), tuple((k, np.asarray(v).shape) for k, v in initial_params.items()), dev.index)
+    if cache and key in _MODEL_CACHE and _MODEL_CACHE[key]._fn is log_prob_fn:
+        return _MODEL_CACHE[key]
+    model = DeviceModel(trace(log_prob_fn, initial_params), dev)
+    model._fn = log_prob_fn
+    if cache:
+        _MODEL_CACHE[key] = model
+    return model

@@ -1,0 +1,107 @@
+"""High-level MCMC interface with the reference's call convention (mlx_mcmc/inference/mcmc.py:10-246)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import core as mx
+from ..kernels.hmc import hmc
+from ..kernels.metropolis import metropolis_hastings
+from ..kernels.nuts import nuts
+
+_RULE = "=" * 70
+
+
+class MCMC:
+    """``MCMC(log_prob_fn).run(initial_params, ...)`` -> dict of numpy draws; ``self.samples`` and
+    ``self.acceptance_rate`` are set as in the reference (mcmc.py:33-36,99-100,187).
+
+    ``log_prob_fn(params)`` is traced once per ``run`` configuration into a term table and executed by
+    the CUDA kernels; it must be written against ``mlx_mcmc_b200.core`` (as ``mx``) and the library
+    distributions.  Unsupported operations raise ``UnsupportedOpError``.
+    """
+
+    def __init__(self, log_prob_fn):
+        self.log_prob_fn = log_prob_fn
+        self.samples = None
+        self.acceptance_rate = None
+        self.info = None
+
+    def run(self, initial_params, num_samples=1000, num_warmup=1000, method='metropolis', proposal_scale=0.1,
+            random_seed=0, verbose=True, **kwargs):
+        """Same positional/keyword arguments as the reference (mcmc.py:38-48); ``**kwargs`` go to the
+        sampler verbatim (mcmc.py:96,122,156,177), so e.g. ``step_size`` with ``method='metropolis'``
+        raises TypeError exactly as there.  Extra keyword-only sampler options (``num_chains``,
+        ``adapt``, ``compat``, ``return_torch`` ...) ride in ``kwargs`` too."""
+        if method in ('hmc', 'nuts'):
+            if verbose:
+                print(f"\n{_RULE}\nB200-MCMC: {method.upper()} Sampling\n{_RULE}\n")
+            sampler = hmc if method == 'hmc' else nuts
+            out = sampler(self.log_prob_fn, initial_params, num_samples=num_samples, num_warmup=num_warmup,
+                          key=mx.random.key(random_seed), **kwargs)
+            samples, accept_rate = out[0], out[1]
+            self.info = out[2] if len(out) > 2 else None
+            self.samples = samples if kwargs.get("return_torch") else {k: np.array(v) for k, v in samples.items()}
+            self.acceptance_rate = accept_rate
+            if verbose:
+                print(f"Sampling acceptance rate: {accept_rate:.2%}\n{_RULE}\nSampling complete!\n{_RULE}\n")
+            return self.samples
+        elif method == 'metropolis':
+            sampler = metropolis_hastings
+        else:
+            raise ValueError(f"Unknown sampling method: {method}")
+
+        if verbose:
+            print(f"\n{_RULE}\nB200-MCMC: {method.upper()} Sampling\n{_RULE}\n")
+        num_chains = kwargs.get("num_chains", 1)
+        # warm-up is a separate sampler call with `random_seed`; sampling restarts from its last draw
+        # with `random_seed + 1` (mcmc.py:146-178)
+        if num_warmup > 0:
+            wkw = dict(kwargs)
+            wkw.pop("return_info", None)
+            wkw["return_torch"] = False
+            warm, warm_accept = sampler(self.log_prob_fn, initial_params, num_samples=num_warmup,
+                                        proposal_scale=proposal_scale, random_seed=random_seed, verbose=False, **wkw)
+            if verbose:
+                print(f"Warmup phase: {num_warmup} samples, acceptance rate: {warm_accept:.2%}\n")
+            start = {k: (v[-1] if num_chains == 1 else v[:, -1]) for k, v in warm.items()}
+        else:
+            start = initial_params
+        out = sampler(self.log_prob_fn, start, num_samples=num_samples, proposal_scale=proposal_scale,
+                      random_seed=random_seed + 1 if num_warmup > 0 else random_seed, verbose=False, **kwargs)
+        self.samples, self.acceptance_rate = out[0], out[1]
+        self.info = out[2] if len(out) > 2 else None
+        if verbose:
+            print(f"Sampling phase: {num_samples} samples\nSampling acceptance rate: {self.acceptance_rate:.2%}")
+            print(f"\n{_RULE}\nSampling complete!\n{_RULE}\n")
+        if not kwargs.get("return_torch"):
+            self.samples = {k: np.array(v) for k, v in self.samples.items()}
+        return self.samples
+
+    def summary(self, credible_interval=0.95):
+        """mean / std / median / lower / upper percentile per parameter, keys as in mcmc.py:219-225.
+        Multi-chain draws are pooled over chains."""
+        if self.samples is None:
+            raise ValueError("Must run sampling first. Call run() method.")
+        alpha = 1 - credible_interval
+        lo, hi = 100 * alpha / 2, 100 * (1 - alpha / 2)
+        table = {}
+        for name, draws in self.samples.items():
+            x = np.asarray(draws.detach().cpu() if hasattr(draws, "detach") else draws)
+            table[name] = {
+                'mean': float(np.mean(x)), 'std': float(np.std(x)), 'median': float(np.median(x)),
+                f'{lo:.1f}%': float(np.percentile(x, lo)), f'{hi:.1f}%': float(np.percentile(x, hi)),
+            }
+        return table
+
+    def print_summary(self, credible_interval=0.95):
+        table = self.summary(credible_interval)
+        ci = f"{int(credible_interval * 100)}% CI"
+        print("\nPosterior Summary:")
+        print("=" * 80)
+        print(f"{'Parameter':<15} {'Mean':<10} {'Std':<10} {'Median':<10} {ci:<20}")
+        print("-" * 80)
+        for name, row in table.items():
+            vals = list(row.values())
+            span = f"[{vals[3]:.3f}, {vals[4]:.3f}]"
+            print(f"{name:<15} {row['mean']:<10.3f} {row['std']:<10.3f} {row['median']:<10.3f} {span:<20}")
+        print("=" * 80)

@@ -1,0 +1,72 @@
+"""No-U-Turn sampler front-end with the reference's signature (mlx_mcmc/kernels/nuts.py:16-26)."""
+from __future__ import annotations
+
+from typing import Callable, Dict, Tuple
+
+import numpy as np
+import torch
+
+from .. import _cabi
+from ..engine import launch_nuts
+from ._common import SamplerInfo, alloc_draws, philox_seed, prepare
+
+
+def nuts(
+    log_prob_fn: Callable,
+    initial_params: Dict[str, object],
+    num_samples: int = 1000,
+    num_warmup: int = 1000,
+    step_size: float = 0.1,
+    max_tree_depth: int = 10,
+    adapt_step_size: bool = True,
+    target_accept: float = 0.65,
+    key=None,
+    *,
+    num_chains: int = 1,
+    compat: str = "reference",
+    chain_offset: int = 0,
+    lanes: int = 0,
+    return_torch: bool = False,
+    return_info: bool = False,
+    model=None,
+) -> Tuple[Dict[str, object], float]:
+    """Same arguments and return value as the reference's ``nuts``: ``(samples, rate)`` where rate is the
+    fraction of sampling iterations whose mean acceptance statistic exceeded 0.5 (nuts.py:341,353) and
+    vector parameters come back as ``(num_samples, D)`` (nuts.py:338-339).
+
+    ``compat='reference'`` reproduces the reference's float32 slice round trip and NaN handling
+    (SURVEY.md F6/F7); ``compat='correct'`` keeps the slice in log space (see csrc/nuts_pointwise.cu).
+    Dual averaging follows nuts.py:62-68,298-310 per chain on device; after warm-up every chain
+    switches to its averaged step size (nuts.py:317-320)."""
+    if num_warmup == 0:
+        raise ZeroDivisionError("division by zero")   # nuts.py:322-323
+    if compat not in ("reference", "correct"):
+        raise ValueError(f"Unknown compat mode: {compat}")
+    if not 1 <= max_tree_depth <= _cabi.MAX_TREE_DEPTH:
+        raise ValueError(f"max_tree_depth must be in 1..{_cabi.MAX_TREE_DEPTH}")
+    cmode = _cabi.COMPAT_REFERENCE if compat == "reference" else _cabi.COMPAT_CORRECT
+    seed = philox_seed(key, 0)
+    model, st = prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, model)
+    st.da_state[:, 0] = 0.0                                           # H_bar
+    st.da_state[:, 1] = 1.0                                           # eps_bar
+    st.da_state[:, 2] = float(np.log(np.float32(10.0 * step_size)))   # mu, a float32 in the reference
+    amode = _cabi.ADAPT_DUAL_AVERAGING if adapt_step_size else _cabi.ADAPT_NONE
+    warm_depths = torch.empty((num_warmup, num_chains), dtype=torch.int32, device=model.device) if return_info else None
+    launch_nuts(st, num_warmup, max_tree_depth, amode, cmode, target_accept, seed, 0, depths=warm_depths, lanes=lanes)
+    if adapt_step_size:
+        st.step_size.copy_(st.da_state[:, 1])
+    warm_leaves = st.n_leaves.clone()
+    st.n_accept.zero_()
+    draws = alloc_draws(model, num_samples, num_chains)
+    depths = torch.empty((num_samples, num_chains), dtype=torch.int32, device=model.device)
+    launch_nuts(st, num_samples, max_tree_depth, _cabi.ADAPT_NONE, cmode, target_accept, seed, num_warmup,
+                draws=draws, depths=depths, lanes=lanes)
+    rate = float(st.n_accept.double().sum().item() / max(num_samples * num_chains, 1))
+    samples = model.unpack(draws, squeeze_chain=(num_chains == 1), to_numpy=not return_torch)
+    if return_info:
+        info = SamplerInfo(step_size=st.step_size.cpu().numpy(), depths=depths.cpu().numpy(),
+                           warmup_depths=warm_depths.cpu().numpy(), n_diverge=st.n_diverge.cpu().numpy(),
+                           grad_evals=int(st.n_leaves.sum().item()), warmup_grad_evals=int(warm_leaves.sum().item()),
+                           state=st, model=model)
+        return samples, rate, info
+    return samples, rate

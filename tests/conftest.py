@@ -1,0 +1,20 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def cuda():
+    """GPU tests call the product path, which has no CPU fallback: without a device they must fail, not skip."""
+    import torch
+    assert torch.cuda.is_available(), "GPU test selected but no CUDA device is visible"
+    return torch.device("cuda", 0)

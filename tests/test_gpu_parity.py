@@ -1,0 +1,219 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle and the committed golden fixtures.
+
+Parity check 1: log p and gradient within 1e-5 relative (norm-wise) of the float64 arbiter and the
+                reference's float32 values.
+Parity check 2: with the reference's momentum / uniform draws injected, every accept decision and
+                every NUTS tree decision is identical, states agree to float32 rounding.
+"""
+import numpy as np
+import pytest
+import torch
+
+import mlx_mcmc_b200 as B
+from mlx_mcmc_b200 import _cabi, workloads as W
+from mlx_mcmc_b200.engine import ChainState, compile_model, launch_hmc, launch_mh, launch_nuts
+from util import flat_params, golden, rel_err, tape_normals, tape_nuts, tape_uniforms
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # north_star: "log_prob and gradient match within 1e-5 relative in fp32"
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return (t.to(dtype) if dtype else t).cuda()
+
+
+# ------------------------------------------------------------------------------ parity 1
+@pytest.mark.parametrize("lanes", [1, 4, 32])
+def test_logp_grad_vs_golden(cuda, lanes):
+    g = golden("logp_grad")
+    for model_name, rows in g.items():
+        fn, init, _ = W.ALL_SMALL[model_name](B.ns)
+        model = compile_model(fn, init)
+        theta = np.stack([flat_params(model.layout, r["params"]) for r in rows])
+        lp, gr = model.logp_grad(dev(theta), lanes=lanes)
+        lp, gr = lp.cpu().numpy(), gr.cpu().numpy()
+        for i, r in enumerate(rows):
+            g64 = flat_params(model.layout, r["grad64"])
+            g32 = flat_params(model.layout, r["grad32"])
+            if np.isfinite(r["logp64"]):
+                assert abs(lp[i] - r["logp64"]) <= TOL * max(abs(r["logp64"]), 1.0), (model_name, r["params"], lp[i])
+                assert abs(lp[i] - r["logp32"]) <= TOL * max(abs(r["logp32"]), 1.0)
+            elif np.isnan(r["logp64"]):
+                assert np.isnan(lp[i]), (model_name, r["params"])
+            else:
+                assert lp[i] == r["logp64"], (model_name, r["params"], lp[i])       # -inf outside the support
+            assert np.all(np.isfinite(gr[i]) == np.isfinite(g64)), (model_name, r["params"], gr[i], g64)
+            ok = np.isfinite(g64)
+            if ok.any():
+                assert rel_err(gr[i][ok], g64[ok]) <= TOL, (model_name, r["params"], gr[i], g64)
+                assert rel_err(gr[i][ok], g32[ok]) <= TOL
+
+
+def test_logp_grad_random_points_vs_oracle(cuda):
+    """seeded random points, CUDA vs the oracle's float64 evaluation"""
+    from oracle.ns import ns as ons, value_and_grad
+    rng = np.random.default_rng(0)
+    for name in ("c1_normal", "c2_event_rate", "c5_ab_test", "t_vector_normal"):
+        fn, init, _ = W.ALL_SMALL[name](B.ns)
+        fo, _, _ = W.ALL_SMALL[name](ons)
+        model = compile_model(fn, init)
+        pts = []
+        for _ in range(16):
+            p = {}
+            for k, v in init.items():
+                base = np.asarray(v, dtype=np.float64)
+                if name == "c5_ab_test":
+                    p[k] = float(rng.uniform(0.02, 0.6))
+                elif name == "c1_normal":
+                    p[k] = float(rng.uniform(0.5, 8.0))
+                elif name == "c2_event_rate":
+                    p[k] = float(rng.uniform(0.2, 9.0))
+                else:
+                    p[k] = (base + rng.normal(size=base.shape)).tolist()
+            pts.append(p)
+        theta = np.stack([flat_params(model.layout, p) for p in pts])
+        for lanes in (0, 1, 8):
+            lp, gr = model.logp_grad(dev(theta), lanes=lanes)
+            lp, gr = lp.cpu().numpy(), gr.cpu().numpy()
+            for i, p in enumerate(pts):
+                lp64, g64 = value_and_grad(fo, p, "float64")
+                assert abs(lp[i] - lp64) <= TOL * max(abs(lp64), 1.0), (name, p)
+                assert rel_err(gr[i], flat_params(model.layout, g64)) <= TOL, (name, p)
+
+
+def test_known_answers_through_cuda(cuda):
+    """the reference's known-answer log_prob tests, evaluated by the CUDA kernels"""
+    import math
+    cases = [
+        (lambda p: B.Normal(0, 1).log_prob(p["x"]), 0.0, -0.5 * math.log(2 * math.pi)),
+        (lambda p: B.HalfNormal(1).log_prob(p["x"]), 0.0, math.log(2) - 0.5 * math.log(2 * math.pi)),
+        (lambda p: B.HalfNormal(1).log_prob(p["x"]), -1.0, -math.inf),
+        (lambda p: B.Beta(2, 2).log_prob(p["x"]), -0.1, -math.inf),
+        (lambda p: B.Beta(2, 2).log_prob(p["x"]), 1.5, -math.inf),
+        (lambda p: B.Beta(2, 2).log_prob(p["x"]), 0.0, -math.inf),
+        (lambda p: B.Beta(2, 2).log_prob(p["x"]), 1.0, -math.inf),
+        (lambda p: B.Beta(2, 2).log_prob(p["x"]), 0.5, math.log(1.5)),
+        (lambda p: B.Gamma(2, 1).log_prob(p["x"]), -1.0, -math.inf),
+        (lambda p: B.Gamma(2, 1).log_prob(p["x"]), 1.5, math.log(1.5) - 1.5),
+        (lambda p: B.Exponential(2).log_prob(p["x"]), 0.0, math.log(2)),
+        (lambda p: B.Exponential(2).log_prob(p["x"]), -1.0, -math.inf),
+        (lambda p: B.Normal(0, 1).log_prob(p["x"]) + B.Categorical(probs=[0.2, 0.5, 0.3]).log_prob(1), 0.0,
+         -0.5 * math.log(2 * math.pi) + math.log(0.5)),
+    ]
+    for fn, x, want in cases:
+        model = compile_model(fn, {"x": 0.0}, cache=False)
+        lp, gr = model.logp_grad(dev(np.array([[x]], dtype=np.float32)))
+        got = float(lp.cpu()[0])
+        if math.isinf(want):
+            assert got == want and float(gr.cpu()[0, 0]) == 0.0
+        else:
+            assert abs(got - want) < 1e-5, (x, got, want)
+
+
+# ------------------------------------------------------------------------------ parity 2: HMC / MH
+@pytest.mark.parametrize("name", ["hmc_c1", "hmc_c2", "hmc_normal2d", "hmc_halfnormal"])
+@pytest.mark.parametrize("lanes", [1, 8])
+def test_hmc_injected_draws_match_reference(cuda, name, lanes):
+    g = golden(name)
+    kw = g["kwargs"]
+    fn, init, _ = W.ALL_SMALL[g["model"]](B.ns)
+    model = compile_model(fn, init)
+    nw, ns_ = kw["num_warmup"], kw["num_samples"]
+    tape = g["tape"]
+    st = ChainState(model, model.pack(init, 1), kw["step_size"])
+    zs = tape_normals(tape, model.layout, nw + ns_)
+    us = tape_uniforms(tape, "accept", nw + ns_)
+    en = torch.zeros(nw + ns_, 1, 2, device="cuda")
+    ac = torch.zeros(nw + ns_, 1, dtype=torch.uint8, device="cuda")
+    draws = torch.zeros(ns_, 1, model.D, device="cuda")
+    launch_hmc(st, nw, kw["num_leapfrog_steps"], _cabi.ADAPT_REFERENCE, kw["target_accept"], 0, 0, lanes=lanes,
+               inj_normal=dev(zs[:nw]), inj_uniform=dev(us[:nw]), trace_energy=en[:nw], trace_accept=ac[:nw])
+    st.reset_counters()
+    launch_hmc(st, ns_, kw["num_leapfrog_steps"], _cabi.ADAPT_NONE, kw["target_accept"], 0, nw, draws=draws, lanes=lanes,
+               inj_normal=dev(zs[nw:]), inj_uniform=dev(us[nw:]), trace_energy=en[nw:], trace_accept=ac[nw:])
+    torch.cuda.synchronize()
+    ref_accept = np.array([it["accept"] for it in tape["iters"]], dtype=np.uint8)
+    assert np.array_equal(ac.cpu().numpy()[:, 0], ref_accept)                       # every decision identical
+    assert abs(float(st.step_size.cpu()[0]) - g["final_step_size"]) <= 1e-12 * g["final_step_size"]
+    h0 = np.array([it["H0"] for it in tape["iters"]])
+    h1 = np.array([it["H1"] for it in tape["iters"]])
+    e = en.cpu().numpy()[:, 0]
+    fin = np.isfinite(h1)
+    assert rel_err(e[:, 0], h0) < 5e-5 and rel_err(e[fin, 1], h1[fin]) < 5e-5
+    d = draws.cpu().numpy()[:, 0]
+    for pname, (off, n, _) in model.layout.items():
+        assert rel_err(d[:, off], np.asarray(g["draws"][pname])) < 1e-4, pname
+    rate = float(st.n_accept.cpu()[0]) / ns_
+    assert rate == g["accept_rate"]
+
+
+@pytest.mark.parametrize("name", ["mh_c5", "mh_c1"])
+def test_mh_injected_draws_match_reference(cuda, name):
+    g = golden(name)
+    kw = g["kwargs"]
+    fn, init, _ = W.ALL_SMALL[g["model"]](B.ns)
+    model = compile_model(fn, init)
+    tape = g["tape"]
+    start = tape["iters"][0]["start"]
+    iters = tape["iters"][1:]
+    n = kw["num_samples"]
+    st = ChainState(model, model.pack(start, 1), 0.0)
+    ac = torch.zeros(n, 1, dtype=torch.uint8, device="cuda")
+    draws = torch.zeros(n, 1, model.D, device="cuda")
+    launch_mh(st, n, kw["proposal_scale"], 0, 0, draws=draws, inj_normal=dev(tape_normals(tape, model.layout, n)),
+              inj_uniform=dev(tape_uniforms(tape, "accept", n)), trace_accept=ac)
+    torch.cuda.synchronize()
+    assert np.array_equal(ac.cpu().numpy()[:, 0], np.array([it["accept"] for it in iters], dtype=np.uint8))
+    d = draws.cpu().numpy()[:, 0]
+    for pname, (off, _, _) in model.layout.items():
+        assert rel_err(d[:, off], np.asarray(g["draws"][pname])) < 1e-6, pname
+    assert float(st.n_accept.cpu()[0]) / n == g["accept_rate"]
+
+
+# ------------------------------------------------------------------------------ parity 2: NUTS
+@pytest.mark.parametrize("name", ["nuts_normal1d", "nuts_normal2d", "nuts_halfnormal_scale", "nuts_vector", "nuts_c2"])
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_nuts_injected_draws_match_reference(cuda, name, lanes):
+    g = golden(name)
+    kw = g["kwargs"]
+    fn, init, _ = W.ALL_SMALL[g["model"]](B.ns)
+    model = compile_model(fn, init)
+    nw, ns_, md = kw["num_warmup"], kw["num_samples"], kw["max_tree_depth"]
+    tape = g["tape"]
+    st = ChainState(model, model.pack(init, 1), kw["step_size"])
+    st.da_state[:, 1] = 1.0
+    st.da_state[:, 2] = float(np.log(np.float32(10.0 * kw["step_size"])))
+    tot = nw + ns_
+    inj = {k: dev(v) for k, v in tape_nuts(tape, model.layout, tot, md).items()}
+    tr = torch.full((tot, 1, md, 6), -7, dtype=torch.int32, device="cuda")
+    depths = torch.zeros(tot, 1, dtype=torch.int32, device="cuda")
+    alphas = torch.zeros(tot, 1, device="cuda")
+    draws = torch.zeros(ns_, 1, model.D, device="cuda")
+
+    def sl(lo, hi):
+        return {k: v[lo:hi].contiguous() for k, v in inj.items()}
+
+    launch_nuts(st, nw, md, _cabi.ADAPT_DUAL_AVERAGING, _cabi.COMPAT_REFERENCE, 0.65, 0, 0, depths=depths[:nw],
+                alphas=alphas[:nw], lanes=lanes, inj=sl(0, nw), trace_doubling=tr[:nw])
+    st.step_size.copy_(st.da_state[:, 1])
+    st.n_accept.zero_()
+    launch_nuts(st, ns_, md, _cabi.ADAPT_NONE, _cabi.COMPAT_REFERENCE, 0.65, 0, nw, draws=draws, depths=depths[nw:],
+                alphas=alphas[nw:], lanes=lanes, inj=sl(nw, tot), trace_doubling=tr[nw:])
+    torch.cuda.synchronize()
+    iters = tape["iters"]
+    got_depth = depths.cpu().numpy()[:, 0]
+    want_depth = np.array([it["depth"] for it in iters])
+    assert np.array_equal(got_depth, want_depth), np.nonzero(got_depth != want_depth)
+    trc = tr.cpu().numpy()[:, 0]
+    for i, it in enumerate(iters):                                   # every tree decision identical
+        for dbl in it["doublings"]:
+            want = [dbl["v"], dbl["n_sub"], int(dbl["s_sub"]), int(dbl["took"]), int(dbl["s"]), dbl["n"]]
+            assert trc[i, dbl["j"]].tolist() == want, (i, dbl, trc[i, dbl["j"]])
+    assert rel_err(alphas.cpu().numpy()[:, 0], np.array([it["alpha"] for it in iters])) < 1e-4
+    assert abs(float(st.step_size.cpu()[0]) - g["final_step_size"]) <= 2e-5 * g["final_step_size"]
+    d = draws.cpu().numpy()[:, 0]
+    for pname, (off, n, shp) in model.layout.items():
+        want = np.asarray(g["draws"][pname], dtype=np.float64).reshape(ns_, n)
+        assert rel_err(d[:, off:off + n], want) < 2e-4, pname
+    assert float(st.n_accept.cpu()[0]) / ns_ == g["accept_rate"]

@@ -1,0 +1,174 @@
+"""GPU: the public API end to end -- shapes, reproducibility, shard-independence of the random streams,
+and parity check 3 (posterior moments within 4 Monte-Carlo standard errors of closed forms / the oracle)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import mlx_mcmc_b200 as B
+import mlx_mcmc_b200.core as mx
+from mlx_mcmc_b200 import workloads as W
+from mlx_mcmc_b200.diagnostics import compute_ess, ess_geyer
+
+pytestmark = pytest.mark.gpu
+
+
+def mcse_ok(draws, mean, sd, n_eff, k=4.0):
+    """|mean(draws) - mean| <= k * sd / sqrt(n_eff)  and the sd within k standard errors of sd"""
+    m, s = float(np.mean(draws)), float(np.std(draws))
+    return abs(m - mean) <= k * sd / math.sqrt(n_eff) and abs(s - sd) <= k * sd / math.sqrt(2 * n_eff)
+
+
+# ------------------------------------------------------------------------------ API contract
+def test_single_chain_shapes_and_types(cuda):
+    fn, init, _ = W.c1_normal(B.ns)
+    m = B.MCMC(fn)
+    s = m.run(init, num_samples=200, num_warmup=100, method="hmc", step_size=0.01, num_leapfrog_steps=5, verbose=False)
+    assert set(s) == {"mu", "sigma"} and s["mu"].shape == (200,) and isinstance(s["mu"], np.ndarray)
+    assert isinstance(m.acceptance_rate, float) and 0.0 <= m.acceptance_rate <= 1.0
+    summ = m.summary()
+    assert set(summ["mu"]) == {"mean", "std", "median", "2.5%", "97.5%"}
+    m.print_summary()
+    s = m.run(init, num_samples=150, num_warmup=50, proposal_scale=0.3, verbose=False)      # default: metropolis
+    assert s["sigma"].shape == (150,)
+    fnv, initv, _ = W.t_vector_normal(B.ns, d=3)
+    sv, rate = B.nuts(fnv, initv, num_samples=100, num_warmup=100, step_size=0.3, key=mx.random.key(1))
+    assert sv["x"].shape == (100, 3)                                                           # nuts.py:338-339
+    with pytest.raises(TypeError):
+        m.run(init, num_samples=10, num_warmup=10, method="metropolis", step_size=0.1, verbose=False)
+
+
+def test_multi_chain_shapes_and_torch_return(cuda):
+    fn, init, _ = W.c2_event_rate(B.ns)
+    s, rate = B.hmc(fn, init, num_samples=50, num_warmup=50, num_chains=64)
+    assert s["rate"].shape == (64, 50)
+    s, rate = B.hmc(fn, init, num_samples=50, num_warmup=50, num_chains=64, return_torch=True)
+    assert isinstance(s["rate"], torch.Tensor) and s["rate"].is_cuda and tuple(s["rate"].shape) == (64, 50)
+
+
+def test_same_key_same_draws_and_different_key_differs(cuda):
+    fn, init, _ = W.t_normal_1d(B.ns, 0.0, 1.0)
+    a, _ = B.nuts(fn, init, num_samples=100, num_warmup=100, key=mx.random.key(42))
+    b, _ = B.nuts(fn, init, num_samples=100, num_warmup=100, key=mx.random.key(42))
+    c, _ = B.nuts(fn, init, num_samples=100, num_warmup=100, key=mx.random.key(43))
+    np.testing.assert_array_equal(a["mu"], b["mu"])          # tests/test_nuts.py:110-136, exact here
+    assert not np.array_equal(a["mu"], c["mu"])
+    a, _ = B.hmc(fn, init, num_samples=100, num_warmup=100, key=mx.random.key(7))
+    b, _ = B.hmc(fn, init, num_samples=100, num_warmup=100, key=mx.random.key(7))
+    np.testing.assert_array_equal(a["mu"], b["mu"])          # tests/test_hmc.py:148-177
+
+
+@pytest.mark.parametrize("method", ["hmc", "nuts", "metropolis"])
+def test_draws_do_not_depend_on_sharding_or_lanes(cuda, method):
+    """chains [0,32) in one call == chains [0,16) + [16,32) in two calls == any lanes-per-chain choice"""
+    fn, init, _ = W.c2_event_rate(B.ns)
+
+    def run(nc, off, lanes):
+        if method == "hmc":
+            return B.hmc(fn, init, num_samples=40, num_warmup=40, num_chains=nc, chain_offset=off, lanes=lanes,
+                         key=mx.random.key(3))[0]["rate"]
+        if method == "nuts":
+            return B.nuts(fn, init, num_samples=40, num_warmup=40, num_chains=nc, chain_offset=off, lanes=lanes,
+                          max_tree_depth=6, key=mx.random.key(3))[0]["rate"]
+        return B.metropolis_hastings(fn, init, num_samples=80, proposal_scale=0.3, num_chains=nc, chain_offset=off,
+                                     lanes=lanes, random_seed=3)[0]["rate"]
+
+    whole = run(32, 0, 1)
+    halves = np.concatenate([run(16, 0, 1), run(16, 16, 1)])
+    np.testing.assert_array_equal(whole, halves)
+    wide = run(32, 0, 8)
+    np.testing.assert_allclose(whole, wide, rtol=2e-3)      # lane-split sums differ in the last bits only
+
+
+# ------------------------------------------------------------------------------ parity 3
+def test_c2_hmc_posterior_matches_exact_gamma(cuda):
+    fn, init, meta = W.c2_event_rate(B.ns)
+    s, rate = B.hmc(fn, init, num_samples=1000, num_warmup=500, num_chains=4096, key=mx.random.key(0))
+    x = s["rate"]
+    mean, sd = meta.post_shape / meta.post_rate, math.sqrt(meta.post_shape) / meta.post_rate
+    n_eff = sum(max(ess_geyer(x[c]), 1.0) for c in range(0, 4096, 64)) * 64
+    assert 0.5 < rate <= 1.0
+    assert mcse_ok(x, mean, sd, min(n_eff, x.size)), (np.mean(x), mean, np.std(x), sd, n_eff)
+
+
+def test_c2_hmc_dual_averaging_hits_target(cuda):
+    fn, init, meta = W.c2_event_rate(B.ns)
+    s, rate, info = B.hmc(fn, init, num_samples=500, num_warmup=500, num_chains=2048, adapt="dual_averaging",
+                          target_accept=0.8, return_info=True, key=mx.random.key(1))
+    assert 0.7 < rate < 0.95, rate
+    mean, sd = meta.post_shape / meta.post_rate, math.sqrt(meta.post_shape) / meta.post_rate
+    assert abs(np.mean(s["rate"]) - mean) < 0.02 and abs(np.std(s["rate"]) - sd) < 0.02
+
+
+def test_c5_metropolis_posterior_matches_exact_beta(cuda):
+    fn, init, meta = W.c5_ab_test(B.ns)
+    m = B.MCMC(fn)
+    s = m.run(init, num_samples=2000, num_warmup=1000, proposal_scale=0.02, num_chains=8192, random_seed=0, verbose=False)
+    assert 0.2 < m.acceptance_rate < 0.5          # the reference reports ~0.33
+    for name, (a, b) in (("p_A", meta.post_a), ("p_B", meta.post_b)):
+        mean, sd = a / (a + b), math.sqrt(a * b / ((a + b) ** 2 * (a + b + 1)))
+        x = s[name]
+        n_eff = sum(max(ess_geyer(x[c]), 1.0) for c in range(0, 8192, 128)) * 128
+        assert mcse_ok(x, mean, sd, min(n_eff, x.size)), (name, np.mean(x), mean, np.std(x), sd)
+        assert np.all((x > 0) & (x < 1))
+
+
+def test_c1_metropolis_agrees_with_oracle_run(cuda):
+    """config-1 model, reference's example-01/02 Metropolis settings: pooled CUDA chains vs one long oracle chain"""
+    from oracle.ns import ns as ons, samplers
+    fo, init, _ = W.c1_normal(ons)
+    so, _ = samplers.run_port(fo, init, num_samples=3000, num_warmup=1000, proposal_scale=0.3, random_seed=42)
+    fn, _, _ = W.c1_normal(B.ns)
+    m = B.MCMC(fn)
+    s = m.run(init, num_samples=1000, num_warmup=1000, proposal_scale=0.3, num_chains=1024, random_seed=42, verbose=False)
+    for name in ("mu", "sigma"):
+        o = np.asarray(so[name])
+        ess_o = max(ess_geyer(o), 10.0)
+        mcse = np.std(o) / math.sqrt(ess_o)
+        assert abs(np.mean(s[name]) - np.mean(o)) <= 4 * mcse, (name, np.mean(s[name]), np.mean(o), mcse)
+        assert abs(np.std(s[name]) - np.std(o)) <= 4 * np.std(o) / math.sqrt(2 * ess_o)
+
+
+def test_nuts_prior_models_match_truth(cuda):
+    """the reference's own NUTS tests (tests/test_nuts.py:13-54,88-108) over many chains"""
+    fn, init, _ = W.t_normal_1d(B.ns, 5.0, 2.0)
+    s, rate = B.nuts(fn, init, num_samples=500, num_warmup=500, step_size=0.5, num_chains=1024, key=mx.random.key(42))
+    x = s["mu"]
+    assert abs(np.mean(x) - 5.0) < 0.05 and abs(np.std(x) - 2.0) < 0.05 and rate > 0.5
+    fn, init, _ = W.t_normal_2d(B.ns)
+    s, _ = B.nuts(fn, init, num_samples=500, num_warmup=500, step_size=0.3, num_chains=1024, key=mx.random.key(123))
+    assert abs(np.mean(s["mu1"])) < 0.05 and abs(np.mean(s["mu2"]) - 5.0) < 0.08
+    assert abs(np.std(s["mu1"]) - 1.0) < 0.05 and abs(np.std(s["mu2"]) - 2.0) < 0.08
+    fn, init, _ = W.t_halfnormal_scale(B.ns)
+    s, _ = B.nuts(fn, init, num_samples=300, num_warmup=300, step_size=0.1, num_chains=256, key=mx.random.key(456))
+    assert np.all(s["sigma"] > 0)
+
+
+def test_nuts_correct_mode_c2_matches_exact_gamma(cuda):
+    """compat='correct' (log-space slice) on a data model; the exact posterior is Gamma(52, 15.1)"""
+    fn, init, meta = W.c2_event_rate(B.ns)
+    s, rate, info = B.nuts(fn, init, num_samples=500, num_warmup=500, num_chains=2048, compat="correct",
+                           return_info=True, key=mx.random.key(5))
+    mean, sd = meta.post_shape / meta.post_rate, math.sqrt(meta.post_shape) / meta.post_rate
+    x = s["rate"]
+    assert abs(np.mean(x) - mean) < 0.02 and abs(np.std(x) - sd) < 0.02, (np.mean(x), mean, np.std(x), sd)
+    assert info.grad_evals > 0 and info.depths.max() <= 10
+
+
+def test_hmc_constrained_parameter_stays_positive(cuda):
+    """tests/test_hmc.py:118-146 across chains: HalfNormal(2) draws are all positive"""
+    fn, init, _ = W.t_halfnormal(B.ns, 2.0)
+    s, rate = B.hmc(fn, init, num_samples=500, num_warmup=300, step_size=0.1, num_leapfrog_steps=10, num_chains=512)
+    assert np.all(s["sigma"] > 0)
+    assert 0.5 < np.mean(s["sigma"]) < 3.0
+
+
+def test_ess_helpers(cuda):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(4000)
+    assert 2500 < compute_ess(x) <= 4000 * 1.2 and 2500 < ess_geyer(x) < 5000
+    ar = np.zeros(4000)
+    for i in range(1, 4000):
+        ar[i] = 0.9 * ar[i - 1] + rng.standard_normal()
+    assert 100 < ess_geyer(ar) < 500                          # n (1-rho)/(1+rho) = 210

@@ -1,0 +1,200 @@
+"""CPU: tracer, host distribution classes, API surface, and that the C-ABI library loads and exports
+every symbol include/b200mcmc.h declares (no compute calls)."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mlx_mcmc_b200 as B
+import mlx_mcmc_b200.core as mx
+from mlx_mcmc_b200 import _cabi, tracer, workloads as W
+from mlx_mcmc_b200.tracer import (EXPONENTIAL, GAMMA, NORMAL, OP_CONST, OP_DATA, OP_LIN, OP_MATVEC, OP_PARAM,
+                                  OP_PARAMVEC, UnsupportedOpError, trace)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ----------------------------------------------------------------------------- C ABI
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _cabi.load()
+    header = open(os.path.join(ROOT, "include", "b200mcmc.h")).read()
+    declared = set(re.findall(r"\b(b2m_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} not exported"
+    assert lib.b2m_abi_version() == _cabi.ABI_VERSION
+    sizes = (ctypes.c_int32 * 6)()
+    lib.b2m_struct_sizes(sizes)
+    assert list(sizes) == [ctypes.sizeof(t) for t in (_cabi.Term, _cabi.Operand, _cabi.LinEntry, _cabi.HmcArgs,
+                                                        _cabi.MhArgs, _cabi.NutsArgs)]
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", _cabi.lib_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_bad_arguments_return_errors_not_crashes():
+    lib = _cabi.load()
+    assert lib.b2m_model_create(None, 0, None, 0, None, 0, 1, ctypes.byref(ctypes.c_void_p())) != 0
+    assert b"terms" in lib.b2m_last_error()
+    t = (_cabi.Term * 1)()
+    t[0].dist = 99
+    t[0].length = 1
+    assert lib.b2m_model_create(t, 1, None, 0, None, 0, 1, ctypes.byref(ctypes.c_void_p())) != 0
+    assert b"unknown distribution" in lib.b2m_last_error()
+    assert lib.b2m_hmc_run(None, None, None) != 0
+
+
+# ----------------------------------------------------------------------------- tracer
+def test_trace_c1_all_three_idioms_give_the_same_table():
+    tabs = []
+    for style in ("vector", "unrolled", "stack"):
+        fn, init, meta = W.c1_normal(B.ns, style=style)
+        tm = trace(fn, init)
+        assert tm.D == 2 and len(tm.terms) == 3 and not tm.is_glm
+        lik = tm.terms[2]
+        assert (lik.dist, lik.length, lik.x.kind, lik.p0.kind, lik.p1.kind) == (NORMAL, 100, OP_DATA, OP_PARAM, OP_PARAM)
+        np.testing.assert_array_equal(tm.arrays[lik.x.a], meta.y.astype(np.float32))
+        tabs.append(tm.describe())
+    assert tabs[0] == tabs[1] == tabs[2]
+
+
+def test_trace_c2_and_param_in_scale_slot():
+    fn, init, _ = W.c2_event_rate(B.ns, style="unrolled")
+    tm = trace(fn, init)
+    assert [t.dist for t in tm.terms] == [GAMMA, EXPONENTIAL] and tm.terms[1].length == 50
+    assert tm.terms[0].k[0] == 2.0 and abs(tm.terms[0].k[1]) < 1e-7       # lgamma(2) = 0
+    fn, init, _ = W.t_halfnormal_scale(B.ns)
+    tm = trace(fn, init)
+    t = tm.terms[1]
+    assert (t.x.kind, t.x.c, t.p0.kind, t.p1.kind, t.p1.a) == (OP_CONST, 0.5, OP_CONST, OP_PARAM, 0)
+
+
+def test_trace_regression_is_glm_class():
+    fn, init, meta = W.regression(B.ns, 64, 5)
+    tm = trace(fn, init)
+    assert tm.is_glm and tm.D == 5
+    prior, lik = tm.terms
+    assert prior.x.kind == OP_PARAMVEC and prior.length == 5
+    assert lik.p0.kind == OP_MATVEC and lik.length == 64 and tm.arrays[lik.p0.a].shape == (64, 5)
+
+
+def test_trace_affine_operands_and_weights():
+    x = np.linspace(-1, 1, 7).astype(np.float32)
+    y = (2 * x + 1).astype(np.float32)
+
+    def log_prob(p):
+        mean = p["a"] + p["b"] * mx.array(x)
+        return 0.5 * mx.sum(B.Normal(mean, 2.0).log_prob(mx.array(y))) - B.Normal(0, 1).log_prob(p["a"]) * 2 + 3.0
+
+    tm = trace(log_prob, {"a": 0.0, "b": 0.0})
+    lik = tm.terms[0]
+    assert lik.p0.kind == OP_LIN and lik.weight == 0.5 and lik.length == 7
+    ents = tm.lin[lik.p0.a: lik.p0.a + lik.p0.b]
+    assert (0, -1, 1.0) in ents and any(e[0] == 1 and e[1] >= 0 for e in ents)
+    assert tm.terms[1].weight == -2.0
+    assert tm.terms[-1].dist == tracer.CONSTANT and tm.terms[-1].k[0] == 3.0
+
+
+@pytest.mark.parametrize("body, needle", [
+    (lambda p: B.Normal(0, 1).log_prob(mx.log(p["x"])), "mx.log of a traced value"),
+    (lambda p: B.Normal(0, 1).log_prob(p["x"] * p["x"]), "product of two traced values"),
+    (lambda p: B.Normal(0, 1).log_prob(p["x"]) if float(p["x"]) > 0 else 0.0, "float()"),
+    (lambda p: B.Gamma(p["x"], 1.0).log_prob(2.0), "shape parameter"),
+    (lambda p: B.Categorical(probs=[p["x"], 0.5]).log_prob(0), "Categorical with traced"),
+    (lambda p: p["x"] + 1.0, "raw expression"),
+    (lambda p: B.Normal(0, 1).log_prob(mx.array(np.ones(3, dtype=np.float32)) * p["x"]), "scalar"),
+    (lambda p: 1.0, "does not depend"),
+])
+def test_unsupported_ops_raise_at_trace_time(body, needle):
+    with pytest.raises(UnsupportedOpError) as e:
+        trace(body, {"x": 0.5})
+    assert needle in str(e.value)
+
+
+# ----------------------------------------------------------------------------- host distribution classes
+def test_known_answers_host_classes():
+    """The reference's known-answer tests (tests/test_distributions.py:18-32,67-79;
+    tests/test_new_distributions.py:18-37,89-99,144-154,203-226)."""
+    assert np.isclose(float(B.Normal(0, 1).log_prob(0.0)), -0.5 * math.log(2 * math.pi), rtol=1e-5)
+    assert float(B.Normal(0, 1).log_prob(1.0)) == float(B.Normal(0, 1).log_prob(-1.0))
+    assert np.isclose(float(B.HalfNormal(1).log_prob(0.0)), math.log(2) - 0.5 * math.log(2 * math.pi), rtol=1e-5)
+    assert float(B.HalfNormal(1).log_prob(-1.0)) == -math.inf
+    for x in (-0.1, 1.5, 0.0, 1.0):
+        assert float(B.Beta(2, 2).log_prob(x)) == -math.inf
+    assert math.isfinite(float(B.Beta(2, 2).log_prob(0.5)))
+    assert float(B.Gamma(2, 1).log_prob(-1.0)) == -math.inf and float(B.Gamma(2, 1).log_prob(1.5)) < 0
+    assert np.isclose(float(B.Exponential(2).log_prob(0.0)), math.log(2)) and float(B.Exponential(2).log_prob(-1.0)) == -math.inf
+    c = B.Categorical(probs=[0.2, 0.5, 0.3])
+    assert np.isclose(float(c.log_prob(0)), math.log(0.2), rtol=1e-2) and np.isclose(float(c.log_prob(1)), math.log(0.5), rtol=1e-2)
+    assert float(c.log_prob(-1)) == -math.inf and float(c.log_prob(3)) == -math.inf
+    with pytest.raises(ValueError):
+        B.Categorical()
+    with pytest.raises(ValueError):
+        B.Categorical(probs=[0.5, 0.5], logits=[0.0, 0.0])
+    assert np.isclose(float(B.Beta(2, 5).mean()), 2 / 7) and np.isclose(float(B.Gamma(3, 2).mean()), 1.5)
+    assert np.isclose(float(B.Exponential(4).mean()), 0.25) and int(B.Categorical(probs=[.1, .7, .2]).mode()) == 1
+
+
+def test_host_classes_agree_with_oracle_classes():
+    from oracle.ns import ns as ons
+    xs = np.array([-1.0, 0.0, 0.3, 0.99, 2.5], dtype=np.float32)
+    pairs = [(B.Normal(0.5, 1.5), ons.Normal(0.5, 1.5)), (B.HalfNormal(2.0), ons.HalfNormal(2.0)),
+             (B.Exponential(1.7), ons.Exponential(1.7)), (B.Gamma(2.5, 0.7), ons.Gamma(2.5, 0.7)),
+             (B.Beta(2.0, 3.0), ons.Beta(2.0, 3.0))]
+    for mine, theirs in pairs:
+        a, b = np.asarray(mine.log_prob(xs)), np.asarray(theirs.log_prob(ons.mx.array(xs)))
+        np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-6)
+
+
+def test_sampling_moments():
+    k = mx.random.key(0)
+    assert abs(np.mean(B.Normal(2.0, 3.0).sample(k, (20000,))) - 2.0) < 0.1
+    assert np.all(B.HalfNormal(1.0).sample(k, (1000,)) >= 0)
+    assert abs(np.mean(B.Gamma(3.0, 2.0).sample(k, (20000,))) - 1.5) < 0.05
+    assert abs(np.mean(B.Beta(2.0, 5.0).sample(k, (20000,))) - 2 / 7) < 0.02
+    assert abs(np.mean(B.Exponential(4.0).sample(k, (20000,))) - 0.25) < 0.02
+    s = B.Categorical(probs=[0.2, 0.5, 0.3]).sample(k, (20000,))
+    assert abs(np.mean(s == 1) - 0.5) < 0.02
+
+
+# ----------------------------------------------------------------------------- API surface
+def test_export_list_matches_reference():
+    for name in ["Normal", "HalfNormal", "Beta", "Gamma", "Exponential", "Categorical", "metropolis_hastings", "hmc",
+                 "nuts", "MCMC"]:
+        assert name in B.__all__ and hasattr(B, name)
+
+
+def test_mcmc_errors_before_any_device_work():
+    m = B.MCMC(lambda p: B.Normal(0, 1).log_prob(p["x"]))
+    with pytest.raises(ValueError, match="Unknown sampling method"):
+        m.run({"x": 0.0}, method="gibbs", verbose=False)
+    with pytest.raises(ValueError, match="Must run sampling first"):
+        m.summary()
+    with pytest.raises(ZeroDivisionError):
+        B.hmc(lambda p: B.Normal(0, 1).log_prob(p["x"]), {"x": 0.0}, num_warmup=0)
+    with pytest.raises(ZeroDivisionError):
+        B.nuts(lambda p: B.Normal(0, 1).log_prob(p["x"]), {"x": 0.0}, num_warmup=0)
+
+
+def test_product_never_imports_the_oracle():
+    import subprocess
+    import sys
+    code = ("import sys; import mlx_mcmc_b200, mlx_mcmc_b200.engine, mlx_mcmc_b200.workloads; "
+            "bad=[m for m in sys.modules if m.split('.')[0] in ('oracle','mlx')]; print(bad); sys.exit(1 if bad else 0)")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_no_cuda_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        B.MCMC(lambda p: B.Normal(0, 1).log_prob(p["x"])).run({"x": 0.0}, num_samples=5, num_warmup=5, verbose=False)
