@@ -233,41 +233,78 @@ __device__ inline float eval_model(const SModel &sm, const float *th, float *gr,
 
     const bool params_fixed = !op_varies(o0) && !op_varies(o1);
     if (params_fixed && ox.kind == B2M_OP_DATA && dist == B2M_NORMAL) {
-      // Hot pattern (C1 likelihood): Normal(mu, sigma) over an observation vector.
+      // Hot pattern (C1 likelihood): Normal(mu, sigma) over an observation vector.  Four independent
+      // accumulators per statistic: breaks the FADD dependency chain and shortens each rounding chain.
       const float mu = op_fetch(o0, 0, th, TS, sm), sg = op_fetch(o1, 0, th, TS, sm);
       const float inv_var = 1.0f / (sg * sg), base = -kHalfLog2Pi - logf(sg);
       const float *y = sm.arrays[ox.a].ptr;
-      float s1 = 0.f, s2 = 0.f;
-      int cnt = 0;
-      for (int n = lane; n < len; n += G) {
-        float z = y[n] - mu;
-        s1 += z;
-        s2 = fmaf(z, z, s2);
-        ++cnt;
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+      int n = lane;
+      if (G == 1 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        const float4 *y4 = reinterpret_cast<const float4 *>(y);
+        for (; n + 3 < len; n += 4) {  // one 16-byte broadcast load per four observations
+          const float4 v = y4[n >> 2];
+          const float z0 = v.x - mu, z1 = v.y - mu, z2 = v.z - mu, z3 = v.w - mu;
+          s1[0] += z0; s1[1] += z1; s1[2] += z2; s1[3] += z3;
+          s2[0] = fmaf(z0, z0, s2[0]); s2[1] = fmaf(z1, z1, s2[1]);
+          s2[2] = fmaf(z2, z2, s2[2]); s2[3] = fmaf(z3, z3, s2[3]);
+        }
+      } else {
+        for (; n + 3 * G < len; n += 4 * G) {
+          const float z0 = y[n] - mu, z1 = y[n + G] - mu, z2 = y[n + 2 * G] - mu, z3 = y[n + 3 * G] - mu;
+          s1[0] += z0; s1[1] += z1; s1[2] += z2; s1[3] += z3;
+          s2[0] = fmaf(z0, z0, s2[0]); s2[1] = fmaf(z1, z1, s2[1]);
+          s2[2] = fmaf(z2, z2, s2[2]); s2[3] = fmaf(z3, z3, s2[3]);
+        }
       }
-      acc = cnt * base - 0.5f * s2 * inv_var;
-      a0 = s1 * inv_var;
-      a1 = (s2 * inv_var - (float)cnt) / sg;
+      for (; n < len; n += G) {
+        const float z = y[n] - mu;
+        s1[0] += z;
+        s2[0] = fmaf(z, z, s2[0]);
+      }
+      const float t1 = (s1[0] + s1[1]) + (s1[2] + s1[3]), t2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+      const float cnt = (float)((len - lane + G - 1) / G);
+      acc = cnt * base - 0.5f * t2 * inv_var;
+      a0 = t1 * inv_var;
+      a1 = (t2 * inv_var - cnt) / sg;
     } else if (params_fixed && ox.kind == B2M_OP_DATA && dist == B2M_EXPONENTIAL) {
       // Hot pattern (C2 likelihood): Exponential(rate) over an observation vector.
       const float rate = op_fetch(o0, 0, th, TS, sm);
       const float lr = logf(rate), ir = 1.0f / rate;
       const float *y = sm.arrays[ox.a].ptr;
-      float s1 = 0.f;
-      int cnt = 0;
-      bool bad = false;
-      for (int n = lane; n < len; n += G) {
-        float v = y[n];
-        bad |= !(v >= 0.f);
-        s1 += v;
-        ++cnt;
+      float s1[4] = {0.f, 0.f, 0.f, 0.f};
+      float lo = INFINITY;  // min over the data: a negative (or NaN) datum is outside the support
+      int n = lane;
+      if (G == 1 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        const float4 *y4 = reinterpret_cast<const float4 *>(y);
+        for (; n + 3 < len; n += 4) {
+          const float4 v = y4[n >> 2];
+          s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+          lo = fminf(fminf(lo, fminf(v.x, v.y)), fminf(v.z, v.w));
+        }
+      } else {
+        for (; n + 3 * G < len; n += 4 * G) {
+          const float v0 = y[n], v1 = y[n + G], v2 = y[n + 2 * G], v3 = y[n + 3 * G];
+          s1[0] += v0; s1[1] += v1; s1[2] += v2; s1[3] += v3;
+          lo = fminf(fminf(lo, fminf(v0, v1)), fminf(v2, v3));
+        }
       }
-      acc = bad ? -INFINITY : cnt * lr - rate * s1;
-      a0 = bad ? 0.f : cnt * ir - s1;  // any out-of-support datum: -inf value; its own cotangent is 0
-      if (bad) {                        // exact masked gradient needs the per-element path
+      for (; n < len; n += G) {
+        const float v = y[n];
+        s1[0] += v;
+        lo = fminf(lo, v);
+      }
+      const float t1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+      const float cnt = (float)((len - lane + G - 1) / G);
+      const bool bad = !(lo >= 0.f) || !(t1 == t1);
+      if (!bad) {
+        acc = cnt * lr - rate * t1;
+        a0 = cnt * ir - t1;
+      } else {  // some datum outside the support: -inf value, masked per-element gradient (rare path)
+        acc = -INFINITY;
         a0 = 0.f;
-        for (int n = lane; n < len; n += G) {
-          float v = y[n];
+        for (int m = lane; m < len; m += G) {
+          const float v = y[m];
           if (v >= 0.f) a0 += ir - v;
         }
       }

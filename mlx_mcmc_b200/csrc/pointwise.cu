@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(128) hmc_kernel(KModel km, b2m_hmc_args A) {
       if ((int64_t)giter > 10) eps *= ((double)n_acc / (double)n_tot < A.target_accept) ? 0.95 : 1.05;
     } else if (A.adapt == B2M_ADAPT_DUAL_AVERAGING) {
       // Hoffman & Gelman Alg. 5 recurrences with the constants the reference uses in nuts.py:62-68
-      float a = expf(fminf(log_ratio, 0.f));
-      if (!(a == a)) a = 0.f;
+      // a divergent trajectory (NaN / -inf energy) counts as acceptance probability 0
+      float a = (log_ratio == log_ratio) ? expf(fminf(log_ratio, 0.f)) : 0.f;
       const double m = (double)giter + 1.0, eta = 1.0 / (m + 10.0);
       h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - (double)a);
       double log_eps = da_mu - sqrt(m) / 0.05 * h_bar;

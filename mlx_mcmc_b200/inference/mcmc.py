@@ -52,22 +52,20 @@ class MCMC:
 
         if verbose:
             print(f"\n{_RULE}\nB200-MCMC: {method.upper()} Sampling\n{_RULE}\n")
-        num_chains = kwargs.get("num_chains", 1)
         # warm-up is a separate sampler call with `random_seed`; sampling restarts from its last draw
         # with `random_seed + 1` (mcmc.py:146-178)
+        extra = {}
         if num_warmup > 0:
             wkw = dict(kwargs)
-            wkw.pop("return_info", None)
-            wkw["return_torch"] = False
-            warm, warm_accept = sampler(self.log_prob_fn, initial_params, num_samples=num_warmup,
-                                        proposal_scale=proposal_scale, random_seed=random_seed, verbose=False, **wkw)
+            wkw.update(return_info=True, return_torch=True)
+            _, warm_accept, winfo = sampler(self.log_prob_fn, initial_params, num_samples=num_warmup,
+                                            proposal_scale=proposal_scale, random_seed=random_seed, verbose=False, **wkw)
             if verbose:
                 print(f"Warmup phase: {num_warmup} samples, acceptance rate: {warm_accept:.2%}\n")
-            start = {k: (v[-1] if num_chains == 1 else v[:, -1]) for k, v in warm.items()}
-        else:
-            start = initial_params
-        out = sampler(self.log_prob_fn, start, num_samples=num_samples, proposal_scale=proposal_scale,
-                      random_seed=random_seed + 1 if num_warmup > 0 else random_seed, verbose=False, **kwargs)
+            # the last warm-up draw of every chain is the chain's final position (mcmc.py:162)
+            extra = dict(theta0=winfo.state.theta, model=winfo.model)
+        out = sampler(self.log_prob_fn, initial_params, num_samples=num_samples, proposal_scale=proposal_scale,
+                      random_seed=random_seed + 1 if num_warmup > 0 else random_seed, verbose=False, **kwargs, **extra)
         self.samples, self.acceptance_rate = out[0], out[1]
         self.info = out[2] if len(out) > 2 else None
         if verbose:

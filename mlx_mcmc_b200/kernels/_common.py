@@ -17,9 +17,16 @@ def philox_seed(key, random_seed=None) -> int:
     return int(random_seed or 0)
 
 
-def prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, model=None):
+def prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, model=None, theta0=None):
+    """Trace/compile (cached) and build the per-chain state.  `theta0` ([num_chains, D] device tensor)
+    overrides the common starting point -- used to hand the warm-up's final positions to the sampling call."""
     model = model if isinstance(model, DeviceModel) else compile_model(log_prob_fn, initial_params)
-    theta = model.pack(initial_params, num_chains)
+    if theta0 is not None:
+        if tuple(theta0.shape) != (num_chains, model.D):
+            raise ValueError(f"theta0 has shape {tuple(theta0.shape)}, expected {(num_chains, model.D)}")
+        theta = theta0.to(device=model.device, dtype=torch.float32).clone()
+    else:
+        theta = model.pack(initial_params, num_chains)
     return model, ChainState(model, theta, step_size, chain_offset)
 
 
