@@ -1,10 +1,11 @@
 // C ABI of libb200mcmc.so (declared in include/b200mcmc.h): model handle, validation, dispatch.
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
 #include <vector>
 
-#include "model.cuh"
+#include "glm.cuh"
 
 namespace b2m {
 
@@ -18,6 +19,7 @@ int launch_logp_grad(const KModel &km, const float *theta, int64_t C, float *log
 int launch_hmc(const KModel &km, b2m_hmc_args a, cudaStream_t st);
 int launch_mh(const KModel &km, b2m_mh_args a, cudaStream_t st);
 int launch_nuts(const KModel &km, b2m_nuts_args a, cudaStream_t st);
+int glm_build(GlmModel &g, const float *X, const float *y, int N, int D);
 
 }  // namespace b2m
 
@@ -28,6 +30,8 @@ struct b2m_model {
   std::vector<b2m_term> terms;
   std::vector<b2m_lin_entry> lin;
   std::vector<b2m_array> arrays;
+  b2m::GlmModel glm;           // model_class == 1
+  void *dev_prior_terms = nullptr;
 };
 
 using b2m::set_error;
@@ -62,6 +66,57 @@ static int check_operand(const b2m_operand &o, int length, int D, int n_lin, con
       return 0;
     default: return fail("unknown operand kind " + std::to_string(o.kind));
   }
+}
+
+// GLM class: exactly one Normal likelihood whose location is X @ beta (+ const), observed y, scale constant or
+// a scalar parameter; every other term is a pointwise prior.
+static int setup_glm(b2m_model *m, int D) {
+  int lik = -1;
+  for (size_t t = 0; t < m->terms.size(); ++t) {
+    const b2m_term &T = m->terms[t];
+    const bool has_mv = T.x.kind == B2M_OP_MATVEC || T.p0.kind == B2M_OP_MATVEC || T.p1.kind == B2M_OP_MATVEC;
+    if (!has_mv) continue;
+    B2M_REQUIRE(lik < 0, "GLM class: only one X @ beta term is supported");
+    B2M_REQUIRE(T.dist == B2M_NORMAL && T.p0.kind == B2M_OP_MATVEC && T.x.kind == B2M_OP_DATA &&
+                    (T.p1.kind == B2M_OP_CONST || T.p1.kind == B2M_OP_PARAM),
+                "GLM class: X @ beta must be the location of a Normal likelihood over an observed vector, with a "
+                "constant or scalar-parameter scale");
+    lik = (int)t;
+  }
+  B2M_REQUIRE(lik >= 0, "GLM class: no X @ beta term found");
+  const b2m_term &L = m->terms[lik];
+  const b2m_array &X = m->arrays[L.p0.a];
+  const b2m_array &Y = m->arrays[L.x.a];
+  B2M_REQUIRE(X.rows == L.length && Y.rows >= L.length, "GLM class: X rows / y length do not match the term length");
+  b2m::GlmModel &g = m->glm;
+  g.Dtot = D;
+  g.beta_off = L.p0.b;
+  g.loc_const = L.p0.c;
+  g.weight = L.weight;
+  g.sigma_param = L.p1.kind == B2M_OP_PARAM ? L.p1.a : -1;
+  g.sigma_const = L.p1.kind == B2M_OP_CONST ? L.p1.c : 1.f;
+  const char *path = getenv("B2M_GLM_PATH");
+  g.use_tc = b2m::tc_available() && !(path && std::string(path) == "simt");
+  if (int rc = b2m::glm_build(g, X.data, Y.data, (int)L.length, (int)X.cols)) return rc;
+  // prior = all other terms
+  std::vector<b2m_term> prior;
+  for (size_t t = 0; t < m->terms.size(); ++t)
+    if ((int)t != lik) prior.push_back(m->terms[t]);
+  g.has_prior = !prior.empty();
+  g.prior = m->km;
+  g.prior.n_terms = (int)prior.size();
+  g.prior.max_len = 1;
+  if (g.has_prior) {
+    B2M_CHECK_CUDA(cudaMalloc(&m->dev_prior_terms, sizeof(b2m_term) * prior.size()));
+    B2M_CHECK_CUDA(cudaMemcpy(m->dev_prior_terms, prior.data(), sizeof(b2m_term) * prior.size(), cudaMemcpyHostToDevice));
+    g.prior.terms = static_cast<const b2m_term *>(m->dev_prior_terms);
+    // 1-D arrays used by the priors are small; the big matrices are never staged (cols != 1) but y is 1-D:
+    // disable staging when it would not fit
+    int64_t stage = 0;
+    for (auto &a : m->arrays) if (a.cols == 1) stage += (a.rows + 3) & ~int64_t(3);
+    g.prior.stage_floats = (stage * 4 <= 32 * 1024) ? (int32_t)stage : 0;
+  }
+  return 0;
 }
 
 extern "C" {
@@ -141,6 +196,12 @@ int b2m_model_create(const b2m_term *terms, int32_t n_terms, const b2m_lin_entry
   m->km.max_len = max_len;
   // observation vectors are staged in shared memory when they fit beside the mailboxes
   m->km.stage_floats = (stage * 4 <= 96 * 1024) ? (int32_t)stage : 0;
+  if (m->model_class == 1) {
+    if (int rc = setup_glm(m, D)) {
+      b2m_model_destroy(m);
+      return rc;
+    }
+  }
   *out = m;
   return 0;
 }
@@ -150,6 +211,8 @@ void b2m_model_destroy(b2m_model *m) {
   if (m->dev_terms) cudaFree(m->dev_terms);
   if (m->dev_lin) cudaFree(m->dev_lin);
   if (m->dev_arrays) cudaFree(m->dev_arrays);
+  if (m->dev_prior_terms) cudaFree(m->dev_prior_terms);
+  if (m->model_class == 1) b2m::glm_free(m->glm);
   delete m;
 }
 
@@ -161,7 +224,8 @@ int b2m_logp_grad(b2m_model *m, const float *theta, int64_t n_chains, float *log
   B2M_REQUIRE(m && theta && logp, "b2m_logp_grad: NULL argument");
   B2M_REQUIRE(n_chains > 0, "b2m_logp_grad: n_chains must be positive");
   B2M_REQUIRE(valid_lanes(lanes), "b2m_logp_grad: lanes must be 0 or a power of two <= 32");
-  B2M_REQUIRE(m->model_class == 0, "b2m_logp_grad: GLM-class models are not built in this library version");
+  if (m->model_class == 1)
+    return b2m::glm_logp_grad(m->glm, theta, n_chains, logp, grad, static_cast<cudaStream_t>(stream));
   return b2m::launch_logp_grad(m->km, theta, n_chains, logp, grad, lanes, static_cast<cudaStream_t>(stream));
 }
 
@@ -172,8 +236,8 @@ int b2m_hmc_run(b2m_model *m, const b2m_hmc_args *a, void *stream) {
   B2M_REQUIRE(valid_lanes(a->lanes), "b2m_hmc_run: lanes must be 0 or a power of two <= 32");
   B2M_REQUIRE(a->adapt >= B2M_ADAPT_NONE && a->adapt <= B2M_ADAPT_DUAL_AVERAGING, "b2m_hmc_run: bad adapt mode");
   B2M_REQUIRE(a->adapt != B2M_ADAPT_DUAL_AVERAGING || a->da_state, "b2m_hmc_run: dual averaging needs da_state");
-  B2M_REQUIRE(m->model_class == 0, "b2m_hmc_run: GLM-class models are not built in this library version");
   if (a->n_iter == 0) return 0;
+  if (m->model_class == 1) return b2m::glm_hmc_run(m->glm, *a, static_cast<cudaStream_t>(stream));
   return b2m::launch_hmc(m->km, *a, static_cast<cudaStream_t>(stream));
 }
 
@@ -182,8 +246,8 @@ int b2m_mh_run(b2m_model *m, const b2m_mh_args *a, void *stream) {
   B2M_REQUIRE(a->n_chains > 0 && a->n_iter >= 0, "b2m_mh_run: bad sizes");
   B2M_REQUIRE(a->theta && a->logp && a->n_accept, "b2m_mh_run: NULL state pointer");
   B2M_REQUIRE(valid_lanes(a->lanes), "b2m_mh_run: lanes must be 0 or a power of two <= 32");
-  B2M_REQUIRE(m->model_class == 0, "b2m_mh_run: GLM-class models are not built in this library version");
   if (a->n_iter == 0) return 0;
+  if (m->model_class == 1) return b2m::glm_mh_run(m->glm, *a, static_cast<cudaStream_t>(stream));
   return b2m::launch_mh(m->km, *a, static_cast<cudaStream_t>(stream));
 }
 
@@ -194,8 +258,8 @@ int b2m_nuts_run(b2m_model *m, const b2m_nuts_args *a, void *stream) {
   B2M_REQUIRE(a->theta && a->step_size && a->da_state && a->n_accept && a->n_leaves && a->n_diverge,
               "b2m_nuts_run: NULL state pointer");
   B2M_REQUIRE(valid_lanes(a->lanes), "b2m_nuts_run: lanes must be 0 or a power of two <= 32");
-  B2M_REQUIRE(m->model_class == 0, "b2m_nuts_run: GLM-class models are not built in this library version");
   if (a->n_iter == 0) return 0;
+  if (m->model_class == 1) return b2m::glm_nuts_run(m->glm, *a, static_cast<cudaStream_t>(stream));
   return b2m::launch_nuts(m->km, *a, static_cast<cudaStream_t>(stream));
 }
 

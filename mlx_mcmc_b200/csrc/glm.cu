@@ -1,0 +1,276 @@
+// GLM-class evaluation pipeline: pack -> GEMM (B X^T) with residual epilogue -> GEMM (R X) -> finish.
+#include "glm.cuh"
+
+#include <vector>
+
+namespace b2m {
+
+// ---------------------------------------------------------------- memory
+template <typename T>
+static int dev_alloc(T **p, size_t n) {
+  B2M_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(p), sizeof(T) * (n ? n : 1)));
+  return 0;
+}
+#define FREE(p) do { if (p) cudaFree(p); p = nullptr; } while (0)
+
+static void free_workspace(GlmModel &g) {
+  FREE(g.B); FREE(g.Bh); FREE(g.Bl); FREE(g.R); FREE(g.Rh); FREE(g.Rl); FREE(g.G); FREE(g.ss_part); FREE(g.inv_var);
+  g.cap = 0;
+}
+
+void glm_free(GlmModel &g) {
+  free_workspace(g);
+  FREE(g.X); FREE(g.XT); FREE(g.Xh); FREE(g.Xl); FREE(g.XTh); FREE(g.XTl); FREE(g.y);
+}
+
+int glm_reserve(GlmModel &g, int64_t n_chains) {
+  const int64_t cp = (n_chains + 127) / 128 * 128;
+  if (cp <= g.cap) return 0;
+  free_workspace(g);
+  if (dev_alloc(&g.B, cp * g.Dp) || dev_alloc(&g.G, cp * g.Dp) || dev_alloc(&g.R, cp * (size_t)g.Np) ||
+      dev_alloc(&g.ss_part, (size_t)(g.Np / 64) * cp) || dev_alloc(&g.inv_var, cp))
+    return 2;
+  if (g.use_tc) {
+    if (dev_alloc(&g.Bh, cp * g.Dp) || dev_alloc(&g.Bl, cp * g.Dp) || dev_alloc(&g.Rh, cp * (size_t)g.Np) ||
+        dev_alloc(&g.Rl, cp * (size_t)g.Np))
+      return 2;
+  }
+  g.cap = cp;
+  return 0;
+}
+
+// ---------------------------------------------------------------- data preparation (once per model)
+__global__ void pad_transpose_split_kernel(const float *__restrict__ X, int N, int D, int Np, int Dp, float *Xp,
+                                           float *XT, float *Xh, float *Xl, float *XTh, float *XTl) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)Np * Dp) return;
+  const int n = int(i / Dp), d = int(i % Dp);
+  const float v = (n < N && d < D) ? X[(int64_t)n * D + d] : 0.f;
+  float hi, lo;
+  split_tf32(v, hi, lo);
+  Xp[i] = v;
+  XT[(int64_t)d * Np + n] = v;
+  if (Xh) {
+    Xh[i] = hi; Xl[i] = lo;
+    XTh[(int64_t)d * Np + n] = hi; XTl[(int64_t)d * Np + n] = lo;
+  }
+}
+
+__global__ void pad_vector_kernel(const float *__restrict__ y, int N, int Np, float *yp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Np) yp[i] = i < N ? y[i] : 0.f;
+}
+
+int glm_build(GlmModel &g, const float *X, const float *y, int N, int D) {
+  g.N = N; g.D = D;
+  g.Np = (N + 255) / 256 * 256;
+  g.Dp = (D + 63) / 64 * 64;
+  const size_t nd = (size_t)g.Np * g.Dp;
+  if (dev_alloc(&g.X, nd) || dev_alloc(&g.XT, nd) || dev_alloc(&g.y, g.Np)) return 2;
+  if (g.use_tc && (dev_alloc(&g.Xh, nd) || dev_alloc(&g.Xl, nd) || dev_alloc(&g.XTh, nd) || dev_alloc(&g.XTl, nd))) return 2;
+  pad_transpose_split_kernel<<<(unsigned)((nd + 255) / 256), 256>>>(X, N, D, g.Np, g.Dp, g.X, g.XT, g.Xh, g.Xl, g.XTh, g.XTl);
+  pad_vector_kernel<<<(g.Np + 255) / 256, 256>>>(y, N, g.Np, g.y);
+  g_launches += 2;
+  B2M_CHECK_CUDA(cudaGetLastError());
+  B2M_CHECK_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+// ---------------------------------------------------------------- pack: theta -> B (+ tf32 split), 1/sigma^2
+__global__ void glm_pack_kernel(const float *__restrict__ theta, int64_t C, int64_t Cp, int Dtot, int beta_off, int D,
+                                int Dp, int sigma_param, float sigma_const, float *B, float *Bh, float *Bl,
+                                float *inv_var) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cp * Dp) return;
+  const int64_t c = i / Dp;
+  const int d = int(i % Dp);
+  const float v = (c < C && d < D) ? theta[c * Dtot + beta_off + d] : 0.f;
+  B[i] = v;
+  if (Bh) {
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    Bh[i] = hi; Bl[i] = lo;
+  }
+  if (d == 0) {
+    const float s = (c < C && sigma_param >= 0) ? theta[c * Dtot + sigma_param] : sigma_const;
+    inv_var[c] = 1.0f / (s * s);
+  }
+}
+
+// ---------------------------------------------------------------- SIMT contractions (fp32, 64x64x16 tiles)
+// C[m, n] = sum_k A[m, k] * Bm[n, k]; both operands K-major; all dimensions padded to the tile.
+constexpr int TM = 64, TN = 64, TK = 16;
+
+template <bool RESID>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const float *__restrict__ A, const float *__restrict__ Bm,
+                                                        int K, int lda, int ldb, float *__restrict__ Cout, int ldc,
+                                                        const float *__restrict__ y, const float *__restrict__ inv_var,
+                                                        float *__restrict__ ss_part, int64_t Cp, int N_valid,
+                                                        float loc_const, float weight) {
+  __shared__ float sA[TK][TM + 4], sB[TK][TN + 4];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  float acc[4][4] = {};
+  const int lr = tid / 4, lc = (tid % 4) * 4;  // each thread loads one float4 of A and one of Bm per k-step
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    const float4 a = *reinterpret_cast<const float4 *>(A + (int64_t)(m0 + lr) * lda + k0 + lc);
+    const float4 b = *reinterpret_cast<const float4 *>(Bm + (int64_t)(n0 + lr) * ldb + k0 + lc);
+    sA[lc + 0][lr] = a.x; sA[lc + 1][lr] = a.y; sA[lc + 2][lr] = a.z; sA[lc + 3][lr] = a.w;
+    sB[lc + 0][lr] = b.x; sB[lc + 1][lr] = b.y; sB[lc + 2][lr] = b.z; sB[lc + 3][lr] = b.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = sA[k][ty * 4 + i]; bv[i] = sB[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  if (RESID) {
+    // epilogue: z = y - c - M ; R = w z / sigma^2 ; per-row partial sum of z^2 over this column tile
+    __shared__ float red[TM][17];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      const float iv = inv_var[m] * weight;
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        const float z = (n < N_valid) ? (y[n] - loc_const) - acc[i][j] : 0.f;
+        s = fmaf(z, z, s);
+        acc[i][j] = z * iv;
+      }
+      *reinterpret_cast<float4 *>(Cout + (int64_t)m * ldc + n0 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      red[ty * 4 + i][tx] = s;
+    }
+    __syncthreads();
+    if (tid < TM) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s += red[tid][j];
+      ss_part[(int64_t)blockIdx.x * Cp + m0 + tid] = s;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4 *>(Cout + (int64_t)(m0 + ty * 4 + i) * ldc + n0 + tx * 4) =
+          make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+}
+
+int simt_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st) {
+  dim3 grid(g.Np / TN, (unsigned)(Cp / TM));
+  simt_gemm_kernel<true><<<grid, 256, 0, st>>>(g.B, g.X, g.Dp, g.Dp, g.Dp, g.R, g.Np, g.y, g.inv_var, g.ss_part, Cp,
+                                                g.N, g.loc_const, g.weight);
+  ++g_launches;
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int simt_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
+  dim3 grid(g.Dp / TN, (unsigned)(Cp / TM));
+  simt_gemm_kernel<false><<<grid, 256, 0, st>>>(g.R, g.XT, g.Np, g.Np, g.Np, g.G, g.Dp, nullptr, nullptr, nullptr, Cp,
+                                                 0, 0.f, 0.f);
+  ++g_launches;
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------- finish: assemble log p and the full gradient
+// One warp per chain.  Likelihood value from the partial sums (fixed summation order => deterministic),
+// gradient of beta from G, gradient of sigma analytically, then the prior terms (generic densities)
+// added on top.  n_tiles = number of 64-wide column tiles that wrote ss_part.
+__global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_prior, const float *__restrict__ theta,
+                                                          int64_t C, int64_t Cp, int Dtot, int beta_off, int D, int Dp,
+                                                          int sigma_param, float sigma_const, float weight, int N,
+                                                          int n_tiles, const float *__restrict__ ss_part,
+                                                          const float *__restrict__ G, float *__restrict__ logp,
+                                                          float *__restrict__ grad) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SModel sm;
+  sm.n_terms = 0;
+  if (has_prior) model_to_smem(prior, smem, sm);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t c = (int64_t)blockIdx.x * (blockDim.x / 32) + warp;
+  if (c >= C) return;
+  const float *th = theta + c * Dtot;
+  float ss = 0.f;
+  for (int t = lane; t < n_tiles; t += 32) ss += ss_part[(int64_t)t * Cp + c];
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float sg = sigma_param >= 0 ? th[sigma_param] : sigma_const;
+  const float iv = 1.0f / (sg * sg);
+  float lp = weight * ((float)N * (-kHalfLog2Pi - logf(sg)) - 0.5f * ss * iv);
+  float *gr = grad ? grad + c * Dtot : nullptr;
+  if (gr) {
+    for (int d = lane; d < Dtot; d += 32) {
+      float v = 0.f;
+      if (d >= beta_off && d < beta_off + D) v = G[c * Dp + (d - beta_off)];
+      if (d == sigma_param) v = weight * (ss * iv - (float)N) / sg;
+      gr[d] = v;
+    }
+    __syncwarp();
+  }
+  // priors: lanes stride the elements of each term; each element touches its own theta entries
+  float pl = 0.f;
+  for (int t = 0; t < sm.n_terms; ++t) {
+    const b2m_term &T = sm.terms[t];
+    float acc = 0.f, ax = 0.f, a0 = 0.f, a1 = 0.f;
+    for (int n = lane; n < T.length; n += 32) {
+      const float x = op_fetch(T.x, n, th, 1, sm), p0 = op_fetch(T.p0, n, th, 1, sm), p1 = op_fetch(T.p1, n, th, 1, sm);
+      Elem e = dist_eval<true>(T.dist, x, p0, p1, T.k0, T.k1, T.k2);
+      acc += e.lp;
+      if (gr) {
+        if (T.x.kind == B2M_OP_PARAM) ax += e.dx; else if (T.x.kind == B2M_OP_PARAMVEC) gr[T.x.a + n] += T.weight * e.dx;
+        if (T.p0.kind == B2M_OP_PARAM) a0 += e.d0; else if (T.p0.kind == B2M_OP_PARAMVEC) gr[T.p0.a + n] += T.weight * e.d0;
+        if (T.p1.kind == B2M_OP_PARAM) a1 += e.d1; else if (T.p1.kind == B2M_OP_PARAMVEC) gr[T.p1.a + n] += T.weight * e.d1;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      ax += __shfl_xor_sync(0xffffffffu, ax, o);
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    pl += T.weight * acc;
+    if (gr && lane == 0) {
+      if (T.x.kind == B2M_OP_PARAM) gr[T.x.a] += T.weight * ax;
+      if (T.p0.kind == B2M_OP_PARAM) gr[T.p0.a] += T.weight * a0;
+      if (T.p1.kind == B2M_OP_PARAM) gr[T.p1.a] += T.weight * a1;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) logp[c] = lp + pl;
+}
+
+int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st) {
+  if (int rc = glm_reserve(g, C)) return rc;
+  const int64_t Cp = (C + 127) / 128 * 128;
+  const int64_t tot = Cp * g.Dp;
+  glm_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
+                                                                  g.sigma_param, g.sigma_const, g.B, g.Bh, g.Bl, g.inv_var);
+  ++g_launches;
+  int n_tiles;
+  if (g.use_tc) {
+    if (int rc = tc_gemm_resid(g, Cp, st)) return rc;
+    if (grad) if (int rc = tc_gemm_grad(g, Cp, st)) return rc;
+    n_tiles = g.Np / 256;
+  } else {
+    if (int rc = simt_gemm_resid(g, Cp, st)) return rc;
+    if (grad) if (int rc = simt_gemm_grad(g, Cp, st)) return rc;
+    n_tiles = g.Np / TN;
+  }
+  const size_t smem = g.has_prior ? model_smem_bytes(g.prior) : 16;
+  glm_finish_kernel<<<(unsigned)((C + 3) / 4), 128, smem, st>>>(g.prior, g.has_prior ? 1 : 0, theta, C, Cp, g.Dtot, g.beta_off,
+                                                                 g.D, g.Dp, g.sigma_param, g.sigma_const, g.weight, g.N,
+                                                                 n_tiles, g.ss_part, g.G, logp, grad);
+  ++g_launches;
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b2m

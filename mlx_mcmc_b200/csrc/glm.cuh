@@ -1,0 +1,69 @@
+// GLM-class models: log p(theta) = priors(theta) + w * sum_n Normal(y_n | c + (X @ beta)_n, sigma)
+// with beta a slice of theta and sigma a constant or a scalar parameter.
+//
+// The gradient of the likelihood is two dense contractions shared by all chains of a lock-step batch:
+//     M = B X^T     [C, D] x [D, N]   -> residual epilogue  R = w (y - c - M) / sigma_c^2,  ss_c = sum_n (y - c - M)^2
+//     G = R X       [C, N] x [N, D]
+// (K5 / K6 of SURVEY.md 2b).  Two implementations sit behind the same interface:
+//   * fp32 SIMT tiles (glm_simt.cu)    -- any shape, the validation path
+//   * TMA + tcgen05 3xTF32 (glm_tc.cu) -- B, X, R split into tf32 hi + lo parts, fp32 accumulation in TMEM
+#pragma once
+#include "model.cuh"
+
+namespace b2m {
+
+struct GlmModel {
+  // problem
+  int N = 0, D = 0;        // observations, regression coefficients
+  int Np = 0, Dp = 0;      // padded: Np % 256 == 0, Dp % 64 == 0 (zero padded)
+  int Dtot = 0;            // full parameter count
+  int beta_off = 0;        // beta = theta[beta_off : beta_off + D]
+  int sigma_param = -1;    // index of sigma in theta, or -1 when constant
+  float sigma_const = 1.f, loc_const = 0.f, weight = 1.f;
+  // observed data in HBM (owned by the handle)
+  float *X = nullptr, *XT = nullptr;                         // [Np, Dp], [Dp, Np] fp32
+  float *Xh = nullptr, *Xl = nullptr, *XTh = nullptr, *XTl = nullptr;  // tf32 hi / lo splits
+  float *y = nullptr;                                        // [Np]
+  // prior terms (everything except the matvec likelihood) as a pointwise term table
+  KModel prior{};
+  bool has_prior = false;
+  // workspace sized for `cap` chains (padded to 128)
+  int64_t cap = 0;
+  float *B = nullptr, *Bh = nullptr, *Bl = nullptr;          // [cap, Dp]
+  float *R = nullptr, *Rh = nullptr, *Rl = nullptr;          // [cap, Np]
+  float *G = nullptr;                                        // [cap, Dp]
+  float *ss_part = nullptr;                                  // [Np / 64, cap] per-column-tile partial sum of squares
+  float *inv_var = nullptr;                                  // [cap]
+  int use_tc = 0;                                            // 1: tcgen05 path, 0: SIMT path
+};
+
+int glm_reserve(GlmModel &g, int64_t n_chains);
+void glm_free(GlmModel &g);
+
+// log p and gradient for `theta` [C, Dtot] (device).  grad may be NULL.
+int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st);
+
+// the two contractions (SIMT implementation)
+int simt_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st);   // B -> R, ss_part
+int simt_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st);    // R -> G
+// tcgen05 implementation (glm_tc.cu)
+int tc_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st);
+int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st);
+bool tc_available();
+
+int glm_hmc_run(GlmModel &g, const b2m_hmc_args &a, cudaStream_t st);
+int glm_nuts_run(GlmModel &g, const b2m_nuts_args &a, cudaStream_t st);
+int glm_mh_run(GlmModel &g, const b2m_mh_args &a, cudaStream_t st);
+
+// round-to-nearest split of an fp32 value into two tf32-representable parts, x ~= hi + lo
+__host__ __device__ inline void split_tf32(float x, float &hi, float &lo) {
+  union { float f; uint32_t u; } a, b;
+  a.f = x;
+  a.u = (a.u + 0x00001000u) & 0xffffe000u;
+  hi = a.f;
+  b.f = x - hi;
+  b.u = (b.u + 0x00001000u) & 0xffffe000u;
+  lo = b.f;
+}
+
+}  // namespace b2m

@@ -1,0 +1,570 @@
+// Lock-step samplers for GLM-class models: chain state lives in HBM as [C, Dtot] arrays, every leapfrog
+// step of every chain shares one pair of dense contractions (glm_logp_grad), and small per-chain kernels
+// (one warp per chain) do the integrator arithmetic, energies, U-turn dot products and tree bookkeeping.
+//
+// Replaces the same reference code as the pointwise kernels: kernels/hmc.py:113-198, kernels/nuts.py:137-343,
+// kernels/metropolis.py:64-92.  The NUTS tree is the iterative restatement of build_tree: one
+// leaf per lock-step, per-chain masks for chains whose subtree / trajectory has ended.
+#include <vector>
+
+#include "glm.cuh"
+
+namespace b2m {
+
+constexpr int WPB = 4;  // warps (= chains) per block
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// N(0,1) for dimension d of (chain, iteration) -- same slot map as the pointwise kernels (common.cuh)
+__device__ __forceinline__ void normals4(uint64_t seed, uint64_t gchain, uint32_t giter, int group, float out[4]) {
+  // group 0 -> dims 2..5, group k -> dims 2+4k .. 5+4k (slot 1+k)
+  const uint4 w = Philox::draw(seed, gchain, giter, 1u + (uint32_t)group);
+  box_muller(w.x, w.y, out[0], out[1]);
+  box_muller(w.z, w.w, out[2], out[3]);
+}
+
+__device__ inline void fill_momentum(float *p, int D, const float *inj, uint64_t seed, uint64_t gchain, uint32_t giter,
+                                     uint4 w0, int lane) {
+  if (inj) {
+    for (int d = lane; d < D; d += 32) p[d] = inj[d];
+    return;
+  }
+  if (lane == 0) {
+    float a, b;
+    box_muller(w0.x, w0.y, a, b);
+    p[0] = a;
+    if (D > 1) p[1] = b;
+  }
+  for (int grp = lane; 2 + 4 * grp < D; grp += 32) {
+    float z[4];
+    normals4(seed, gchain, giter, grp, z);
+    for (int i = 0; i < 4; ++i)
+      if (2 + 4 * grp + i < D) p[2 + 4 * grp + i] = z[i];
+  }
+}
+
+__device__ __forceinline__ float kinetic_w(const float *p, int D, int lane) {
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) s = fmaf(p[d], p[d], s);
+  return 0.5f * warp_sum(s);
+}
+
+#define CHAIN_PROLOGUE(C)                                                        \
+  const int lane = threadIdx.x & 31;                                             \
+  const int64_t c = (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5);              \
+  if (c >= (C)) return;
+
+// ================================================================= HMC
+struct HmcBufs {
+  float *p, *g, *qn, *gn, *lp, *lpn, *h0;
+};
+
+__global__ void __launch_bounds__(32 * WPB) hmc_begin_kernel(b2m_hmc_args A, HmcBufs W, int D, int it) {
+  CHAIN_PROLOGUE(A.n_chains)
+  const uint64_t gchain = (uint64_t)(A.chain_offset + c);
+  const uint32_t giter = (uint32_t)(A.iter_offset + it);
+  const size_t row = (size_t)it * A.n_chains + c;
+  float *p = W.p + c * D, *qn = W.qn + c * D;
+  const float *q = A.theta + c * D, *g = W.g + c * D;
+  const uint4 w0 = Philox::draw(A.seed, gchain, giter, 0u);
+  fill_momentum(p, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0, lane);
+  __syncwarp();
+  const float kin = kinetic_w(p, D, lane);
+  if (lane == 0) W.h0[c] = -W.lp[c] + kin;
+  const double eps = A.step_size[c];
+  const float he = (float)(0.5 * eps), fe = (float)eps;
+  for (int d = lane; d < D; d += 32) {
+    const float pv = __fadd_rn(p[d], __fmul_rn(he, g[d]));
+    p[d] = pv;
+    qn[d] = __fadd_rn(q[d], __fmul_rn(fe, pv));
+  }
+}
+
+// between two leapfrog steps: second half kick of step l, first half kick + drift of step l+1
+__global__ void __launch_bounds__(32 * WPB) hmc_mid_kernel(b2m_hmc_args A, HmcBufs W, int D) {
+  CHAIN_PROLOGUE(A.n_chains)
+  float *p = W.p + c * D, *qn = W.qn + c * D;
+  const float *gn = W.gn + c * D;
+  const double eps = A.step_size[c];
+  const float he = (float)(0.5 * eps), fe = (float)eps;
+  for (int d = lane; d < D; d += 32) {
+    float pv = __fadd_rn(p[d], __fmul_rn(he, gn[d]));
+    pv = __fadd_rn(pv, __fmul_rn(he, gn[d]));
+    p[d] = pv;
+    qn[d] = __fadd_rn(qn[d], __fmul_rn(fe, pv));
+  }
+}
+
+__global__ void __launch_bounds__(32 * WPB) hmc_end_kernel(b2m_hmc_args A, HmcBufs W, int D, int it) {
+  CHAIN_PROLOGUE(A.n_chains)
+  const uint64_t gchain = (uint64_t)(A.chain_offset + c);
+  const uint32_t giter = (uint32_t)(A.iter_offset + it);
+  const size_t row = (size_t)it * A.n_chains + c;
+  float *p = W.p + c * D, *q = A.theta + c * D, *g = W.g + c * D;
+  const float *qn = W.qn + c * D, *gn = W.gn + c * D;
+  double eps = A.step_size[c];
+  const float he = (float)(0.5 * eps);
+  for (int d = lane; d < D; d += 32) p[d] = __fadd_rn(p[d], __fmul_rn(he, gn[d]));
+  __syncwarp();
+  const float kin = kinetic_w(p, D, lane);
+  const float h0 = W.h0[c], h1 = -W.lpn[c] + kin;
+  float u;
+  if (A.inj_uniform) u = A.inj_uniform[row];
+  else u = u01(Philox::draw(A.seed, gchain, giter, 0u).z);
+  const float log_ratio = -(h1 - h0);
+  const bool accept = logf(u) < log_ratio;
+  if (accept) {
+    for (int d = lane; d < D; d += 32) { q[d] = qn[d]; g[d] = gn[d]; }
+  }
+  if (lane == 0) {
+    if (accept) W.lp[c] = W.lpn[c];
+    int64_t n_acc = A.n_accept[c] + (accept ? 1 : 0), n_tot = A.n_total[c] + 1;
+    A.n_accept[c] = n_acc;
+    A.n_total[c] = n_tot;
+    if (A.adapt == B2M_ADAPT_REFERENCE) {
+      if ((int64_t)giter > 10) eps *= ((double)n_acc / (double)n_tot < A.target_accept) ? 0.95 : 1.05;
+      A.step_size[c] = eps;
+    } else if (A.adapt == B2M_ADAPT_DUAL_AVERAGING) {
+      double h_bar = A.da_state[c * 3 + 0], log_eps_bar = A.da_state[c * 3 + 1];
+      const double mu = A.da_state[c * 3 + 2];
+      const float a = (log_ratio == log_ratio) ? expf(fminf(log_ratio, 0.f)) : 0.f;
+      const double m = (double)giter + 1.0, eta = 1.0 / (m + 10.0);
+      h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - (double)a);
+      double log_eps = mu - sqrt(m) / 0.05 * h_bar;
+      log_eps = fmin(fmax(log_eps, -10.0), 10.0);
+      const double wt = pow(m, -0.75);
+      log_eps_bar = wt * log_eps + (1.0 - wt) * log_eps_bar;
+      A.step_size[c] = exp(log_eps);
+      A.da_state[c * 3 + 0] = h_bar;
+      A.da_state[c * 3 + 1] = log_eps_bar;
+    }
+    if (A.trace_energy) { A.trace_energy[row * 2] = h0; A.trace_energy[row * 2 + 1] = h1; }
+    if (A.trace_accept) A.trace_accept[row] = accept ? 1 : 0;
+  }
+  if (A.draws) {
+    __syncwarp();
+    for (int d = lane; d < D; d += 32) A.draws[row * D + d] = q[d];
+  }
+}
+
+template <typename T>
+static int tmp_alloc(std::vector<void *> &pool, T **p, size_t n) {
+  B2M_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(p), sizeof(T) * (n ? n : 1)));
+  pool.push_back(*p);
+  return 0;
+}
+static void tmp_free(std::vector<void *> &pool) {
+  for (void *p : pool) cudaFree(p);
+  pool.clear();
+}
+
+int glm_hmc_run(GlmModel &gm, const b2m_hmc_args &a, cudaStream_t st) {
+  const int64_t C = a.n_chains;
+  const int D = gm.Dtot;
+  std::vector<void *> pool;
+  HmcBufs W{};
+  if (tmp_alloc(pool, &W.p, C * D) || tmp_alloc(pool, &W.g, C * D) || tmp_alloc(pool, &W.qn, C * D) ||
+      tmp_alloc(pool, &W.gn, C * D) || tmp_alloc(pool, &W.lp, C) || tmp_alloc(pool, &W.lpn, C) || tmp_alloc(pool, &W.h0, C)) {
+    tmp_free(pool);
+    return 2;
+  }
+  const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
+  int rc = glm_logp_grad(gm, a.theta, C, W.lp, W.g, st);
+  for (int it = 0; it < a.n_iter && !rc; ++it) {
+    hmc_begin_kernel<<<grid, 32 * WPB, 0, st>>>(a, W, D, it);
+    ++g_launches;
+    for (int l = 0; l < a.n_leapfrog && !rc; ++l) {
+      rc = glm_logp_grad(gm, W.qn, C, W.lpn, W.gn, st);
+      if (l + 1 < a.n_leapfrog) {
+        hmc_mid_kernel<<<grid, 32 * WPB, 0, st>>>(a, W, D);
+        ++g_launches;
+      }
+    }
+    hmc_end_kernel<<<grid, 32 * WPB, 0, st>>>(a, W, D, it);
+    ++g_launches;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  tmp_free(pool);
+  if (rc) return rc;
+  B2M_CHECK_CUDA(e);
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================= Metropolis
+__global__ void __launch_bounds__(32 * WPB) mh_propose_kernel(b2m_mh_args A, float *qn, int D, int it) {
+  CHAIN_PROLOGUE(A.n_chains)
+  const uint64_t gchain = (uint64_t)(A.chain_offset + c);
+  const uint32_t giter = (uint32_t)(A.iter_offset + it);
+  const size_t row = (size_t)it * A.n_chains + c;
+  float *z = qn + c * D;
+  const float *q = A.theta + c * D;
+  const uint4 w0 = Philox::draw(A.seed, gchain, giter, 0u);
+  fill_momentum(z, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0, lane);
+  __syncwarp();
+  for (int d = lane; d < D; d += 32) z[d] = __fadd_rn(q[d], __fmul_rn(z[d], A.proposal_scale));
+}
+
+__global__ void __launch_bounds__(32 * WPB) mh_accept_kernel(b2m_mh_args A, const float *qn, const float *lpn, int D, int it) {
+  CHAIN_PROLOGUE(A.n_chains)
+  const uint64_t gchain = (uint64_t)(A.chain_offset + c);
+  const uint32_t giter = (uint32_t)(A.iter_offset + it);
+  const size_t row = (size_t)it * A.n_chains + c;
+  float *q = A.theta + c * D;
+  float u;
+  if (A.inj_uniform) u = A.inj_uniform[row];
+  else u = u01(Philox::draw(A.seed, gchain, giter, 0u).z);
+  const bool accept = logf(u) < __fsub_rn(lpn[c], A.logp[c]);
+  if (accept)
+    for (int d = lane; d < D; d += 32) q[d] = qn[c * D + d];
+  __syncwarp();
+  if (lane == 0) {
+    if (accept) { A.logp[c] = lpn[c]; A.n_accept[c] += 1; }
+    if (A.trace_accept) A.trace_accept[row] = accept ? 1 : 0;
+  }
+  if (A.draws)
+    for (int d = lane; d < D; d += 32) A.draws[row * D + d] = q[d];
+}
+
+int glm_mh_run(GlmModel &gm, const b2m_mh_args &a, cudaStream_t st) {
+  const int64_t C = a.n_chains;
+  const int D = gm.Dtot;
+  std::vector<void *> pool;
+  float *qn, *lpn;
+  if (tmp_alloc(pool, &qn, C * D) || tmp_alloc(pool, &lpn, C)) { tmp_free(pool); return 2; }
+  const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
+  // the cached current log-prob is recomputed at the start of every call, as metropolis.py:55 does
+  int rc = glm_logp_grad(gm, a.theta, C, a.logp, nullptr, st);
+  for (int it = 0; it < a.n_iter && !rc; ++it) {
+    mh_propose_kernel<<<grid, 32 * WPB, 0, st>>>(a, qn, D, it);
+    rc = glm_logp_grad(gm, qn, C, lpn, nullptr, st);
+    mh_accept_kernel<<<grid, 32 * WPB, 0, st>>>(a, qn, lpn, D, it);
+    g_launches += 2;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  tmp_free(pool);
+  if (rc) return rc;
+  B2M_CHECK_CUDA(e);
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================= NUTS
+struct NutsBufs {
+  // [C, D] vectors
+  float *g, *p0, *q_lo, *p_lo, *g_lo, *q_hi, *p_hi, *g_hi, *cq, *cg, *fq, *fp, *fg, *sfq, *sfp, *scq, *scg;
+  float *st_fq, *st_fp, *st_cq, *st_cg;  // [MD, C, D] stack of parked left subtrees
+  // [C] scalars
+  float *lp, *clp, *h0, *log_slice, *flp, *sclp, *feps, *heps;
+  int *n, *s, *v, *leaf, *building, *sub_n, *sub_na, *sub_s, *alpha_cnt, *depth;
+  double *alpha_sum, *sub_alpha;
+  // [MD, C] stack scalars
+  float *st_clp;
+  int *st_n, *st_na;
+  double *st_alpha;
+  int *any_active;  // device flag
+};
+
+__device__ __forceinline__ void vcopy(float *dst, const float *src, int D, int lane) {
+  for (int d = lane; d < D; d += 32) dst[d] = src[d];
+}
+
+// continue-straight test of nuts.py:119-135 on [D] vectors (warp reduction)
+__device__ __forceinline__ bool straight_w(const float *q_lo, const float *q_hi, const float *p_lo, const float *p_hi,
+                                           int D, int lane) {
+  float a = 0.f, b = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float dq = q_hi[d] - q_lo[d];
+    a = fmaf(dq, p_lo[d], a);
+    b = fmaf(dq, p_hi[d], b);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  return a >= 0.f && b >= 0.f;
+}
+
+__global__ void __launch_bounds__(32 * WPB) nuts_begin_kernel(b2m_nuts_args A, NutsBufs W, int D, int it) {
+  CHAIN_PROLOGUE(A.n_chains)
+  const uint64_t gchain = (uint64_t)(A.chain_offset + c);
+  const uint32_t giter = (uint32_t)(A.iter_offset + it);
+  const size_t row = (size_t)it * A.n_chains + c;
+  const size_t o = (size_t)c * D;
+  const uint4 w0 = Philox::draw(A.seed, gchain, giter, 0u);
+  fill_momentum(W.p0 + o, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0, lane);
+  __syncwarp();
+  const float kin = kinetic_w(W.p0 + o, D, lane);
+  const float *q = A.theta + o;
+  vcopy(W.q_lo + o, q, D, lane); vcopy(W.q_hi + o, q, D, lane);
+  vcopy(W.p_lo + o, W.p0 + o, D, lane); vcopy(W.p_hi + o, W.p0 + o, D, lane);
+  vcopy(W.g_lo + o, W.g + o, D, lane); vcopy(W.g_hi + o, W.g + o, D, lane);
+  vcopy(W.cq + o, q, D, lane); vcopy(W.cg + o, W.g + o, D, lane);
+  if (lane == 0) {
+    const float h0 = -W.lp[c] + kin;
+    const float us = A.inj_slice ? A.inj_slice[row] : u01(w0.z);
+    const double log_u64 = (double)(-h0) + (double)logf(us);
+    W.h0[c] = h0;
+    W.log_slice[c] = A.compat == B2M_COMPAT_REFERENCE ? logf(expf((float)log_u64)) : (float)log_u64;
+    W.clp[c] = W.lp[c];
+    W.n[c] = 1; W.s[c] = 1; W.alpha_sum[c] = 0.0; W.alpha_cnt[c] = 0; W.depth[c] = 0; W.building[c] = 0;
+    if (A.trace_energy) A.trace_energy[row] = h0;
+  }
+}
+
+__global__ void __launch_bounds__(32 * WPB) nuts_doubling_begin_kernel(b2m_nuts_args A, NutsBufs W, int D, int it, int j) {
+  CHAIN_PROLOGUE(A.n_chains)
+  if (!W.s[c]) { if (lane == 0) W.building[c] = 0; return; }
+  const uint64_t gchain = (uint64_t)(A.chain_offset + c);
+  const uint32_t giter = (uint32_t)(A.iter_offset + it);
+  const size_t row = (size_t)it * A.n_chains + c;
+  const size_t o = (size_t)c * D;
+  float ud;
+  if (A.inj_dir) ud = A.inj_dir[row * A.max_tree_depth + j];
+  else ud = u01(Philox::draw(A.seed, gchain, giter, SLOT_NUTS_DOUBLING + j).x);
+  const int v = ud < 0.5f ? 1 : -1;
+  if (v == 1) { vcopy(W.fq + o, W.q_hi + o, D, lane); vcopy(W.fp + o, W.p_hi + o, D, lane); vcopy(W.fg + o, W.g_hi + o, D, lane); }
+  else        { vcopy(W.fq + o, W.q_lo + o, D, lane); vcopy(W.fp + o, W.p_lo + o, D, lane); vcopy(W.fg + o, W.g_lo + o, D, lane); }
+  if (lane == 0) {
+    const double eps = A.step_size[c];
+    W.v[c] = v;
+    W.feps[c] = (float)((double)v * eps);
+    W.heps[c] = (float)(0.5 * ((double)v * eps));
+    W.leaf[c] = 0;
+    W.building[c] = 1;
+  }
+}
+
+__global__ void __launch_bounds__(32 * WPB) nuts_leaf_pre_kernel(b2m_nuts_args A, NutsBufs W, int D) {
+  CHAIN_PROLOGUE(A.n_chains)
+  if (!W.building[c]) return;
+  const size_t o = (size_t)c * D;
+  const float he = W.heps[c], fe = W.feps[c];
+  float *fq = W.fq + o, *fp = W.fp + o;
+  const float *fg = W.fg + o;
+  for (int d = lane; d < D; d += 32) {
+    const float pv = __fadd_rn(fp[d], __fmul_rn(he, fg[d]));
+    fp[d] = pv;
+    fq[d] = __fadd_rn(fq[d], __fmul_rn(fe, pv));
+  }
+}
+
+__global__ void __launch_bounds__(32 * WPB) nuts_leaf_post_kernel(b2m_nuts_args A, NutsBufs W, int D, int it, int j) {
+  CHAIN_PROLOGUE(A.n_chains)
+  if (!W.building[c]) return;
+  const int64_t C = A.n_chains;
+  const uint64_t gchain = (uint64_t)(A.chain_offset + c);
+  const uint32_t giter = (uint32_t)(A.iter_offset + it);
+  const size_t row = (size_t)it * C + c;
+  const size_t o = (size_t)c * D;
+  const int MD = A.max_tree_depth;
+  const bool ref_compat = A.compat == B2M_COMPAT_REFERENCE;
+  float *fq = W.fq + o, *fp = W.fp + o;
+  const float *fg = W.fg + o;
+  const float he = W.heps[c];
+  for (int d = lane; d < D; d += 32) fp[d] = __fadd_rn(fp[d], __fmul_rn(he, fg[d]));
+  __syncwarp();
+  const float kin = kinetic_w(fp, D, lane);
+  const float flp = W.flp[c], h0 = W.h0[c], log_slice = W.log_slice[c];
+  const float h1 = -flp + kin;
+  const int n1 = (log_slice <= -h1) ? 1 : 0;
+  const bool s1 = log_slice < (1000.0f - h1);
+  float a1 = expf(-h1 + h0);
+  if (a1 != a1) a1 = ref_compat ? 1.0f : 0.0f;
+  a1 = fminf(a1, 1.0f);
+  const int v = W.v[c], i = W.leaf[c];
+  if (lane == 0) {
+    A.n_leaves[c] += 1;
+    if (!s1) A.n_diverge[c] += 1;
+  }
+  // the subtree being assembled = this leaf
+  vcopy(W.sfq + o, fq, D, lane); vcopy(W.sfp + o, fp, D, lane);
+  vcopy(W.scq + o, fq, D, lane); vcopy(W.scg + o, fg, D, lane);
+  __syncwarp();
+  float sub_clp = flp;
+  int sub_n = n1, sub_na = 1;
+  bool sub_s = s1;
+  double sub_alpha = (double)a1;
+  int k = 0;
+  bool finished = false;
+  while (true) {
+    if (k == j) { finished = true; break; }
+    const size_t so = ((size_t)k * C + c) * D, ss = (size_t)k * C + c;
+    if ((i >> k) & 1) {
+      const int m = i - __popc(i) + k;
+      float um;
+      if (A.inj_merge) {
+        um = A.inj_merge[(row * MD + j) * ((1 << MD) - 1) + m];
+      } else {
+        const uint4 wm = Philox::draw(A.seed, gchain, giter, SLOT_NUTS_MERGE + 1024u * j + (m >> 2));
+        const uint32_t word = (m & 3) == 0 ? wm.x : (m & 3) == 1 ? wm.y : (m & 3) == 2 ? wm.z : wm.w;
+        um = u01(word);
+      }
+      const int n_tot = W.st_n[ss] + sub_n;
+      const double ratio = (double)sub_n / fmax((double)n_tot, 1.0);
+      if (!((double)um < ratio)) {
+        vcopy(W.scq + o, W.st_cq + so, D, lane); vcopy(W.scg + o, W.st_cg + so, D, lane);
+        sub_clp = W.st_clp[ss];
+      }
+      bool st;
+      if (v == 1) st = straight_w(W.st_fq + so, fq, W.st_fp + so, fp, D, lane);
+      else        st = straight_w(fq, W.st_fq + so, fp, W.st_fp + so, D, lane);
+      sub_s = sub_s && st;
+      vcopy(W.sfq + o, W.st_fq + so, D, lane); vcopy(W.sfp + o, W.st_fp + so, D, lane);
+      __syncwarp();
+      sub_n = n_tot;
+      sub_alpha = W.st_alpha[ss] + sub_alpha;
+      sub_na = W.st_na[ss] + sub_na;
+      ++k;
+    } else {
+      if (sub_s) {
+        vcopy(W.st_fq + so, W.sfq + o, D, lane); vcopy(W.st_fp + so, W.sfp + o, D, lane);
+        vcopy(W.st_cq + so, W.scq + o, D, lane); vcopy(W.st_cg + so, W.scg + o, D, lane);
+        if (lane == 0) { W.st_clp[ss] = sub_clp; W.st_n[ss] = sub_n; W.st_na[ss] = sub_na; W.st_alpha[ss] = sub_alpha; }
+        break;
+      }
+      ++k;
+    }
+  }
+  if (lane == 0) {
+    if (finished) {
+      W.building[c] = 0;
+      W.sclp[c] = sub_clp; W.sub_n[c] = sub_n; W.sub_na[c] = sub_na; W.sub_s[c] = sub_s ? 1 : 0; W.sub_alpha[c] = sub_alpha;
+    } else {
+      W.leaf[c] = i + 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32 * WPB) nuts_doubling_end_kernel(b2m_nuts_args A, NutsBufs W, int D, int it, int j) {
+  CHAIN_PROLOGUE(A.n_chains)
+  if (!W.s[c]) return;  // chain was not growing in this doubling
+  const uint64_t gchain = (uint64_t)(A.chain_offset + c);
+  const uint32_t giter = (uint32_t)(A.iter_offset + it);
+  const size_t row = (size_t)it * A.n_chains + c;
+  const size_t o = (size_t)c * D;
+  const int v = W.v[c];
+  if (v == 1) { vcopy(W.q_hi + o, W.fq + o, D, lane); vcopy(W.p_hi + o, W.fp + o, D, lane); vcopy(W.g_hi + o, W.fg + o, D, lane); }
+  else        { vcopy(W.q_lo + o, W.fq + o, D, lane); vcopy(W.p_lo + o, W.fp + o, D, lane); vcopy(W.g_lo + o, W.fg + o, D, lane); }
+  const int sub_n = W.sub_n[c], sub_s = W.sub_s[c];
+  const int n = W.n[c];
+  int took = 0;
+  if (sub_s) {
+    float ut;
+    if (A.inj_take) ut = A.inj_take[row * A.max_tree_depth + j];
+    else ut = u01(Philox::draw(A.seed, gchain, giter, SLOT_NUTS_DOUBLING + j).y);
+    const double pr = fmin(1.0, (double)sub_n / fmax((double)n, 1.0));
+    if ((double)ut < pr) {
+      vcopy(W.cq + o, W.scq + o, D, lane); vcopy(W.cg + o, W.scg + o, D, lane);
+      took = 1;
+    }
+  }
+  __syncwarp();
+  const bool st = straight_w(W.q_lo + o, W.q_hi + o, W.p_lo + o, W.p_hi + o, D, lane);
+  const int s_new = (sub_s && st) ? 1 : 0;
+  if (lane == 0) {
+    if (took) W.clp[c] = W.sclp[c];
+    W.n[c] = n + sub_n;
+    W.s[c] = s_new;
+    W.alpha_sum[c] += W.sub_alpha[c];
+    W.alpha_cnt[c] += W.sub_na[c];
+    W.depth[c] = j + 1;
+    if (s_new && j + 1 < A.max_tree_depth) atomicOr(W.any_active, 1);
+    if (A.trace_doubling) {
+      int32_t *tr = A.trace_doubling + ((size_t)row * A.max_tree_depth + j) * 6;
+      tr[0] = v; tr[1] = sub_n; tr[2] = sub_s; tr[3] = took; tr[4] = s_new; tr[5] = n + sub_n;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32 * WPB) nuts_end_kernel(b2m_nuts_args A, NutsBufs W, int D, int it) {
+  CHAIN_PROLOGUE(A.n_chains)
+  const uint32_t giter = (uint32_t)(A.iter_offset + it);
+  const size_t row = (size_t)it * A.n_chains + c;
+  const size_t o = (size_t)c * D;
+  vcopy(A.theta + o, W.cq + o, D, lane);
+  vcopy(W.g + o, W.cg + o, D, lane);
+  if (A.draws) vcopy(A.draws + row * D, W.cq + o, D, lane);
+  if (lane == 0) {
+    W.lp[c] = W.clp[c];
+    const double mean_alpha = W.alpha_sum[c] / fmax((double)W.alpha_cnt[c], 1.0);
+    A.n_accept[c] += mean_alpha > 0.5 ? 1 : 0;
+    if (A.adapt == B2M_ADAPT_DUAL_AVERAGING) {
+      double h_bar = A.da_state[c * 3 + 0], eps_bar = A.da_state[c * 3 + 1];
+      const float mu = (float)A.da_state[c * 3 + 2];
+      const double m = (double)giter, eta = 1.0 / (m + 10.0);
+      h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - mean_alpha);
+      float log_eps = __fsub_rn(mu, (float)((sqrt(m + 1.0) / 0.05) * h_bar));
+      log_eps = fmaxf(fminf(log_eps, 10.0f), -10.0f);
+      const double eps = (double)expf(log_eps);
+      const double wgt = pow(m + 1.0, -0.75);
+      eps_bar = (double)expf((float)(wgt * log(eps) + (1.0 - wgt) * log(eps_bar)));
+      A.step_size[c] = eps;
+      A.da_state[c * 3 + 0] = h_bar;
+      A.da_state[c * 3 + 1] = eps_bar;
+    }
+    if (A.depths) A.depths[row] = W.depth[c];
+    if (A.alphas) A.alphas[row] = (float)mean_alpha;
+  }
+}
+
+int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
+  const int64_t C = a.n_chains;
+  const int D = gm.Dtot, MD = a.max_tree_depth;
+  std::vector<void *> pool;
+  NutsBufs W{};
+  const size_t cd = (size_t)C * D;
+  float **vecs[] = {&W.g, &W.p0, &W.q_lo, &W.p_lo, &W.g_lo, &W.q_hi, &W.p_hi, &W.g_hi, &W.cq, &W.cg,
+                    &W.fq, &W.fp, &W.fg, &W.sfq, &W.sfp, &W.scq, &W.scg};
+  int rc = 0;
+  for (auto v : vecs) rc |= tmp_alloc(pool, v, cd);
+  float **stk[] = {&W.st_fq, &W.st_fp, &W.st_cq, &W.st_cg};
+  for (auto v : stk) rc |= tmp_alloc(pool, v, cd * MD);
+  float **fs[] = {&W.lp, &W.clp, &W.h0, &W.log_slice, &W.flp, &W.sclp, &W.feps, &W.heps};
+  for (auto v : fs) rc |= tmp_alloc(pool, v, C);
+  int **is[] = {&W.n, &W.s, &W.v, &W.leaf, &W.building, &W.sub_n, &W.sub_na, &W.sub_s, &W.alpha_cnt, &W.depth};
+  for (auto v : is) rc |= tmp_alloc(pool, v, C);
+  rc |= tmp_alloc(pool, &W.alpha_sum, C) | tmp_alloc(pool, &W.sub_alpha, C);
+  rc |= tmp_alloc(pool, &W.st_clp, (size_t)C * MD) | tmp_alloc(pool, &W.st_n, (size_t)C * MD) |
+        tmp_alloc(pool, &W.st_na, (size_t)C * MD) | tmp_alloc(pool, &W.st_alpha, (size_t)C * MD);
+  rc |= tmp_alloc(pool, &W.any_active, 1);
+  if (rc) { tmp_free(pool); return 2; }
+  int *h_flag = nullptr;
+  if (cudaMallocHost(&h_flag, sizeof(int)) != cudaSuccess) { tmp_free(pool); set_error("cudaMallocHost failed"); return 2; }
+
+  const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
+  const int T = 32 * WPB;
+  rc = glm_logp_grad(gm, a.theta, C, W.lp, W.g, st);
+  for (int it = 0; it < a.n_iter && !rc; ++it) {
+    nuts_begin_kernel<<<grid, T, 0, st>>>(a, W, D, it);
+    ++g_launches;
+    for (int j = 0; j < MD && !rc; ++j) {
+      cudaMemsetAsync(W.any_active, 0, sizeof(int), st);
+      nuts_doubling_begin_kernel<<<grid, T, 0, st>>>(a, W, D, it, j);
+      ++g_launches;
+      for (int leaf = 0; leaf < (1 << j) && !rc; ++leaf) {
+        nuts_leaf_pre_kernel<<<grid, T, 0, st>>>(a, W, D);
+        rc = glm_logp_grad(gm, W.fq, C, W.flp, W.fg, st);
+        nuts_leaf_post_kernel<<<grid, T, 0, st>>>(a, W, D, it, j);
+        g_launches += 2;
+      }
+      nuts_doubling_end_kernel<<<grid, T, 0, st>>>(a, W, D, it, j);
+      ++g_launches;
+      cudaMemcpyAsync(h_flag, W.any_active, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) { rc = 2; set_error("NUTS lock-step: stream error"); break; }
+      if (!*h_flag) break;
+    }
+    nuts_end_kernel<<<grid, T, 0, st>>>(a, W, D, it);
+    ++g_launches;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFreeHost(h_flag);
+  tmp_free(pool);
+  if (rc) return rc;
+  B2M_CHECK_CUDA(e);
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b2m

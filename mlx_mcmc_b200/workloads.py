@@ -173,8 +173,32 @@ def t_vector_normal(ns, d=3):
     return log_prob, {"x": np.zeros(d, dtype=np.float32)}, SimpleNamespace(name="t_vector_normal", D=d, N=0, loc=loc, scale=sc)
 
 
+def t_regression_small(ns, n=40, d=3):
+    """A small instance of the regression model (vector parameter, X @ beta) for decision-level NUTS parity;
+    H0 stays below the reference's float32 slice underflow."""
+    fn, init, meta = regression(ns, n, d, seed=3)
+    meta.name = "t_regression_small"
+    return fn, init, meta
+
+
+def t_regression_sigma(ns, n=60, d=4):
+    """Regression with an unknown noise scale: sigma is a scalar parameter next to the coefficient vector."""
+    mx, Normal, HalfNormal = ns.mx, ns.Normal, ns.HalfNormal
+    X, y, beta_true = data_regression(n, d, seed=5, noise=0.7)
+    Xa, ya = mx.array(X), mx.array(y)
+
+    def log_prob(params):
+        beta, sigma = params["beta"], params["sigma"]
+        return (mx.sum(Normal(0, 5.0).log_prob(beta)) + HalfNormal(2.0).log_prob(sigma)
+                + mx.sum(Normal(Xa @ beta, sigma).log_prob(ya)))
+
+    meta = SimpleNamespace(name="t_regression_sigma", D=d + 1, N=n, X=X, y=y, beta_true=beta_true)
+    return log_prob, {"beta": np.zeros(d, dtype=np.float32), "sigma": 1.0}, meta
+
+
 ALL_SMALL = {
     "c1_normal": c1_normal, "c2_event_rate": c2_event_rate, "c5_ab_test": c5_ab_test,
     "t_normal_1d": t_normal_1d, "t_normal_2d": t_normal_2d, "t_halfnormal_scale": t_halfnormal_scale,
     "t_halfnormal": t_halfnormal, "t_vector_normal": t_vector_normal,
+    "t_regression_small": t_regression_small, "t_regression_sigma": t_regression_sigma,
 }

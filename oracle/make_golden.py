@@ -68,6 +68,9 @@ POINTS = {
     "t_halfnormal_scale": [{"sigma": 1.0}, {"sigma": 0.3}, {"sigma": 6.0}, {"sigma": -0.4}],
     "t_halfnormal": [{"sigma": 1.0}, {"sigma": 3.0}, {"sigma": -1.0}],
     "t_vector_normal": [{"x": [0.0, 0.0, 0.0]}, {"x": [0.5, -1.0, 2.5]}],
+    "t_regression_small": [{"beta": [0.0, 0.0, 0.0]}, {"beta": [0.3, -1.2, 0.8]}, {"beta": [2.0, 2.0, -2.0]}],
+    "t_regression_sigma": [{"beta": [0.0, 0.0, 0.0, 0.0], "sigma": 1.0}, {"beta": [0.5, -0.5, 1.0, 0.1], "sigma": 0.7},
+                           {"beta": [1.0, 1.0, 1.0, 1.0], "sigma": 3.0}],
 }
 
 RUNS = [
@@ -82,6 +85,8 @@ RUNS = [
     ("nuts_normal2d", "t_normal_2d", "nuts", dict(num_samples=60, num_warmup=60, step_size=0.15, max_tree_depth=6, seed=123)),
     ("nuts_halfnormal_scale", "t_halfnormal_scale", "nuts", dict(num_samples=60, num_warmup=60, step_size=0.1, max_tree_depth=6, seed=456)),
     ("nuts_vector", "t_vector_normal", "nuts", dict(num_samples=50, num_warmup=50, step_size=0.2, max_tree_depth=6, seed=7)),
+    ("nuts_regression", "t_regression_small", "nuts", dict(num_samples=40, num_warmup=40, step_size=0.05, max_tree_depth=6, seed=21)),
+    ("nuts_regression_sigma", "t_regression_sigma", "nuts", dict(num_samples=30, num_warmup=40, step_size=0.05, max_tree_depth=6, seed=22)),
     ("nuts_c2", "c2_event_rate", "nuts", dict(num_samples=40, num_warmup=40, step_size=0.1, max_tree_depth=5, seed=11)),
 ]
 

@@ -199,7 +199,7 @@ class array:
         return array(-self.t)
 
     def __matmul__(self, o):
-        return array(self.t @ _weak(o, self.t))
+        return matmul(self, o)
 
     # -- comparisons / logic
     def __lt__(self, o):
@@ -332,7 +332,11 @@ def allclose(a, b, rtol=1e-5, atol=1e-8):
 
 
 def matmul(a, b):
-    return array(_raw(a) @ _raw(b))
+    ta, tb = _raw(a), _raw(b)
+    if ta.dtype != tb.dtype:       # observed float32 data against float64 parameters (arbiter mode)
+        dt = _torch.promote_types(ta.dtype, tb.dtype)
+        ta, tb = ta.to(dt), tb.to(dt)
+    return array(ta @ tb)
 
 
 def stack(xs, axis=0):

@@ -195,7 +195,8 @@ def _dual_averaging_states(tape, nw, step_size, target=0.65):
     return out, float(mu)
 
 
-@pytest.mark.parametrize("name", ["nuts_normal1d", "nuts_normal2d", "nuts_halfnormal_scale", "nuts_vector", "nuts_c2"])
+@pytest.mark.parametrize("name", ["nuts_normal1d", "nuts_normal2d", "nuts_halfnormal_scale", "nuts_vector", "nuts_c2",
+                                  "nuts_regression", "nuts_regression_sigma"])
 @pytest.mark.parametrize("lanes", [1, 4])
 def test_nuts_tree_decisions_match_reference(cuda, name, lanes):
     """Every NUTS transition of the reference run is replayed on the GPU from the reference's own state

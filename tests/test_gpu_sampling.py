@@ -184,3 +184,49 @@ def test_ess_helpers(cuda):
     for i in range(1, 4000):
         ar[i] = 0.9 * ar[i - 1] + rng.standard_normal()
     assert 100 < ess_geyer(ar) < 500                          # n (1-rho)/(1+rho) = 210
+
+
+# ------------------------------------------------------------------------------ GLM class (X @ beta)
+def test_regression_logp_grad_medium_vs_float64(cuda):
+    """README 'Medium' shape scaled down: N=2000, D=96, 300 chains at random positions vs float64 numpy"""
+    from mlx_mcmc_b200.engine import compile_model
+    fn, init, meta = W.regression(B.ns, 2000, 96, seed=1)
+    model = compile_model(fn, init, cache=False)
+    assert model.model_class == 1
+    rng = np.random.default_rng(0)
+    theta = (meta.beta_true[None, :] + 0.3 * rng.standard_normal((300, 96))).astype(np.float32)
+    lp, gr = model.logp_grad(torch.from_numpy(theta).cuda())
+    X, y, b = meta.X.astype(np.float64), meta.y.astype(np.float64), theta.astype(np.float64)
+    r = y[None, :] - b @ X.T
+    lp64 = (-0.5 * (r ** 2).sum(1) - 2000 * 0.5 * math.log(2 * math.pi)
+            - 0.5 * (b ** 2).sum(1) / 100.0 - 96 * (0.5 * math.log(2 * math.pi) + math.log(10.0)))
+    g64 = r @ X - b / 100.0
+    assert np.max(np.abs(lp.cpu().numpy() - lp64) / np.abs(lp64)) < 1e-5
+    assert np.max(np.abs(gr.cpu().numpy() - g64)) / np.max(np.abs(g64)) < 1e-5
+
+
+def test_regression_nuts_matches_closed_form_posterior(cuda):
+    """parity check 3 on the regression model: compat='correct' NUTS vs the closed-form N(m, V)"""
+    fn, init, meta = W.regression(B.ns, 500, 8, seed=2)
+    m, V = W.regression_posterior(meta)
+    s, rate, info = B.nuts(fn, init, num_samples=300, num_warmup=300, step_size=0.05, num_chains=512, compat="correct",
+                           return_info=True, key=mx.random.key(4))
+    x = s["beta"]                                   # (C, S, D)
+    assert x.shape == (512, 300, 8)
+    sd = np.sqrt(np.diag(V))
+    for d in range(8):
+        assert mcse_ok(x[:, :, d], m[d], sd[d]), (d, x[:, :, d].mean(), m[d], x[:, :, d].std(), sd[d])
+    assert info.grad_evals > 0
+
+
+def test_regression_hmc_and_metropolis_run(cuda):
+    fn, init, meta = W.regression(B.ns, 300, 4, seed=6)
+    m, V = W.regression_posterior(meta)
+    s, rate = B.hmc(fn, init, num_samples=400, num_warmup=300, step_size=0.02, num_leapfrog_steps=8, num_chains=256,
+                    key=mx.random.key(2))
+    assert s["beta"].shape == (256, 400, 4) and rate > 0.5
+    sd = np.sqrt(np.diag(V))
+    for d in range(4):
+        assert mcse_ok(s["beta"][:, :, d], m[d], sd[d]), d
+    s, rate = B.metropolis_hastings(fn, init, num_samples=300, proposal_scale=0.03, num_chains=64, random_seed=1)
+    assert s["beta"].shape == (64, 300, 4) and 0.05 < rate < 0.95

@@ -8,7 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden")
 
 RUN_FIXTURES = ["hmc_c1", "hmc_c2", "hmc_normal2d", "hmc_halfnormal", "mh_c5", "mh_c1", "nuts_normal1d",
-                "nuts_normal2d", "nuts_halfnormal_scale", "nuts_vector", "nuts_c2"]
+                "nuts_normal2d", "nuts_halfnormal_scale", "nuts_vector", "nuts_c2", "nuts_regression",
+                "nuts_regression_sigma"]
 
 
 def golden(name):
