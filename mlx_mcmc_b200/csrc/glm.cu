@@ -27,7 +27,8 @@ int glm_reserve(GlmModel &g, int64_t n_chains) {
   const int64_t cp = (n_chains + 127) / 128 * 128;
   if (cp <= g.cap) return 0;
   free_workspace(g);
-  if (dev_alloc(&g.B, cp * g.Dp) || dev_alloc(&g.G, cp * g.Dp) || dev_alloc(&g.R, cp * (size_t)g.Np) ||
+  g.g_splits_cap = g.use_tc ? grad_splits(g, cp) : 1;
+  if (dev_alloc(&g.B, cp * g.Dp) || dev_alloc(&g.G, (size_t)g.g_splits_cap * cp * g.Dp) || dev_alloc(&g.R, cp * (size_t)g.Np) ||
       dev_alloc(&g.ss_part, (size_t)(g.Np / 64) * cp) || dev_alloc(&g.inv_var, cp))
     return 2;
   if (g.use_tc) {
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
                                                           int64_t C, int64_t Cp, int Dtot, int beta_off, int D, int Dp,
                                                           int sigma_param, float sigma_const, float weight, int N,
                                                           int n_tiles, const float *__restrict__ ss_part,
-                                                          const float *__restrict__ G, float *__restrict__ logp,
+                                                          const float *__restrict__ G, int g_splits, float *__restrict__ logp,
                                                           float *__restrict__ grad) {
   extern __shared__ __align__(16) unsigned char smem[];
   SModel sm;
@@ -209,7 +210,8 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
   if (gr) {
     for (int d = lane; d < Dtot; d += 32) {
       float v = 0.f;
-      if (d >= beta_off && d < beta_off + D) v = G[c * Dp + (d - beta_off)];
+      if (d >= beta_off && d < beta_off + D)
+        for (int s = 0; s < g_splits; ++s) v += G[((int64_t)s * Cp + c) * Dp + (d - beta_off)];  // fixed order
       if (d == sigma_param) v = weight * (ss * iv - (float)N) / sg;
       gr[d] = v;
     }
@@ -267,7 +269,7 @@ int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float
   const size_t smem = g.has_prior ? model_smem_bytes(g.prior) : 16;
   glm_finish_kernel<<<(unsigned)((C + 3) / 4), 128, smem, st>>>(g.prior, g.has_prior ? 1 : 0, theta, C, Cp, g.Dtot, g.beta_off,
                                                                  g.D, g.Dp, g.sigma_param, g.sigma_const, g.weight, g.N,
-                                                                 n_tiles, g.ss_part, g.G, logp, grad);
+                                                                 n_tiles, g.ss_part, g.G, g.use_tc ? g.g_splits : 1, logp, grad);
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -31,7 +31,8 @@ struct GlmModel {
   int64_t cap = 0;
   float *B = nullptr, *Bh = nullptr, *Bl = nullptr;          // [cap, Dp]
   float *R = nullptr, *Rh = nullptr, *Rl = nullptr;          // [cap, Np]
-  float *G = nullptr;                                        // [cap, Dp]
+  float *G = nullptr;                                        // [g_splits_cap, cap, Dp] split-K partials of the gradient
+  int g_splits = 1, g_splits_cap = 1;
   float *ss_part = nullptr;                                  // [Np / 64, cap] per-column-tile partial sum of squares
   float *inv_var = nullptr;                                  // [cap]
   int use_tc = 0;                                            // 1: tcgen05 path, 0: SIMT path
@@ -50,6 +51,7 @@ int simt_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st);    // R -> G
 int tc_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st);
 int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st);
 bool tc_available();
+int grad_splits(const GlmModel &g, int64_t Cp);
 
 int glm_hmc_run(GlmModel &g, const b2m_hmc_args &a, cudaStream_t st);
 int glm_nuts_run(GlmModel &g, const b2m_nuts_args &a, cudaStream_t st);

@@ -1,9 +1,345 @@
-// tcgen05 + TMA implementation of the two GLM contractions (3xTF32).  Placeholder until the kernel lands:
-// reports "not available" so the SIMT path is used.
+// K5 / K6 on the 5th-generation tensor cores: TMA-staged tcgen05 GEMMs in 3xTF32.
+//
+//   D[m, n] = sum_k (Ah + Al)[m, k] * (Bh + Bl)[n, k]   ~=   Ah.Bh + Ah.Bl + Al.Bh      (fp32 accumulate in TMEM)
+//
+// Every operand is K-major fp32 holding tf32-representable values (round-to-nearest hi/lo split, glm.cuh), so
+// the dropped Al.Bl term is ~2^-22 relative: the two contractions hold the 1e-5 log-prob / gradient tolerance.
+//
+// Kernel anatomy (one 128 x BLOCK_N output tile per CTA, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the four operand tiles of a k-block
+//               (BLOCK_K = 32 floats = one 128-byte swizzle row) into a ring of shared-memory stages
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs x 4 k-steps per stage),
+//               tcgen05.commit releases the stage / signals the epilogue
+//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulators (lane = output row), then either
+//                 RESID: z = y - c - acc, per-row sum z^2, R = w z / sigma^2 split into tf32 hi/lo   (K5)
+//                 PLAIN: store the split-K partial of G                                              (K6)
+#include <cuda.h>
+
 #include "glm.cuh"
 
 namespace b2m {
-bool tc_available() { return false; }
-int tc_gemm_resid(GlmModel &, int64_t, cudaStream_t) { set_error("tcgen05 path not built"); return 1; }
-int tc_gemm_grad(GlmModel &, int64_t, cudaStream_t) { set_error("tcgen05 path not built"); return 1; }
+
+namespace {
+
+constexpr int BLOCK_M = 128, BLOCK_K = 32;            // 32 floats = 128 bytes = SWIZZLE_128B row
+constexpr int UMMA_K = 8;                             // tf32: 32 bytes per MMA k-step
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
+constexpr int NUM_THREADS = 192;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 | LBO (unused for swizzled K-major, = 1) << 16 | SBO = 1024 B (8 rows x 128 B) >> 4 << 32 |
+// version 1 << 46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+struct EpiParams {
+  // RESID
+  const float *y;
+  const float *inv_var;
+  float *Rh, *Rl, *ss_part;
+  int64_t Cp;
+  int Np, N_valid;
+  float loc_const, weight;
+  // PLAIN
+  float *Gpart;  // [splits, Cp, Dp]
+  int Dp;
+};
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+};
+
+template <int BLOCK_N, bool RESID>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int k_blocks_total,
+               int k_blocks_per_split, EpiParams E) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t *empty = full + C::STAGES;
+  uint64_t *tmem_full = empty + C::STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N;
+  const int kb0 = blockIdx.z * k_blocks_per_split;
+  const int kb1 = min(kb0 + k_blocks_per_split, k_blocks_total);
+  const int nkb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        unsigned char *st = smem + stage * C::STAGE_BYTES;
+        mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+        tma_load_2d(st, &tmAh, &full[stage], kb * BLOCK_K, m0);
+        tma_load_2d(st + A_TILE_BYTES, &tmAl, &full[stage], kb * BLOCK_K, m0);
+        tma_load_2d(st + 2 * A_TILE_BYTES, &tmBh, &full[stage], kb * BLOCK_K, n0);
+        tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tmBl, &full[stage], kb * BLOCK_K, n0);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
+        const uint64_t dAh = make_desc(st), dAl = make_desc(st + A_TILE_BYTES);
+        const uint64_t dBh = make_desc(st + 2 * A_TILE_BYTES), dBl = make_desc(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance the start-address field inside the swizzle row
+          umma_tf32(tmem_base, dAh + adv, dBh + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base, dAh + adv, dBl + adv, idesc, 1u);
+          umma_tf32(tmem_base, dAl + adv, dBh + adv, idesc, 1u);
+        }
+        umma_commit(&empty[stage]);  // frees the stage once the MMAs above have read it
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);        // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    float ss = 0.f;
+    const float ivw = RESID ? E.inv_var[m] * E.weight : 0.f;
+#pragma unroll 1
+    for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+      uint32_t v[32];
+      tmem_ld32(trow + cb * 32, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int nb = n0 + cb * 32;
+      if (RESID) {
+        float *rh = E.Rh + (int64_t)m * E.Np + nb, *rl = E.Rl + (int64_t)m * E.Np + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float hi[4], lo[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int n = nb + j + t;
+            const float z = (n < E.N_valid) ? (__ldg(E.y + n) - E.loc_const) - __uint_as_float(v[j + t]) : 0.f;
+            ss = fmaf(z, z, ss);
+            split_tf32(z * ivw, hi[t], lo[t]);
+          }
+          *reinterpret_cast<float4 *>(rh + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4 *>(rl + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      } else {
+        float *g = E.Gpart + ((int64_t)blockIdx.z * E.Cp + m) * E.Dp + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4 *>(g + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+    if (RESID) E.ss_part[(int64_t)blockIdx.y * E.Cp + m] = ss;
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows, cols] row-major fp32, box = 32 columns (128 bytes) x box_rows rows, 128-byte swizzle
+int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  B2M_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 2;
+  }
+  return 0;
+}
+
+template <int BLOCK_N, bool RESID>
+int launch_tc(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &Bh, const CUtensorMap &Bl, dim3 grid,
+              int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st) {
+  using C = Cfg<BLOCK_N>;
+  auto kernel = tc_gemm_kernel<BLOCK_N, RESID>;
+  static bool configured = false;
+  if (!configured) {
+    B2M_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  kernel<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(Ah, Al, Bh, Bl, kb_total, kb_per_split, E);
+  ++g_launches;
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+bool tc_available() { return encode_fn() != nullptr; }
+
+int grad_block_n(const GlmModel &g) { return g.Dp % 256 == 0 ? 256 : (g.Dp % 128 == 0 ? 128 : 64); }
+
+int grad_splits(const GlmModel &g, int64_t Cp) {
+  const int64_t tiles = (Cp / BLOCK_M) * (g.Dp / grad_block_n(g));
+  const int kb = g.Np / BLOCK_K;
+  int64_t s = 148 / (tiles > 0 ? tiles : 1);
+  if (s < 1) s = 1;
+  if (s > kb / 8) s = kb / 8 > 0 ? kb / 8 : 1;
+  if (s > 32) s = 32;
+  return (int)s;
+}
+
+int tc_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st) {
+  CUtensorMap Ah, Al, Bh, Bl;
+  if (make_map(&Ah, g.Bh, Cp, g.Dp, BLOCK_M) || make_map(&Al, g.Bl, Cp, g.Dp, BLOCK_M) ||
+      make_map(&Bh, g.Xh, g.Np, g.Dp, 256) || make_map(&Bl, g.Xl, g.Np, g.Dp, 256))
+    return 2;
+  EpiParams E{};
+  E.y = g.y; E.inv_var = g.inv_var; E.Rh = g.Rh; E.Rl = g.Rl; E.ss_part = g.ss_part; E.Cp = Cp; E.Np = g.Np;
+  E.N_valid = g.N; E.loc_const = g.loc_const; E.weight = g.weight;
+  dim3 grid((unsigned)(Cp / BLOCK_M), g.Np / 256, 1);
+  return launch_tc<256, true>(Ah, Al, Bh, Bl, grid, g.Dp / BLOCK_K, g.Dp / BLOCK_K, E, st);
+}
+
+int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
+  const int bn = grad_block_n(g);
+  const int splits = grad_splits(g, Cp);
+  const int kb_total = g.Np / BLOCK_K;
+  const int kb_per = (kb_total + splits - 1) / splits;
+  CUtensorMap Ah, Al, Bh, Bl;
+  if (make_map(&Ah, g.Rh, Cp, g.Np, BLOCK_M) || make_map(&Al, g.Rl, Cp, g.Np, BLOCK_M) ||
+      make_map(&Bh, g.XTh, g.Dp, g.Np, bn) || make_map(&Bl, g.XTl, g.Dp, g.Np, bn))
+    return 2;
+  EpiParams E{};
+  E.Gpart = g.G; E.Cp = Cp; E.Dp = g.Dp;
+  dim3 grid((unsigned)(Cp / BLOCK_M), g.Dp / bn, (unsigned)((kb_total + kb_per - 1) / kb_per));
+  g.g_splits = (int)grid.z;
+  if (bn == 256) return launch_tc<256, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st);
+  if (bn == 128) return launch_tc<128, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st);
+  return launch_tc<64, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st);
+}
+
 }  // namespace b2m
