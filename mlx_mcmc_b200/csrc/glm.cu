@@ -260,7 +260,7 @@ int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float
   if (g.use_tc) {
     if (int rc = tc_gemm_resid(g, Cp, st)) return rc;
     if (grad) if (int rc = tc_gemm_grad(g, Cp, st)) return rc;
-    n_tiles = g.Np / 256;
+    n_tiles = g.Np / 128;   // 256-wide tiles, two column halves each
   } else {
     if (int rc = simt_gemm_resid(g, Cp, st)) return rc;
     if (grad) if (int rc = simt_gemm_grad(g, Cp, st)) return rc;

@@ -9,8 +9,13 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the four operand tiles of a k-block
 //               (BLOCK_K = 32 floats = one 128-byte swizzle row) into a ring of shared-memory stages
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs x 4 k-steps per stage),
-//               tcgen05.commit releases the stage / signals the epilogue
-//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulators (lane = output row), then either
+//               tcgen05.commit releases the stage / hands a finished K-chunk to the promotion warps
+//   warps 2..9  promotion + epilogue.  The tensor core adds into its fp32 accumulator with truncation, so a
+//               long K loop drifts (~T * 2^-24 relative after T MMAs: measured 4e-6 at K = 1000, would be
+//               ~2e-3 at K = 100,000).  Therefore TMEM holds only a CHUNK of 4 k-blocks (K = 128) at a time,
+//               double buffered; these warps tcgen05.ld each finished chunk and add it round-to-nearest into
+//               fp32 master accumulators in registers (lane = output row, 8 warps = 4 lane quarters x 2 column
+//               halves).  At the end:
 //                 RESID: z = y - c - acc, per-row sum z^2, R = w z / sigma^2 split into tf32 hi/lo   (K5)
 //                 PLAIN: store the split-K partial of G                                              (K6)
 #include <cuda.h>
@@ -24,7 +29,9 @@ namespace {
 constexpr int BLOCK_M = 128, BLOCK_K = 32;            // 32 floats = 128 bytes = SWIZZLE_128B row
 constexpr int UMMA_K = 8;                             // tf32: 32 bytes per MMA k-step
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp, MMA warp, 8 promotion/epilogue warps
+constexpr int CHUNK_KB = 4;                             // k-blocks accumulated inside the tensor core per chunk
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -49,6 +56,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
   asm volatile(
@@ -115,7 +125,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;        // two chunk accumulators (power of two >= 32)
+  static constexpr int COLS_PER_WARP = BLOCK_N / 2;    // each promotion warp owns 32 rows x half of the columns
 };
 
 template <int BLOCK_N, bool RESID>
@@ -128,14 +139,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t *empty = full + C::STAGES;
-  uint64_t *tmem_full = empty + C::STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+  uint64_t *tmem_full = empty + C::STAGES;   // [2]
+  uint64_t *tmem_empty = tmem_full + 2;      // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N;
   const int kb0 = blockIdx.z * k_blocks_per_split;
   const int kb1 = min(kb0 + k_blocks_per_split, k_blocks_total);
   const int nkb = kb1 - kb0;
+  const int n_chunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
@@ -143,7 +156,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -177,63 +190,80 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full[stage], phase);
+      int kb = 0;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int buf = ch & 1;
+        mbar_wait(&tmem_empty[buf], ((ch >> 1) & 1) ^ 1);   // the promotion warps have drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
-        const uint64_t dAh = make_desc(st), dAl = make_desc(st + A_TILE_BYTES);
-        const uint64_t dBh = make_desc(st + 2 * A_TILE_BYTES), dBl = make_desc(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
+        const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
+        const int kb_end = min(kb + CHUNK_KB, nkb);
+        for (int kc = 0; kb < kb_end; ++kb, ++kc) {
+          mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t dAh = make_desc(st), dAl = make_desc(st + A_TILE_BYTES);
+          const uint64_t dBh = make_desc(st + 2 * A_TILE_BYTES), dBl = make_desc(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance the start-address field inside the swizzle row
-          umma_tf32(tmem_base, dAh + adv, dBh + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_tf32(tmem_base, dAh + adv, dBl + adv, idesc, 1u);
-          umma_tf32(tmem_base, dAl + adv, dBh + adv, idesc, 1u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // start-address advance inside the swizzle row
+            umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, (kc | k) != 0 ? 1u : 0u);
+            umma_tf32(tmem_d, dAh + adv, dBl + adv, idesc, 1u);
+            umma_tf32(tmem_d, dAl + adv, dBh + adv, idesc, 1u);
+          }
+          umma_commit(&empty[stage]);  // frees the stage once the MMAs above have read it
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty[stage]);  // frees the stage once the MMAs above have read it
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full[buf]);  // chunk accumulator complete
       }
-      umma_commit(tmem_full);        // accumulator complete
     }
   } else {
-    // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
-    const int q = warp & 3;
+    // ===== promotion + epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int m = m0 + q * 32 + lane;
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    float ss = 0.f;
-    const float ivw = RESID ? E.inv_var[m] * E.weight : 0.f;
-#pragma unroll 1
-    for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
-      uint32_t v[32];
-      tmem_ld32(trow + cb * 32, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int nb = n0 + cb * 32;
-      if (RESID) {
-        float *rh = E.Rh + (int64_t)m * E.Np + nb, *rl = E.Rl + (int64_t)m * E.Np + nb;
+    constexpr int CW = C::COLS_PER_WARP;
+    float acc[CW];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float hi[4], lo[4];
+    for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int buf = ch & 1;
+      mbar_wait(&tmem_full[buf], (ch >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BLOCK_N + half * CW;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int n = nb + j + t;
-            const float z = (n < E.N_valid) ? (__ldg(E.y + n) - E.loc_const) - __uint_as_float(v[j + t]) : 0.f;
-            ss = fmaf(z, z, ss);
-            split_tf32(z * ivw, hi[t], lo[t]);
-          }
-          *reinterpret_cast<float4 *>(rh + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4 *>(rl + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-      } else {
-        float *g = E.Gpart + ((int64_t)blockIdx.z * E.Cp + m) * E.Dp + nb;
+      for (int cb = 0; cb < CW / 32; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(trow + cb * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4 *>(g + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int j = 0; j < 32; ++j) acc[cb * 32 + j] += __uint_as_float(v[j]);   // round-to-nearest promotion
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tmem_empty[buf]);
     }
-    if (RESID) E.ss_part[(int64_t)blockIdx.y * E.Cp + m] = ss;
+    const int nb = n0 + half * CW;
+    if (RESID) {
+      float ss = 0.f;
+      const float ivw = E.inv_var[m] * E.weight;
+      float *rh = E.Rh + (int64_t)m * E.Np + nb, *rl = E.Rl + (int64_t)m * E.Np + nb;
+#pragma unroll
+      for (int j = 0; j < CW; j += 4) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int n = nb + j + t;
+          const float z = (n < E.N_valid) ? (__ldg(E.y + n) - E.loc_const) - acc[j + t] : 0.f;
+          ss = fmaf(z, z, ss);
+          split_tf32(z * ivw, hi[t], lo[t]);
+        }
+        *reinterpret_cast<float4 *>(rh + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4 *>(rl + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      E.ss_part[((int64_t)blockIdx.y * 2 + half) * E.Cp + m] = ss;
+    } else {
+      float *g = E.Gpart + ((int64_t)blockIdx.z * E.Cp + m) * E.Dp + nb;
+#pragma unroll
+      for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4 *>(g + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

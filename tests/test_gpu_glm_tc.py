@@ -49,8 +49,12 @@ def test_tc_logp_grad_vs_float64_and_simt(cuda, n, d, c):
     for lp, g, tol in ((lp_tc, g_tc, 1e-5), (lp_s, g_s, 1e-5)):
         assert np.max(np.abs(lp.cpu().numpy() - lp64) / np.abs(lp64)) < tol
         assert np.max(np.abs(g.cpu().numpy() - g64)) / np.max(np.abs(g64)) < tol
-    # 3xTF32 is as accurate as fp32 FMA tiles: the two paths agree to a few float32 ulps of the gradient scale
-    assert np.max(np.abs(g_tc.cpu().numpy() - g_s.cpu().numpy())) / np.max(np.abs(g64)) < 5e-6
+    # 3xTF32 with chunked promotion is as accurate as fp32 FMA tiles
+    e_tc = np.max(np.abs(g_tc.cpu().numpy() - g64)) / np.max(np.abs(g64))
+    e_s = np.max(np.abs(g_s.cpu().numpy() - g64)) / np.max(np.abs(g64))
+    print(f"n={n} d={d} c={c}: grad err tc {e_tc:.2e} simt {e_s:.2e}; "
+          f"logp err tc {np.max(np.abs(lp_tc.cpu().numpy() - lp64) / np.abs(lp64)):.2e}")
+    assert e_tc < 3e-6
 
 
 def test_tc_value_only_and_repeatability(cuda):

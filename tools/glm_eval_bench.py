@@ -1,0 +1,64 @@
+"""Time one batched value+gradient of the regression model (K5 + K6) and check it against float64.
+
+    python tools/glm_eval_bench.py --n 100000 --d 1000 --chains 4096 [--path tc|simt] [--check 64]
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=100000)
+ap.add_argument("--d", type=int, default=1000)
+ap.add_argument("--chains", type=int, default=4096)
+ap.add_argument("--path", default="tc")
+ap.add_argument("--check", type=int, default=64)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--spread", type=float, default=0.01)
+args = ap.parse_args()
+os.environ["B2M_GLM_PATH"] = args.path
+
+import mlx_mcmc_b200 as B
+from mlx_mcmc_b200 import workloads as W
+from mlx_mcmc_b200.engine import compile_model
+
+t0 = time.time()
+fn, init, meta = W.regression(B.ns, args.n, args.d, seed=0)
+model = compile_model(fn, init, cache=False)
+torch.cuda.synchronize()
+print(f"model built in {time.time() - t0:.1f}s", file=sys.stderr)
+rng = np.random.default_rng(1)
+theta = (meta.beta_true[None, :] + args.spread * rng.standard_normal((args.chains, args.d))).astype(np.float32)
+t = torch.from_numpy(theta).cuda()
+lp, g = model.logp_grad(t)
+torch.cuda.synchronize()
+times = []
+for _ in range(args.reps):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    lp, g = model.logp_grad(t)
+    b.record()
+    torch.cuda.synchronize()
+    times.append(a.elapsed_time(b))
+ms = float(np.median(times))
+flops = 4.0 * args.n * args.d * args.chains
+out = {"n": args.n, "d": args.d, "chains": args.chains, "path": args.path, "ms_per_eval": ms, "all_ms": times,
+       "useful_tflops": flops / ms / 1e9, "grad_evals_per_s": args.chains / ms * 1e3,
+       "logical_GBps": 4.0 * args.n * args.d * args.chains / ms / 1e6}
+if args.check:
+    k = args.check
+    X, y, b = meta.X.astype(np.float64), meta.y.astype(np.float64), theta[:k].astype(np.float64)
+    r = y[None, :] - b @ X.T
+    lp64 = (-0.5 * (r ** 2).sum(1) - args.n * 0.5 * math.log(2 * math.pi)
+            - 0.5 * (b ** 2).sum(1) / 100.0 - args.d * (0.5 * math.log(2 * math.pi) + math.log(10.0)))
+    g64 = r @ X - b / 100.0
+    out["logp_rel_err"] = float(np.max(np.abs(lp[:k].cpu().numpy() - lp64) / np.abs(lp64)))
+    out["grad_normwise_err"] = float(np.max(np.abs(g[:k].cpu().numpy() - g64)) / np.max(np.abs(g64)))
+    out["grad_scale"] = float(np.max(np.abs(g64)))
+print(json.dumps(out))
