@@ -20,6 +20,8 @@ int launch_hmc(const KModel &km, b2m_hmc_args a, cudaStream_t st);
 int launch_mh(const KModel &km, b2m_mh_args a, cudaStream_t st);
 int launch_nuts(const KModel &km, b2m_nuts_args a, cudaStream_t st);
 int glm_build(GlmModel &g, const float *X, const float *y, int N, int D);
+int debug_tc_gemm(const float *A, const float *Bm, int M, int N, int K, float *Cout, int chunk_kb, int mma_mask,
+                  cudaStream_t st);
 
 }  // namespace b2m
 
@@ -124,6 +126,13 @@ extern "C" {
 const char *b2m_last_error(void) { return b2m::tl_error.c_str(); }
 int b2m_abi_version(void) { return B2M_ABI_VERSION; }
 int64_t b2m_launch_count(void) { return b2m::g_launches; }
+
+// Internal (not part of the public header): C[M,N] = A[M,K] . B[N,K]^T through the 3xTF32 tcgen05 kernel, with the
+// promotion interval and the set of partial products selectable, for accuracy experiments and tests.
+int b2m_debug_tc_gemm(const float *A, const float *Bm, int M, int N, int K, float *C, int chunk_kb, int mma_mask,
+                      void *stream) {
+  return b2m::debug_tc_gemm(A, Bm, M, N, K, C, chunk_kb, mma_mask, static_cast<cudaStream_t>(stream));
+}
 
 int b2m_struct_sizes(int32_t *out6) {
   out6[0] = (int32_t)sizeof(b2m_term);

@@ -31,7 +31,7 @@ constexpr int UMMA_K = 8;                             // tf32: 32 bytes per MMA 
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp, MMA warp, 8 promotion/epilogue warps
-constexpr int CHUNK_KB = 4;                             // k-blocks accumulated inside the tensor core per chunk
+constexpr int DEFAULT_CHUNK_KB = 4;                     // k-blocks accumulated inside the tensor core per chunk
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -133,7 +133,7 @@ template <int BLOCK_N, bool RESID>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int k_blocks_total,
-               int k_blocks_per_split, EpiParams E) {
+               int k_blocks_per_split, int CHUNK_KB, int mma_mask, EpiParams E) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -207,8 +207,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // start-address advance inside the swizzle row
             umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, (kc | k) != 0 ? 1u : 0u);
-            umma_tf32(tmem_d, dAh + adv, dBl + adv, idesc, 1u);
-            umma_tf32(tmem_d, dAl + adv, dBh + adv, idesc, 1u);
+            if (mma_mask & 2) umma_tf32(tmem_d, dAh + adv, dBl + adv, idesc, 1u);
+            if (mma_mask & 4) umma_tf32(tmem_d, dAl + adv, dBh + adv, idesc, 1u);
           }
           umma_commit(&empty[stage]);  // frees the stage once the MMAs above have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -312,7 +312,8 @@ int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, in
 
 template <int BLOCK_N, bool RESID>
 int launch_tc(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &Bh, const CUtensorMap &Bl, dim3 grid,
-              int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st) {
+              int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st, int chunk_kb = DEFAULT_CHUNK_KB,
+              int mma_mask = 7) {
   using C = Cfg<BLOCK_N>;
   auto kernel = tc_gemm_kernel<BLOCK_N, RESID>;
   static bool configured = false;
@@ -320,7 +321,7 @@ int launch_tc(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &B
     B2M_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  kernel<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(Ah, Al, Bh, Bl, kb_total, kb_per_split, E);
+  kernel<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(Ah, Al, Bh, Bl, kb_total, kb_per_split, chunk_kb, mma_mask, E);
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -370,6 +371,40 @@ int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
   if (bn == 256) return launch_tc<256, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st);
   if (bn == 128) return launch_tc<128, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st);
   return launch_tc<64, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st);
+}
+
+
+// ---------------------------------------------------------------- raw 3xTF32 GEMM for experiments / tests
+__global__ void split_kernel(const float *__restrict__ x, int64_t n, float *hi, float *lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) split_tf32(x[i], hi[i], lo[i]);
+}
+
+int debug_tc_gemm(const float *A, const float *Bm, int M, int N, int K, float *Cout, int chunk_kb, int mma_mask,
+                  cudaStream_t st) {
+  B2M_REQUIRE(M % BLOCK_M == 0 && N % 64 == 0 && K % BLOCK_K == 0, "debug_tc_gemm: M%128, N%64, K%32 must be 0");
+  float *Ah, *Al, *Bh, *Bl;
+  B2M_CHECK_CUDA(cudaMalloc(&Ah, sizeof(float) * M * (size_t)K));
+  B2M_CHECK_CUDA(cudaMalloc(&Al, sizeof(float) * M * (size_t)K));
+  B2M_CHECK_CUDA(cudaMalloc(&Bh, sizeof(float) * N * (size_t)K));
+  B2M_CHECK_CUDA(cudaMalloc(&Bl, sizeof(float) * N * (size_t)K));
+  split_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, st>>>(A, (int64_t)M * K, Ah, Al);
+  split_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(Bm, (int64_t)N * K, Bh, Bl);
+  const int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+  CUtensorMap mAh, mAl, mBh, mBl;
+  int rc = make_map(&mAh, Ah, M, K, BLOCK_M) || make_map(&mAl, Al, M, K, BLOCK_M) || make_map(&mBh, Bh, N, K, bn) ||
+           make_map(&mBl, Bl, N, K, bn);
+  if (!rc) {
+    EpiParams E{};
+    E.Gpart = Cout; E.Cp = M; E.Dp = N;
+    dim3 grid(M / BLOCK_M, N / bn, 1);
+    if (bn == 256) rc = launch_tc<256, false>(mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
+    else if (bn == 128) rc = launch_tc<128, false>(mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
+    else rc = launch_tc<64, false>(mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl);
+  return rc ? 2 : 0;
 }
 
 }  // namespace b2m
