@@ -234,7 +234,7 @@ int b2m_logp_grad(b2m_model *m, const float *theta, int64_t n_chains, float *log
   B2M_REQUIRE(n_chains > 0, "b2m_logp_grad: n_chains must be positive");
   B2M_REQUIRE(valid_lanes(lanes), "b2m_logp_grad: lanes must be 0 or a power of two <= 32");
   if (m->model_class == 1)
-    return b2m::glm_logp_grad(m->glm, theta, n_chains, logp, grad, static_cast<cudaStream_t>(stream));
+    return b2m::glm_logp_grad(m->glm, theta, n_chains, logp, grad, static_cast<cudaStream_t>(stream), true);
   return b2m::launch_logp_grad(m->km, theta, n_chains, logp, grad, lanes, static_cast<cudaStream_t>(stream));
 }
 

@@ -21,6 +21,7 @@ static void free_workspace(GlmModel &g) {
 void glm_free(GlmModel &g) {
   free_workspace(g);
   FREE(g.X); FREE(g.XT); FREE(g.Xh); FREE(g.Xl); FREE(g.XTh); FREE(g.XTl); FREE(g.y);
+  FREE(g.y0); FREE(g.beta0); FREE(g.center_part);
 }
 
 int glm_reserve(GlmModel &g, int64_t n_chains) {
@@ -67,7 +68,9 @@ int glm_build(GlmModel &g, const float *X, const float *y, int N, int D) {
   g.Np = (N + 255) / 256 * 256;
   g.Dp = (D + 63) / 64 * 64;
   const size_t nd = (size_t)g.Np * g.Dp;
-  if (dev_alloc(&g.X, nd) || dev_alloc(&g.XT, nd) || dev_alloc(&g.y, g.Np)) return 2;
+  if (dev_alloc(&g.X, nd) || dev_alloc(&g.XT, nd) || dev_alloc(&g.y, g.Np) || dev_alloc(&g.y0, g.Np) ||
+      dev_alloc(&g.beta0, g.Dp) || dev_alloc(&g.center_part, (size_t)kCenterSlices * g.Dp))
+    return 2;
   if (g.use_tc && (dev_alloc(&g.Xh, nd) || dev_alloc(&g.Xl, nd) || dev_alloc(&g.XTh, nd) || dev_alloc(&g.XTl, nd))) return 2;
   pad_transpose_split_kernel<<<(unsigned)((nd + 255) / 256), 256>>>(X, N, D, g.Np, g.Dp, g.X, g.XT, g.Xh, g.Xl, g.XTh, g.XTl);
   pad_vector_kernel<<<(g.Np + 255) / 256, 256>>>(y, N, g.Np, g.y);
@@ -77,15 +80,88 @@ int glm_build(GlmModel &g, const float *X, const float *y, int N, int D) {
   return 0;
 }
 
-// ---------------------------------------------------------------- pack: theta -> B (+ tf32 split), 1/sigma^2
-__global__ void glm_pack_kernel(const float *__restrict__ theta, int64_t C, int64_t Cp, int Dtot, int beta_off, int D,
-                                int Dp, int sigma_param, float sigma_const, float *B, float *Bh, float *Bl,
-                                float *inv_var) {
+// ---------------------------------------------------------------- centering (once per sampler iteration)
+// Near the posterior mode the residual z = y - X beta is a small difference of large numbers, and the gradient
+// X^T z amplifies any systematic error of X beta by N (the tensor core accumulates with truncation: measured
+// 1e-6 relative shrinkage of X beta => 1e-6 * N * |beta| absolute error in the gradient).  The contraction is
+// therefore taken around a reference point beta0 shared by all chains of the batch:
+//     z_c = (y - c - X beta0) - X (beta_c - beta0)
+// with y0 = y - c - X beta0 accumulated in float64 once per sampler iteration (one GEMV, X read once) and
+// beta0 = the mean of the chains' current positions.  X (beta_c - beta0) is then of the size of the
+// posterior spread, and its rounding no longer dominates z.  Same function, different association.
+
+__global__ void __launch_bounds__(256) glm_center_partial_kernel(const float *__restrict__ theta, int64_t C, int Dtot,
+                                                                 int beta_off, int D, int Dp, double *__restrict__ part) {
+  __shared__ double sh[8][33];
+  const int d = blockIdx.x * 32 + threadIdx.x, ty = threadIdx.y;
+  const int64_t per = (C + kCenterSlices - 1) / kCenterSlices;
+  const int64_t c0 = (int64_t)blockIdx.y * per, c1 = (c0 + per < C) ? c0 + per : C;
+  double acc = 0.0;
+  if (d < D)
+    for (int64_t c = c0 + ty; c < c1; c += 8) {
+      const float v = theta[c * Dtot + beta_off + d];
+      if (fabsf(v) <= 3.0e38f) acc += (double)v;   // a diverged / NaN chain must not move the centre
+    }
+  sh[ty][threadIdx.x] = acc;
+  __syncthreads();
+  if (ty == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sh[i][threadIdx.x];   // fixed order => deterministic
+    part[(int64_t)blockIdx.y * Dp + d] = s;
+  }
+}
+
+__global__ void glm_center_final_kernel(const double *__restrict__ part, int Dp, int64_t C, float *__restrict__ beta0) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= Dp) return;
+  double s = 0.0;
+  for (int i = 0; i < kCenterSlices; ++i) s += part[(int64_t)i * Dp + d];
+  beta0[d] = (float)(s / (double)C);
+}
+
+// y0[n] = (y[n] - c) - sum_d X[n, d] beta0[d], float64 accumulation, one warp per observation row
+__global__ void __launch_bounds__(256) glm_y0_kernel(const float *__restrict__ X, const float *__restrict__ y,
+                                                     const float *__restrict__ beta0, int N, int Np, int Dp,
+                                                     float loc_const, float *__restrict__ y0) {
+  extern __shared__ float sb[];
+  for (int d = threadIdx.x; d < Dp; d += blockDim.x) sb[d] = beta0[d];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= Np) return;
+  double acc = 0.0;
+  if (n < N) {
+    const float4 *row = reinterpret_cast<const float4 *>(X + (int64_t)n * Dp);
+    const float4 *b4 = reinterpret_cast<const float4 *>(sb);
+    for (int i = lane; i < Dp / 4; i += 32) {
+      const float4 x = __ldg(row + i), b = b4[i];
+      acc += (double)x.x * b.x + (double)x.y * b.y + (double)x.z * b.z + (double)x.w * b.w;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y0[n] = n < N ? (float)(((double)y[n] - (double)loc_const) - acc) : 0.f;
+}
+
+int glm_recenter(GlmModel &g, const float *theta, int64_t C, cudaStream_t st) {
+  dim3 gp(g.Dp / 32, kCenterSlices), bp(32, 8);
+  glm_center_partial_kernel<<<gp, bp, 0, st>>>(theta, C, g.Dtot, g.beta_off, g.D, g.Dp, g.center_part);
+  glm_center_final_kernel<<<(g.Dp + 127) / 128, 128, 0, st>>>(g.center_part, g.Dp, C, g.beta0);
+  glm_y0_kernel<<<(g.Np + 7) / 8, 256, sizeof(float) * g.Dp, st>>>(g.X, g.y, g.beta0, g.N, g.Np, g.Dp, g.loc_const, g.y0);
+  g_launches += 3;
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------- pack: theta -> B = beta - beta0 (+ tf32 split), 1/sigma^2
+__global__ void glm_pack_kernel(const float *__restrict__ theta, const float *__restrict__ beta0, int64_t C, int64_t Cp,
+                                int Dtot, int beta_off, int D, int Dp, int sigma_param, float sigma_const, float *B,
+                                float *Bh, float *Bl, float *inv_var) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cp * Dp) return;
   const int64_t c = i / Dp;
   const int d = int(i % Dp);
-  const float v = (c < C && d < D) ? theta[c * Dtot + beta_off + d] : 0.f;
+  const float v = (c < C && d < D) ? __fsub_rn(theta[c * Dtot + beta_off + d], beta0[d]) : 0.f;
   B[i] = v;
   if (Bh) {
     float hi, lo;
@@ -166,8 +242,8 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const float *__restrict_
 
 int simt_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st) {
   dim3 grid(g.Np / TN, (unsigned)(Cp / TM));
-  simt_gemm_kernel<true><<<grid, 256, 0, st>>>(g.B, g.X, g.Dp, g.Dp, g.Dp, g.R, g.Np, g.y, g.inv_var, g.ss_part, Cp,
-                                                g.N, g.loc_const, g.weight);
+  simt_gemm_kernel<true><<<grid, 256, 0, st>>>(g.B, g.X, g.Dp, g.Dp, g.Dp, g.R, g.Np, g.y0, g.inv_var, g.ss_part, Cp,
+                                                g.N, 0.f, g.weight);
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -249,11 +325,13 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
   if (lane == 0) logp[c] = lp + pl;
 }
 
-int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st) {
+int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st, bool recenter) {
   if (int rc = glm_reserve(g, C)) return rc;
+  if (recenter)
+    if (int rc = glm_recenter(g, theta, C, st)) return rc;
   const int64_t Cp = (C + 127) / 128 * 128;
   const int64_t tot = Cp * g.Dp;
-  glm_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
+  glm_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, g.beta0, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
                                                                   g.sigma_param, g.sigma_const, g.B, g.Bh, g.Bl, g.inv_var);
   ++g_launches;
   int n_tiles;

@@ -12,6 +12,8 @@
 
 namespace b2m {
 
+constexpr int kCenterSlices = 32;  // chain slices of the deterministic two-stage mean (glm.cu, centring)
+
 struct GlmModel {
   // problem
   int N = 0, D = 0;        // observations, regression coefficients
@@ -24,6 +26,9 @@ struct GlmModel {
   float *X = nullptr, *XT = nullptr;                         // [Np, Dp], [Dp, Np] fp32
   float *Xh = nullptr, *Xl = nullptr, *XTh = nullptr, *XTl = nullptr;  // tf32 hi / lo splits
   float *y = nullptr;                                        // [Np]
+  // centring (glm.cu): beta0 = mean current position of the batch, y0 = y - c - X beta0 (float64 accumulation)
+  float *y0 = nullptr, *beta0 = nullptr;                     // [Np], [Dp]
+  double *center_part = nullptr;                             // [32, Dp]
   // prior terms (everything except the matvec likelihood) as a pointwise term table
   KModel prior{};
   bool has_prior = false;
@@ -41,8 +46,11 @@ struct GlmModel {
 int glm_reserve(GlmModel &g, int64_t n_chains);
 void glm_free(GlmModel &g);
 
-// log p and gradient for `theta` [C, Dtot] (device).  grad may be NULL.
-int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st);
+// log p and gradient for `theta` [C, Dtot] (device).  grad may be NULL.  recenter: move the reference point of
+// the contraction to the mean of `theta` first (the samplers do it once per iteration, from the current states).
+int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st,
+                  bool recenter = false);
+int glm_recenter(GlmModel &g, const float *theta, int64_t C, cudaStream_t st);
 
 // the two contractions (SIMT implementation)
 int simt_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st);   // B -> R, ss_part

@@ -172,8 +172,9 @@ int glm_hmc_run(GlmModel &gm, const b2m_hmc_args &a, cudaStream_t st) {
     return 2;
   }
   const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
-  int rc = glm_logp_grad(gm, a.theta, C, W.lp, W.g, st);
+  int rc = glm_logp_grad(gm, a.theta, C, W.lp, W.g, st, true);
   for (int it = 0; it < a.n_iter && !rc; ++it) {
+    if (it > 0) rc = glm_recenter(gm, a.theta, C, st);   // reference point follows the current states
     hmc_begin_kernel<<<grid, 32 * WPB, 0, st>>>(a, W, D, it);
     ++g_launches;
     for (int l = 0; l < a.n_leapfrog && !rc; ++l) {
@@ -237,8 +238,9 @@ int glm_mh_run(GlmModel &gm, const b2m_mh_args &a, cudaStream_t st) {
   if (tmp_alloc(pool, &qn, C * D) || tmp_alloc(pool, &lpn, C)) { tmp_free(pool); return 2; }
   const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
   // the cached current log-prob is recomputed at the start of every call, as metropolis.py:55 does
-  int rc = glm_logp_grad(gm, a.theta, C, a.logp, nullptr, st);
+  int rc = glm_logp_grad(gm, a.theta, C, a.logp, nullptr, st, true);
   for (int it = 0; it < a.n_iter && !rc; ++it) {
+    if (it > 0 && (it & 15) == 0) rc = glm_recenter(gm, a.theta, C, st);
     mh_propose_kernel<<<grid, 32 * WPB, 0, st>>>(a, qn, D, it);
     rc = glm_logp_grad(gm, qn, C, lpn, nullptr, st);
     mh_accept_kernel<<<grid, 32 * WPB, 0, st>>>(a, qn, lpn, D, it);
@@ -535,8 +537,9 @@ int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
 
   const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
   const int T = 32 * WPB;
-  rc = glm_logp_grad(gm, a.theta, C, W.lp, W.g, st);
+  rc = glm_logp_grad(gm, a.theta, C, W.lp, W.g, st, true);
   for (int it = 0; it < a.n_iter && !rc; ++it) {
+    if (it > 0) rc = glm_recenter(gm, a.theta, C, st);   // reference point follows the current states
     nuts_begin_kernel<<<grid, T, 0, st>>>(a, W, D, it);
     ++g_launches;
     for (int j = 0; j < MD && !rc; ++j) {

@@ -19,6 +19,7 @@
 //                 RESID: z = y - c - acc, per-row sum z^2, R = w z / sigma^2 split into tf32 hi/lo   (K5)
 //                 PLAIN: store the split-K partial of G                                              (K6)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "glm.cuh"
 
@@ -331,6 +332,13 @@ int launch_tc(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &B
 
 bool tc_available() { return encode_fn() != nullptr; }
 
+// k-blocks (of 32) accumulated inside the tensor core between two fp32 promotions; tunable for experiments
+static int chunk_kb(const char *env, int dflt) {
+  const char *v = getenv(env);
+  const int c = v ? atoi(v) : 0;
+  return c > 0 ? c : dflt;
+}
+
 int grad_block_n(const GlmModel &g) { return g.Dp % 256 == 0 ? 256 : (g.Dp % 128 == 0 ? 128 : 64); }
 
 int grad_splits(const GlmModel &g, int64_t Cp) {
@@ -349,10 +357,11 @@ int tc_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st) {
       make_map(&Bh, g.Xh, g.Np, g.Dp, 256) || make_map(&Bl, g.Xl, g.Np, g.Dp, 256))
     return 2;
   EpiParams E{};
-  E.y = g.y; E.inv_var = g.inv_var; E.Rh = g.Rh; E.Rl = g.Rl; E.ss_part = g.ss_part; E.Cp = Cp; E.Np = g.Np;
-  E.N_valid = g.N; E.loc_const = g.loc_const; E.weight = g.weight;
+  E.y = g.y0; E.inv_var = g.inv_var; E.Rh = g.Rh; E.Rl = g.Rl; E.ss_part = g.ss_part; E.Cp = Cp; E.Np = g.Np;
+  E.N_valid = g.N; E.loc_const = 0.f; E.weight = g.weight;   // y0 is already centred and shifted (glm.cu)
   dim3 grid((unsigned)(Cp / BLOCK_M), g.Np / 256, 1);
-  return launch_tc<256, true>(Ah, Al, Bh, Bl, grid, g.Dp / BLOCK_K, g.Dp / BLOCK_K, E, st);
+  return launch_tc<256, true>(Ah, Al, Bh, Bl, grid, g.Dp / BLOCK_K, g.Dp / BLOCK_K, E, st,
+                              chunk_kb("B2M_TC_CHUNK_RESID", DEFAULT_CHUNK_KB));
 }
 
 int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
@@ -368,9 +377,10 @@ int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
   E.Gpart = g.G; E.Cp = Cp; E.Dp = g.Dp;
   dim3 grid((unsigned)(Cp / BLOCK_M), g.Dp / bn, (unsigned)((kb_total + kb_per - 1) / kb_per));
   g.g_splits = (int)grid.z;
-  if (bn == 256) return launch_tc<256, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st);
-  if (bn == 128) return launch_tc<128, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st);
-  return launch_tc<64, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st);
+  const int ck = chunk_kb("B2M_TC_CHUNK_GRAD", DEFAULT_CHUNK_KB);
+  if (bn == 256) return launch_tc<256, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
+  if (bn == 128) return launch_tc<128, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
+  return launch_tc<64, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
 }
 
 
