@@ -191,6 +191,18 @@ int b2m_hmc_run(b2m_model *m, const b2m_hmc_args *a, void *stream);
 int b2m_mh_run(b2m_model *m, const b2m_mh_args *a, void *stream);
 int b2m_nuts_run(b2m_model *m, const b2m_nuts_args *a, void *stream);
 
+/* ---- observation sharding (no reference counterpart: the reference is single device) ----
+ * Every rank builds the model on its own row shard of (X, y) and holds every chain.  After b2m_model_set_comm each
+ * value+gradient of a GLM-class model sums the [C, D] gradient partial and the [C] sum of squared residuals over
+ * the ranks (one NCCL all-reduce on the caller's stream), so all ranks compute bit-identical results.
+ * NCCL is bound at run time; without it these calls return an error and everything else keeps working. */
+typedef struct b2m_comm b2m_comm;
+int b2m_comm_unique_id(uint8_t *out128);                       /* rank 0 creates the 128-byte id; caller broadcasts it */
+int b2m_comm_init(const uint8_t *id128, int32_t n_ranks, int32_t rank, b2m_comm **out);   /* collective */
+void b2m_comm_destroy(b2m_comm *c);
+int b2m_model_set_comm(b2m_model *m, b2m_comm *c, void *stream); /* collective (sums the shard row counts); c may be NULL */
+int b2m_comm_allreduce_f32(b2m_comm *c, float *buf, int64_t n, void *stream);   /* in place, sum */
+
 /* number of kernel launches this library has issued since load (bench.py's gpu_launches) */
 int64_t b2m_launch_count(void);
 

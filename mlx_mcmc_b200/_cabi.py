@@ -64,7 +64,8 @@ ABI_VERSION = 1
 
 EXPORTS = ["b2m_last_error", "b2m_abi_version", "b2m_struct_sizes", "b2m_model_create", "b2m_model_destroy",
            "b2m_model_dim", "b2m_model_class", "b2m_logp_grad", "b2m_hmc_run", "b2m_mh_run", "b2m_nuts_run",
-           "b2m_launch_count"]
+           "b2m_launch_count", "b2m_comm_unique_id", "b2m_comm_init", "b2m_comm_destroy", "b2m_model_set_comm",
+           "b2m_comm_allreduce_f32"]
 
 _lib = None
 
@@ -107,6 +108,12 @@ def load(build_if_missing: bool = True):
     lib.b2m_hmc_run.argtypes = [c_p, C.POINTER(HmcArgs), c_p]
     lib.b2m_mh_run.argtypes = [c_p, C.POINTER(MhArgs), c_p]
     lib.b2m_nuts_run.argtypes = [c_p, C.POINTER(NutsArgs), c_p]
+    lib.b2m_comm_unique_id.argtypes = [c_p]
+    lib.b2m_comm_init.argtypes = [c_p, C.c_int32, C.c_int32, C.POINTER(c_p)]
+    lib.b2m_comm_destroy.argtypes = [c_p]
+    lib.b2m_comm_destroy.restype = None
+    lib.b2m_model_set_comm.argtypes = [c_p, c_p, c_p]
+    lib.b2m_comm_allreduce_f32.argtypes = [c_p, c_p, C.c_int64, c_p]
     if lib.b2m_abi_version() != ABI_VERSION:
         raise ImportError(f"libb200mcmc.so ABI {lib.b2m_abi_version()} != binding {ABI_VERSION}")
     sizes = (C.c_int32 * 6)()

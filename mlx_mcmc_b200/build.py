@@ -18,7 +18,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libb200mcmc.so")
 STAMP = os.path.join(CSRC, ".build_stamp")
 
-SOURCES = ["capi.cu", "pointwise.cu", "nuts_pointwise.cu", "glm.cu", "glm_samplers.cu", "glm_tc.cu"]
+SOURCES = ["capi.cu", "pointwise.cu", "nuts_pointwise.cu", "glm.cu", "glm_samplers.cu", "glm_tc.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", INCLUDE,
@@ -74,7 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"],
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart", "-ldl"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -238,6 +238,42 @@ int b2m_logp_grad(b2m_model *m, const float *theta, int64_t n_chains, float *log
   return b2m::launch_logp_grad(m->km, theta, n_chains, logp, grad, lanes, static_cast<cudaStream_t>(stream));
 }
 
+struct b2m_comm {
+  b2m::Comm *c = nullptr;
+};
+
+int b2m_comm_unique_id(uint8_t *out128) {
+  B2M_REQUIRE(out128 != nullptr, "b2m_comm_unique_id: NULL argument");
+  return b2m::comm_unique_id(out128);
+}
+
+int b2m_comm_init(const uint8_t *id128, int32_t n_ranks, int32_t rank, b2m_comm **out) {
+  B2M_REQUIRE(id128 && out, "b2m_comm_init: NULL argument");
+  B2M_REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "b2m_comm_init: rank out of range");
+  *out = nullptr;
+  b2m::Comm *c = nullptr;
+  if (int rc = b2m::comm_init(id128, n_ranks, rank, &c)) return rc;
+  *out = new b2m_comm{c};
+  return 0;
+}
+
+void b2m_comm_destroy(b2m_comm *c) {
+  if (!c) return;
+  b2m::comm_destroy(c->c);
+  delete c;
+}
+
+int b2m_model_set_comm(b2m_model *m, b2m_comm *c, void *stream) {
+  B2M_REQUIRE(m != nullptr, "b2m_model_set_comm: NULL model");
+  B2M_REQUIRE(m->model_class == 1, "b2m_model_set_comm: observation sharding is defined for GLM-class models (X @ beta) only");
+  return b2m::glm_set_comm(m->glm, c ? c->c : nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int b2m_comm_allreduce_f32(b2m_comm *c, float *buf, int64_t n, void *stream) {
+  B2M_REQUIRE(c && buf && n >= 0, "b2m_comm_allreduce_f32: bad argument");
+  return b2m::comm_allreduce_f32(c->c, buf, n, static_cast<cudaStream_t>(stream));
+}
+
 int b2m_hmc_run(b2m_model *m, const b2m_hmc_args *a, void *stream) {
   B2M_REQUIRE(m && a, "b2m_hmc_run: NULL argument");
   B2M_REQUIRE(a->n_chains > 0 && a->n_iter >= 0 && a->n_leapfrog > 0, "b2m_hmc_run: bad sizes");

@@ -15,6 +15,7 @@ static int dev_alloc(T **p, size_t n) {
 
 static void free_workspace(GlmModel &g) {
   FREE(g.B); FREE(g.Bh); FREE(g.Bl); FREE(g.R); FREE(g.Rh); FREE(g.Rl); FREE(g.G); FREE(g.ss_part); FREE(g.inv_var);
+  FREE(g.red);
   g.cap = 0;
 }
 
@@ -30,7 +31,8 @@ int glm_reserve(GlmModel &g, int64_t n_chains) {
   free_workspace(g);
   g.g_splits_cap = g.use_tc ? grad_splits(g, cp) : 1;
   if (dev_alloc(&g.B, cp * g.Dp) || dev_alloc(&g.G, (size_t)g.g_splits_cap * cp * g.Dp) || dev_alloc(&g.R, cp * (size_t)g.Np) ||
-      dev_alloc(&g.ss_part, (size_t)(g.Np / 64) * cp) || dev_alloc(&g.inv_var, cp))
+      dev_alloc(&g.ss_part, (size_t)(g.Np / 64) * cp) || dev_alloc(&g.inv_var, cp) ||
+      dev_alloc(&g.red, (size_t)cp * g.Dp + cp))
     return 2;
   if (g.use_tc) {
     if (dev_alloc(&g.Bh, cp * g.Dp) || dev_alloc(&g.Bl, cp * g.Dp) || dev_alloc(&g.Rh, cp * (size_t)g.Np) ||
@@ -65,6 +67,7 @@ __global__ void pad_vector_kernel(const float *__restrict__ y, int N, int Np, fl
 
 int glm_build(GlmModel &g, const float *X, const float *y, int N, int D) {
   g.N = N; g.D = D;
+  g.N_total = N;
   g.Np = (N + 255) / 256 * 256;
   g.Dp = (D + 63) / 64 * 64;
   const size_t nd = (size_t)g.Np * g.Dp;
@@ -258,6 +261,42 @@ int simt_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
   return 0;
 }
 
+// ---------------------------------------------------------------- observation sharding: reduce + all-reduce
+// red[c, d] = sum over split-K partials of G ; red[Cp*Dp + c] = sum over column tiles of ss_part.  Fixed order.
+__global__ void __launch_bounds__(256) glm_reduce_kernel(const float *__restrict__ G, int g_splits,
+                                                         const float *__restrict__ ss_part, int n_tiles, int64_t Cp,
+                                                         int Dp, float *__restrict__ red) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nG = Cp * Dp;
+  if (i < nG) {
+    float v = 0.f;
+    for (int s = 0; s < g_splits; ++s) v += G[(int64_t)s * nG + i];
+    red[i] = v;
+  } else if (i < nG + Cp) {
+    const int64_t c = i - nG;
+    float v = 0.f;
+    for (int t = 0; t < n_tiles; ++t) v += ss_part[(int64_t)t * Cp + c];
+    red[i] = v;
+  }
+}
+
+int glm_set_comm(GlmModel &g, Comm *c, cudaStream_t st) {
+  g.comm = c;
+  g.N_total = g.N;
+  if (!c) return 0;
+  int64_t *d = nullptr, h = g.N;
+  B2M_CHECK_CUDA(cudaMalloc(&d, sizeof(int64_t)));
+  B2M_CHECK_CUDA(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  int rc = comm_allreduce_i64(c, d, 1, st);
+  if (!rc) {
+    cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    g.N_total = h;
+  }
+  cudaFree(d);
+  return rc;
+}
+
 // ---------------------------------------------------------------- finish: assemble log p and the full gradient
 // One warp per chain.  Likelihood value from the partial sums (fixed summation order => deterministic),
 // gradient of beta from G, gradient of sigma analytically, then the prior terms (generic densities)
@@ -345,9 +384,19 @@ int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float
     n_tiles = g.Np / TN;
   }
   const size_t smem = g.has_prior ? model_smem_bytes(g.prior) : 16;
+  const float *ssp = g.ss_part, *Gp = g.G;
+  int splits = g.use_tc ? g.g_splits : 1;
+  if (g.comm) {
+    // observation shard: contiguous [Cp, Dp] gradient partial || [Cp] sum z^2, summed over ranks on this stream
+    const int64_t n_red = Cp * g.Dp + Cp;
+    glm_reduce_kernel<<<(unsigned)((n_red + 255) / 256), 256, 0, st>>>(g.G, grad ? splits : 0, g.ss_part, n_tiles, Cp, g.Dp, g.red);
+    ++g_launches;
+    if (int rc = comm_allreduce_f32(g.comm, grad ? g.red : g.red + Cp * g.Dp, grad ? n_red : Cp, st)) return rc;
+    Gp = g.red; ssp = g.red + Cp * g.Dp; splits = 1; n_tiles = 1;
+  }
   glm_finish_kernel<<<(unsigned)((C + 3) / 4), 128, smem, st>>>(g.prior, g.has_prior ? 1 : 0, theta, C, Cp, g.Dtot, g.beta_off,
-                                                                 g.D, g.Dp, g.sigma_param, g.sigma_const, g.weight, g.N,
-                                                                 n_tiles, g.ss_part, g.G, g.use_tc ? g.g_splits : 1, logp, grad);
+                                                                 g.D, g.Dp, g.sigma_param, g.sigma_const, g.weight,
+                                                                 (int)g.N_total, n_tiles, ssp, Gp, splits, logp, grad);
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;

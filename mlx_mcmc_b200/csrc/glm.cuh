@@ -12,6 +12,14 @@
 
 namespace b2m {
 
+struct Comm;  // comm.cu
+int comm_unique_id(uint8_t *out128);
+int comm_init(const uint8_t *id128, int nranks, int rank, Comm **out);
+void comm_destroy(Comm *c);
+int comm_nranks(const Comm *c);
+int comm_allreduce_f32(Comm *c, float *buf, int64_t n, cudaStream_t st);
+int comm_allreduce_i64(Comm *c, int64_t *buf, int64_t n, cudaStream_t st);
+
 constexpr int kCenterSlices = 32;  // chain slices of the deterministic two-stage mean (glm.cu, centring)
 
 struct GlmModel {
@@ -41,7 +49,13 @@ struct GlmModel {
   float *ss_part = nullptr;                                  // [Np / 64, cap] per-column-tile partial sum of squares
   float *inv_var = nullptr;                                  // [cap]
   int use_tc = 0;                                            // 1: tcgen05 path, 0: SIMT path
+  // observation sharding (comm.cu): this handle holds rows [r0, r0 + N) of a model with N_total rows
+  Comm *comm = nullptr;
+  int64_t N_total = 0;
+  float *red = nullptr;                                      // [cap * Dp + cap] gradient partial || sum z^2, all-reduced
 };
+
+int glm_set_comm(GlmModel &g, Comm *c, cudaStream_t st);
 
 int glm_reserve(GlmModel &g, int64_t n_chains);
 void glm_free(GlmModel &g);

@@ -1,6 +1,7 @@
 """GPU: the public API end to end -- shapes, reproducibility, shard-independence of the random streams,
 and parity check 3 (posterior moments within 4 Monte-Carlo standard errors of closed forms / the oracle)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -230,3 +231,17 @@ def test_regression_hmc_and_metropolis_run(cuda):
         assert mcse_ok(s["beta"][:, :, d], m[d], sd[d]), d
     s, rate = B.metropolis_hastings(fn, init, num_samples=300, proposal_scale=0.03, num_chains=64, random_seed=1)
     assert s["beta"].shape == (64, 300, 4) and 0.05 < rate < 0.95
+
+
+def test_multi_gpu_sharding_when_two_gpus_are_visible(cuda):
+    """tests/mgpu_check.py under torchrun on 2 GPUs: chain sharding is bit-equal to one GPU, observation
+    sharding agrees to float32 rounding and keeps the ranks in lock-step.  Skipped on a 1-GPU box."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(root, "tests", "mgpu_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MGPU_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
