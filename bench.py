@@ -1,24 +1,30 @@
 #!/usr/bin/env python
 """Benchmark of the sampling hot path (BASELINE.json metric: leapfrog grad-evals/sec, min-ESS/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c5|...] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c1|c5] [--impl reference]
 
-Default workload (N=1) is BASELINE.json configs[1]: examples/04_event_rates.py Gamma/Exponential rate
-model, 65,536 independent chains, HMC (step 0.1, 10 leapfrog steps), chains sharded over the GPUs.
+Default workload = BASELINE.json's Target configuration (configs[3], "C4"): Bayesian linear regression with 1000
+coefficients and 100,000 observations, NUTS, 4096 chains per GPU in lock-step (it fits one GPU: X is 400 MB).  With N
+GPUs the chains shard (weak scaling: 4096 chains per GPU, no data-path collective).  The other configurations
+(`--workload`, and the `other_workloads` object of the default line) are C3 (100 x 10K regression, NUTS, 1024 chains),
+C2 (examples/04 event-rate model, 65,536 HMC chains), C1 and C5 (examples/03, 1M Metropolis chains).
 
-One *step* = one launch of the persistent HMC kernel covering ITERS whole HMC iterations (momentum
-draw, L leapfrog steps with a fused log-density+gradient each, Metropolis accept, draw written to HBM)
-for every chain of the rank.  A grad-eval = one value-and-gradient of log_prob for one chain; a step
-performs chains x ITERS x L of them (the gradient at the trajectory start is the cached one).
+A *step*:  GLM workloads (c4, c3) -- one NUTS transition of every chain of the rank (momentum draw, iterative tree
+           build with one lock-step value+gradient per leaf = two tcgen05 3xTF32 GEMMs, U-turn / slice bookkeeping,
+           draw written to HBM);
+           pointwise workloads (c2, c1, c5) -- one launch of the persistent kernel covering ITERS whole iterations.
+A *grad-eval* = one value-and-gradient of log_prob for one chain (= one leapfrog step / NUTS leaf; masked lanes of
+the lock-step are not counted).  Metropolis counts value evaluations.
 
-The JSON line also carries
-  e2e          the same metric through the public API (`hmc(...)`: host initial values -> device, warm-up
-               and sampling launches, draws copied back to pinned host memory), per step;
-  roofline     HBM roofline of the dominant kernel (algorithmic bytes = draws written + chain state
-               read/written per launch) -- this kernel is FP32-issue bound, see `issue`;
-  cpu_baseline the oracle restatement of the reference's HMC (oracle/refport, torch-CPU stand-in for MLX)
-               timed on one host core on a bounded sample of the same workload.
-`--impl reference` times that same restatement on all host cores (one independent chain per core).
+The JSON line carries
+  value        whole-job grad-evals/s over the timed region (CUDA events, inputs resident in HBM, max over ranks)
+  e2e          the same metric through the public API (`nuts(...)` / `hmc(...)`) with HOST initial values and draws
+               copied back to pinned host memory inside the timed region
+  roofline     dominant kernel against its bound: GLM -> tensor pipe (executed tf32 flops of the two GEMM kernels, each
+               timed with CUDA events on the launching stream, vs a measured tf32 cuBLAS peak); pointwise -> HBM bytes
+  cpu_baseline the oracle restatement (reference source semantics on a torch-CPU stand-in for MLX, which cannot be
+               installed here) on the box's host cores, on a bounded sample of the same workload
+`--impl reference` times that same restatement alone (rank 0 only), same metric / unit / config.
 """
 from __future__ import annotations
 
@@ -37,16 +43,21 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # name: (model factory, method, chains at N=1, sampler kwargs, iterations per step)
-    "c2": dict(model="c2_event_rate", method="hmc", chains=65536, step_size=0.1, L=10, iters=100,
-               desc="examples/04_event_rates Gamma/Exponential rate model, 65536 chains, HMC eps0=0.1 L=10"),
-    "c1": dict(model="c1_normal", method="hmc", chains=65536, step_size=0.01, L=10, iters=50,
-               desc="examples/01-02 Normal(mu,sigma) posterior, 100 obs, HMC L=10"),
-    "c5": dict(model="c5_ab_test", method="metropolis", chains=1048576, proposal_scale=0.02, iters=100,
-               desc="examples/03_ab_testing Beta A/B model, 1M Metropolis chains"),
+    "c4": dict(kind="glm", n=100000, d=1000, chains=4096, eps0=8e-4, adapt_iters=40, max_tree_depth=10,
+               desc="Bayesian linear regression 1000 params x 100K obs (README 'Large'), NUTS, 4096 chains/GPU"),
+    "c3": dict(kind="glm", n=10000, d=100, chains=1024, eps0=5e-3, adapt_iters=60, max_tree_depth=10,
+               desc="Bayesian linear regression 100 params x 10K obs (README 'Medium'), NUTS, 1024 chains/GPU"),
+    "c2": dict(kind="pointwise", model="c2_event_rate", method="hmc", chains=65536, step_size=0.1, L=10, iters=100,
+               desc="examples/04_event_rates Gamma/Exponential rate model, 65536 chains/GPU, HMC eps0=0.1 L=10"),
+    "c1": dict(kind="pointwise", model="c1_normal", method="hmc", chains=65536, step_size=0.01, L=10, iters=50,
+               desc="examples/01-02 Normal(mu,sigma) posterior, 100 obs, HMC L=10, 65536 chains/GPU"),
+    "c5": dict(kind="pointwise", model="c5_ab_test", method="metropolis", chains=1048576, proposal_scale=0.02, iters=100,
+               desc="examples/03_ab_testing Beta A/B model, 1M Metropolis chains/GPU"),
 }
 METRIC = "leapfrog_grad_evals_per_sec"
 UNIT = "grad-evals/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
+NCU_TRAFFIC = {"c4": {"bytes": 5.42e9 + 4.11e9, "source": "profiles/r01_tc_gemm_c4_v1_ncu_summary.md (K5 5.42 GB + K6 4.11 GB)"}}
 
 
 # ----------------------------------------------------------------------------------------- clocks
@@ -92,9 +103,37 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------- CPU baseline
+# ----------------------------------------------------------------------------------------- CPU baseline (oracle port)
+def _mode_numpy(X, y, iters=25):
+    """posterior mode of the regression by Richardson iteration on the normal equations (X'X ~ N I for this data)"""
+    n = X.shape[0]
+    b = np.zeros(X.shape[1], dtype=np.float64)
+    Xd = X.astype(np.float64)
+    for _ in range(iters):
+        b = b + (Xd.T @ (y.astype(np.float64) - Xd @ b) - b / 100.0) / n
+    return b.astype(np.float32)
+
+
+def _cpu_glm(wl_name: str, threads: int, n_iter: int, seed: int = 0):
+    """`n_iter` NUTS transitions of ONE chain of the regression workload on the oracle restatement, started at the
+    posterior mode with the workload's step size (no adaptation), all host threads for the matvecs."""
+    import torch
+    from oracle.ns import Tape, ns as ons, samplers
+    from mlx_mcmc_b200 import workloads as W
+    wl = WORKLOADS[wl_name]
+    torch.set_num_threads(max(threads, 1))
+    fn, init, meta = W.regression(ons, wl["n"], wl["d"], seed=0)
+    init = {"beta": _mode_numpy(meta.X, meta.y)}
+    tape = Tape()
+    t0 = time.perf_counter()
+    samplers.nuts_port(fn, init, num_samples=n_iter, num_warmup=1, step_size=wl["eps0"], adapt_step_size=False,
+                       max_tree_depth=wl["max_tree_depth"], key=ons.mx.random.key(seed), tape=tape)
+    dt = time.perf_counter() - t0
+    return tape.leapfrogs, dt, tape.grad_evals
+
+
 def _cpu_chain(args):
-    """one chain of the oracle restatement (runs in a worker process)"""
+    """one chain of the oracle restatement of a pointwise workload (runs in a worker process)"""
     wl_name, seed, n_warm, n_samp = args
     from oracle.ns import Tape, ns as ons, samplers
     from mlx_mcmc_b200 import workloads as W
@@ -103,110 +142,318 @@ def _cpu_chain(args):
     tape = Tape()
     t0 = time.perf_counter()
     if wl["method"] == "hmc":
-        s, _, _ = samplers.hmc_port(fn, init, num_samples=n_samp, num_warmup=n_warm, step_size=wl["step_size"],
-                                    num_leapfrog_steps=wl["L"], key=ons.mx.random.key(seed), tape=tape)
+        samplers.hmc_port(fn, init, num_samples=n_samp, num_warmup=n_warm, step_size=wl["step_size"],
+                          num_leapfrog_steps=wl["L"], key=ons.mx.random.key(seed), tape=tape)
         evals = tape.leapfrogs
     else:
-        s, _ = samplers.run_port(fn, init, num_samples=n_samp, num_warmup=n_warm, method="metropolis",
-                                 proposal_scale=wl["proposal_scale"], random_seed=seed, tape=tape)
+        samplers.run_port(fn, init, num_samples=n_samp, num_warmup=n_warm, method="metropolis",
+                          proposal_scale=wl["proposal_scale"], random_seed=seed, tape=tape)
         evals = n_samp + n_warm
-    dt = time.perf_counter() - t0
-    return evals, dt, tape.grad_evals
+    return evals, time.perf_counter() - t0, tape.grad_evals
 
 
-def cpu_baseline(wl_name: str, cores: int, n_warm=150, n_samp=350):
-    """Oracle port on `cores` host cores, one independent chain per core (the reference is a single
-    Python thread per chain).  Returns the cpu_baseline object."""
-    jobs = [(wl_name, 1000 + i, n_warm, n_samp) for i in range(cores)]
+def cpu_baseline(wl_name: str, cores: int, scale: float = 1.0):
+    """The oracle port on `cores` host cores on a bounded sample of the workload.  Returns the cpu_baseline object.
+    GLM: one chain, the matvecs use `cores` torch threads.  Pointwise: one independent chain per core (the
+    reference is a single Python thread per chain)."""
+    wl = WORKLOADS[wl_name]
     t0 = time.perf_counter()
-    if cores == 1:
-        res = [_cpu_chain(jobs[0])]
+    if wl["kind"] == "glm":
+        n_iter = max(1, int(round((2 if wl_name == "c4" else 20) * scale)))
+        evals, busy, grads = _cpu_glm(wl_name, cores, n_iter)
+        sample = (f"1 chain x {n_iter} NUTS transition(s) (+1 warm-up transition) from the posterior mode, step size "
+                  f"{wl['eps0']}, no adaptation, on the oracle restatement (reference source semantics on a torch-CPU "
+                  f"stand-in for MLX) with {cores} torch threads; one leaf counted as one grad-eval (the reference spends "
+                  f"2 mx.grad + 2 value traces per leaf: {grads} mx.grad calls here)")
     else:
-        import multiprocessing as mp
-        with mp.get_context("spawn").Pool(cores) as pool:
-            res = pool.map(_cpu_chain, jobs)
+        n_warm, n_samp = max(10, int(150 * scale)), max(20, int(350 * scale))
+        jobs = [(wl_name, 1000 + i, n_warm, n_samp) for i in range(cores)]
+        if cores == 1:
+            res = [_cpu_chain(jobs[0])]
+        else:
+            import multiprocessing as mp
+            with mp.get_context("spawn").Pool(cores) as pool:
+                res = pool.map(_cpu_chain, jobs)
+        evals, busy, grads = sum(r[0] for r in res), max(r[1] for r in res), sum(r[2] for r in res)
+        sample = (f"{cores} chain(s) x ({n_warm} warm-up + {n_samp} draws) of the same model/sampler settings on the "
+                  f"oracle restatement (reference source semantics on a torch-CPU stand-in for MLX); one leapfrog step "
+                  f"counted as one grad-eval (the reference spends 2 mx.grad + value traces per step: {grads} mx.grad "
+                  f"calls here)")
     wall = time.perf_counter() - t0
-    evals = sum(r[0] for r in res)
-    busy = max(r[1] for r in res)
-    return {"value": evals / busy, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{cores} chain(s) x ({n_warm} warm-up + {n_samp} draws) of the same model/sampler settings on the "
-                      f"oracle restatement (reference source semantics on a torch-CPU stand-in for MLX); one leapfrog "
-                      f"step counted as one grad-eval (the reference spends 2 mx.grad + value traces per step: "
-                      f"{sum(r[2] for r in res)} mx.grad calls here); wall {wall:.1f}s"}
+    return {"value": evals / busy, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f"; wall {wall:.1f}s"}
 
 
-# ----------------------------------------------------------------------------------------- main
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-ess", action="store_true")
-    args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": wl["desc"], "chains_per_gpu": args.chains or wl["chains"], "iters_per_step": wl["iters"],
-              "sharding": "chains (no data-path collective)", "l2": "flushed between timed steps (256 MiB write)"}
+def reference_arm(args, wl, config):
+    cores = os.cpu_count() or 1
+    if wl["kind"] == "pointwise":
+        cores = min(cores, 32)
+    W_, K = max(args.warmup, 0), max(args.steps, 1)
+    for _ in range(min(W_, 1)):
+        cpu_baseline(args.workload, cores, 0.2)
+    vals, t0, per = [], time.perf_counter(), None
+    for _ in range(K):
+        per = cpu_baseline(args.workload, cores, 0.5)
+        vals.append(per["value"])
+        if time.perf_counter() - t0 > 150:
+            break
+    v = float(np.mean(vals))
+    per["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": min(W_, 1), "ms_per_step": 1e3 * (time.perf_counter() - t0) / len(vals), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": per, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
 
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        cores = os.cpu_count() or 1
-        W_, K = max(args.warmup, 0), max(args.steps, 1)
-        # each step is a bounded sample: one short chain per core
-        for _ in range(min(W_, 1)):
-            cpu_baseline(args.workload, cores, 20, 30)
-        vals, t0 = [], time.perf_counter()
-        per = None
-        for _ in range(K):
-            per = cpu_baseline(args.workload, cores, 30, 70)
-            vals.append(per["value"])
-            if time.perf_counter() - t0 > 150:
-                break
-        v = float(np.mean(vals))
-        per["value"] = v
-        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-                "warmup": min(W_, 1), "ms_per_step": 1e3 * (time.perf_counter() - t0) / len(vals), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": per, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
 
-    import torch
-    import torch.distributed as dist
-    import mlx_mcmc_b200 as B
+# ----------------------------------------------------------------------------------------- helpers
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def tf32_peak_probe(torch):
+    """cuBLAS tf32 GEMM 8192^3 on fp32 inputs: best of 6 (burst) -- the measured tensor-pipe peak for kind::tf32."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(8192, 8192, device="cuda")
+        b = torch.randn(8192, 8192, device="cuda")
+        (a @ b)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            (a @ b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+class Timed:
+    """K CUDA-event-timed steps with an L2 flush before each (not timed)."""
+
+    def __init__(self, torch, steps):
+        self.torch = torch
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        self.ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+
+    def run(self, step_fn):
+        for a, b in self.ev:
+            self.flush.fill_(1)
+            a.record()
+            step_fn()
+            b.record()
+
+    def total_ms(self):
+        return float(sum(a.elapsed_time(b) for a, b in self.ev))
+
+
+# ----------------------------------------------------------------------------------------- GLM workloads (c4, c3)
+def glm_setup(torch, B, wl, C, chain_offset, seed):
+    """model + chains started in the posterior's typical set + dual-averaging warm-up (all untimed)."""
+    from mlx_mcmc_b200 import _cabi, workloads as W
+    from mlx_mcmc_b200.engine import ChainState, compile_model, launch_nuts
+    fn, init, meta = W.regression(B.ns, wl["n"], wl["d"], seed=0)
+    model = compile_model(fn, init)
+    N, D = wl["n"], wl["d"]
+    # posterior mode by Richardson iteration on the device gradient (X'X ~ N I for this synthetic X)
+    th = torch.zeros(128, D, device="cuda")
+    for _ in range(25):
+        _, g = model.logp_grad(th)
+        th = th + g / N
+    mode = th[0].clone()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + chain_offset)
+    theta = mode[None, :] + torch.randn(C, D, device="cuda", generator=gen) / (N ** 0.5)
+    st = ChainState(model, theta.contiguous(), wl["eps0"], chain_offset)
+    st.da_state[:, 0] = 0.0
+    st.da_state[:, 1] = 1.0
+    st.da_state[:, 2] = float(np.log(np.float32(10.0 * wl["eps0"])))
+    log(f"{wl['desc'][:40]}: model on device, mode found; adapting step sizes ({wl['adapt_iters']} iterations)")
+    # adaptation runs with a shallower tree cap: the reference's dual averaging starts at 10 x eps0 and
+    # overshoots down before settling, and a depth-10 tree of lock-step leaves is ~9 s at C4
+    launch_nuts(st, wl["adapt_iters"], min(6, wl["max_tree_depth"]), _cabi.ADAPT_DUAL_AVERAGING, _cabi.COMPAT_CORRECT, 0.65, seed, 0)
+    st.step_size.copy_(st.da_state[:, 1])
+    torch.cuda.synchronize()
+    log(f"adapted: median step size {float(st.step_size.median()):.3e}")
+    return fn, meta, model, st, mode
+
+
+def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, full=True):
+    import mlx_mcmc_b200.core as mx
+    from mlx_mcmc_b200 import _cabi
+    from mlx_mcmc_b200.diagnostics import ess_geyer
+    from mlx_mcmc_b200.engine import launch_nuts
+    C = args.chains or wl["chains"]
+    chain_offset = rank * C
+    seed = 1234
+    N, D, MD = wl["n"], wl["d"], wl["max_tree_depth"]
+    fn, meta, model, st, mode = glm_setup(torch, B, wl, C, chain_offset, seed)
+    it0 = [wl["adapt_iters"]]
+    draws = torch.empty((1, C, D), dtype=torch.float32, device="cuda")
+    depths = torch.empty((1, C), dtype=torch.int32, device="cuda")
+
+    def one_step():
+        launch_nuts(st, 1, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, it0[0], draws=draws, depths=depths)
+        it0[0] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = max(args.warmup, 3)
+    timed = Timed(torch, args.steps)
+    for _ in range(warm):
+        timed.flush.fill_(1)
+        one_step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    leaves0 = int(st.n_leaves.sum().item())
+    n0 = lib.b2m_launch_count()
+    barrier()
+    timed.run(one_step)
+    barrier()
+    launches = lib.b2m_launch_count() - n0
+    leaves = int(st.n_leaves.sum().item()) - leaves0
+    total_ms = timed.total_ms()
+    mean_depth = float(depths.float().mean().item())
+
+    # ---- e2e: public API, HOST initial values in, draws back to pinned host memory, inside the timed region
+    S_e2e, e2e_steps = 2, max(2, min(args.steps, 3))
+    host_theta = st.theta.cpu().numpy().copy()                    # [C, D] per-chain starting points (host memory)
+    host_init = {"beta": np.zeros(D, dtype=np.float32)}
+    eps_host = float(st.step_size.median().item())
+
+    def api_call(k):
+        return B.nuts(fn, host_init, num_samples=S_e2e, num_warmup=1, step_size=eps_host, max_tree_depth=MD,
+                      adapt_step_size=False, key=mx.random.key(100 + k), num_chains=C, chain_offset=chain_offset,
+                      compat="correct", return_info=True, theta0=host_theta)
+
+    api_call(0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_evals = 0
+    for k in range(e2e_steps):
+        _, _, info = api_call(k + 1)
+        e2e_evals += info.grad_evals
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clock_info = clocks.stop()
+    log(f"timed {args.steps} steps: {total_ms / args.steps:.1f} ms/step, mean depth {mean_depth:.2f}; e2e {e2e_s:.1f}s")
+
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([leaves, e2e_evals, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms, e2e_s = float(t[0]), float(t[1])
+    leaves_all, e2e_all, launches_all = float(cnt[0]), float(cnt[1]), int(cnt[2])
+    value = leaves_all / (total_ms * 1e-3)
+    out = {"value": value, "ms_per_step": total_ms / args.steps, "gpu_launches": launches_all, "clocks": clock_info,
+           "e2e": {"value": e2e_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": C * D * 4, "d2h_bytes_per_step": S_e2e * C * D * 4,
+                   "call": f"nuts(num_warmup=1, num_samples={S_e2e}, num_chains={C}, adapt_step_size=False) with [C, D] host "
+                           f"initial values; draws returned as host numpy"},
+           "config_extra": {"chains_per_gpu": C, "iters_per_step": 1, "mean_tree_depth": mean_depth,
+                            "grad_evals_per_step_per_gpu": leaves / args.steps,
+                            "adapted_step_size_median": eps_host}}
+    if rank != 0:
+        return out
+
+    # ---- roofline of the dominant kernels: every GEMM launch of a few lock-step evaluations timed with CUDA events
+    peaks = load_peaks()
+    tf32_probe = tf32_peak_probe(torch)
+    lib.b2m_profile(1)
+    reps = 6
+    for _ in range(reps):
+        model.logp_grad(st.theta)
+    import ctypes
+    four = (ctypes.c_double * 4)()
+    lib.b2m_profile_read(four)
+    lib.b2m_profile(0)
+    k5_ms, k5_n, k6_ms, k6_n = [float(x) for x in four]
+    useful_per_gemm = 2.0 * N * D * C                        # flops of one contraction for all chains
+    k5 = k5_ms / max(k5_n, 1)
+    k6 = k6_ms / max(k6_n, 1)
+    both = k5 + k6
+    executed_tflops = 3 * 2 * useful_per_gemm / (both * 1e-3) / 1e12
+    bf16_half = 0.5 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 0.0)) or 0.0)
+    peak = max(tf32_probe, bf16_half) if bf16_half else tf32_probe
+    alg_bytes = 4.0 * (N * D + N + 2 * C * D)
+    traffic = NCU_TRAFFIC.get(wl_name)
+    out["roofline"] = {
+        "bound": "tensor", "achieved": executed_tflops, "peak": peak, "unit": "TFLOP/s", "frac": executed_tflops / peak,
+        "traffic": traffic["bytes"] if traffic else None,
+        "kernel": "tc_gemm_kernel<256,RESID> (K5: M = (beta-beta0) X^T + residual epilogue) + tc_gemm_kernel<*,PLAIN> (K6: G = R X)",
+        "avg_launch_ms": {"K5": k5, "K6": k6}, "launches_timed": int(k5_n + k6_n),
+        "executed_tf32_tflops": {"K5": 3 * useful_per_gemm / (k5 * 1e-3) / 1e12, "K6": 3 * useful_per_gemm / (k6 * 1e-3) / 1e12},
+        "useful_tflops": 2 * useful_per_gemm / (both * 1e-3) / 1e12,
+        "peak_source": f"max(cuBLAS tf32 8192^3 probe in this run = {tf32_probe:.1f}, 0.5 x bf16_tflops_sustained of "
+                       f"MEASURED_PEAKS.json = {bf16_half:.1f})",
+        "algorithmic_bytes_per_eval": alg_bytes,
+        "logical_GBps_per_chain_view": 4.0 * N * D * C / (both * 1e-3) / 1e9,
+        "hbm_peak_GBps": float(peaks.get("hbm_gbs", 6650.0)),
+        "traffic_source": traffic["source"] if traffic else None,
+        "note": "achieved = executed tf32 flops (3 MMAs per useful product: 3xTF32 is what north_star prescribes to hold "
+                "1e-5) of one lock-step value+gradient / (K5 + K6 launch time); useful_tflops = 4 N D C / t.  "
+                "logical_GBps_per_chain_view = C x 4 N D / t is the north-star's 'HBM roofline per gradient eval' reading "
+                "(each chain would stream X once per gradient if it ran alone); the batch actually moves "
+                "algorithmic_bytes_per_eval."}
+    out["issue"] = {"grad_evals_per_s_per_gpu": value / world, "lockstep_eval_ms": both, "nuts_step_ms": total_ms / args.steps}
+
+    log("roofline pass done")
+    if full and not args.no_ess:
+        S = 40
+        dr = torch.empty((S, C, D), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        launch_nuts(st, S, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, it0[0], draws=dr)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        it0[0] += S
+        sub = dr[:, :: max(C // 64, 1), :: max(D // 16, 1)].cpu().numpy()        # [S, 64 chains, 16 params]
+        ess = np.array([[ess_geyer(sub[:, c, p]) for p in range(sub.shape[2])] for c in range(sub.shape[1])])
+        per_chain_min = float(np.min(np.mean(ess, axis=0)))                       # min over params of mean-over-chains ESS
+        out["ess"] = {"min_ess_per_s_geyer": per_chain_min * C / wall, "draws": S, "wall_s": wall, "chains": C,
+                      "min_over_params_mean_ess_per_chain": per_chain_min,
+                      "note": "sampling phase only (adapted chains), Geyer ESS on 64 chains x 16 coefficients scaled to all "
+                              "chains; per GPU"}
+    return out
+
+
+# ----------------------------------------------------------------------------------------- pointwise workloads
+def bench_pointwise(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, full=True):
     import mlx_mcmc_b200.core as mx
     from mlx_mcmc_b200 import _cabi, workloads as W
     from mlx_mcmc_b200.diagnostics import compute_ess, ess_geyer, min_ess
     from mlx_mcmc_b200.engine import ChainState, compile_model, launch_hmc, launch_mh
-
-    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = _cabi.load(build_if_missing=False)
-
-    C = args.chains or wl["chains"]            # weak scaling: per-GPU work fixed
+    C = args.chains or wl["chains"]
     chain_offset = rank * C
     fn, init, meta = W.ALL_SMALL[wl["model"]](B.ns)
     model = compile_model(fn, init)
     D, ITERS = model.D, wl["iters"]
     st = ChainState(model, model.pack(init, C), wl.get("step_size", 0.0), chain_offset)
     draws = torch.empty((ITERS, C, D), dtype=torch.float32, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     seed = 1234
-
-    # untimed: adapt the step size exactly as run() would (reference rule, 300 iterations)
-    if wl["method"] == "hmc":
+    if wl["method"] == "hmc":   # untimed: adapt the step size exactly as run() would (reference rule, 300 iterations)
         launch_hmc(st, 300, wl["L"], _cabi.ADAPT_REFERENCE, 0.8, seed, 0)
         st.reset_counters()
-
     it_count = [300]
 
     def one_step():
@@ -223,30 +470,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    timed = Timed(torch, args.steps)
     for _ in range(max(args.warmup, 3)):
-        flush.fill_(1)
+        timed.flush.fill_(1)
         one_step()
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
     n0 = lib.b2m_launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    for a, b in ev:
-        flush.fill_(1)                                  # evict L2 between timed steps (not timed)
-        a.record()
-        one_step()
-        b.record()
+    timed.run(one_step)
     barrier()
     launches = lib.b2m_launch_count() - n0
-    kernel_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(kernel_ms))
+    total_ms = timed.total_ms()
 
-    # ---- e2e: the public API call with host buffers, per step
     e2e_steps = max(2, min(args.steps, 5))
     n_warm_e2e = ITERS
-    h2d = C * D * 4
-    d2h = ITERS * C * D * 4
 
     def api_call(k):
         if wl["method"] == "hmc":
@@ -259,63 +498,121 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        out = api_call(k + 1)
+        api_call(k + 1)
     barrier()
     e2e_s = time.perf_counter() - t0
     clock_info = clocks.stop()
     e2e_evals = e2e_steps * C * ((ITERS + n_warm_e2e) * wl["L"] if wl["method"] == "hmc" else ITERS)
 
-    # ---- max over ranks
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_s = float(t[0]), float(t[1])
     value = world * evals_per_step * args.steps / (total_ms * 1e-3)
-    e2e_value = world * e2e_evals / e2e_s
+    out = {"value": value, "ms_per_step": total_ms / args.steps, "gpu_launches": int(launches) * world, "clocks": clock_info,
+           "e2e": {"value": world * e2e_evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": C * D * 4,
+                   "d2h_bytes_per_step": ITERS * C * D * 4,
+                   "call": f"hmc(num_warmup={n_warm_e2e}, num_samples={ITERS}, num_chains={C})" if wl["method"] == "hmc"
+                   else f"metropolis_hastings(num_samples={ITERS}, num_chains={C})"},
+           "config_extra": {"chains_per_gpu": C, "iters_per_step": ITERS}}
+    if rank != 0:
+        return out
+    peaks = load_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    launch_ms = total_ms / max(launches, 1)
+    alg_bytes = ITERS * C * D * 4 + C * (D * 4 + 8 + 16) * 2     # draws written + chain state read and written back
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                       "traffic": None, "kernel": "hmc_kernel" if wl["method"] == "hmc" else "mh_kernel",
+                       "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                       "note": "observations live in shared memory; the kernel is FP32-issue bound, not HBM bound -- see `issue` "
+                               "and profiles/r01_hmc_kernel_c2_v1_ncu_summary.md"}
+    out["issue"] = {"grad_evals_per_s_per_gpu": value / world, "obs_terms_per_s_per_gpu": value / world * getattr(meta, "N", 0),
+                    "avg_launch_ms": launch_ms}
+    if full and not args.no_ess and wl["method"] == "hmc":
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        s, rate = B.hmc(fn, init, num_samples=1000, num_warmup=1000, step_size=wl["step_size"], num_leapfrog_steps=wl["L"],
+                        key=mx.random.key(99), num_chains=C)
+        wall = time.perf_counter() - t0
+        out["ess"] = {"min_ess_per_s_geyer": min_ess(s, C, ess_geyer) / wall,
+                      "min_ess_per_s_reference_estimator": min_ess(s, C, compute_ess) / wall,
+                      "accept_rate": rate, "run": "1000 warm-up + 1000 draws", "wall_s": wall, "chains": C,
+                      "note": "ESS summed over a strided subset of 256 chains scaled to all chains; per GPU"}
+    return out
+
+
+# ----------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ess", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other configurations")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": wl["desc"], "chains_per_gpu": args.chains or wl["chains"],
+              "sharding": "chains (no data-path collective; weak scaling: per-GPU chains fixed)",
+              "l2": "flushed between timed steps (256 MiB write)"}
+    if wl["kind"] == "glm":
+        config.update({"n_obs": wl["n"], "n_params": wl["d"], "sampler": "NUTS (iterative lock-step tree, compat=correct, "
+                       f"max_tree_depth={wl['max_tree_depth']}, per-chain dual-averaged step size, identity mass matrix)",
+                       "arithmetic": "3xTF32 tcgen05 GEMMs, fp32 accumulate, centred contraction"})
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args, wl, config)
+
+    import torch
+    import torch.distributed as dist
+    import mlx_mcmc_b200 as B
+    from mlx_mcmc_b200 import _cabi
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _cabi.load(build_if_missing=False)
+
+    run = bench_glm if wl["kind"] == "glm" else bench_pointwise
+    res = run(torch, dist, B, lib, args, wl, args.workload, rank, world, local_rank)
 
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        launch_ms = total_ms / max(launches, 1)
-        # algorithmic bytes per launch: draws written + chain state read and written back
-        state_bytes = C * (D * 4 + 8 + 16) * 2
-        alg_bytes = ITERS * C * D * 4 + state_bytes
-        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "kernel": "hmc_kernel" if wl["method"] == "hmc" else "mh_kernel",
-                    "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-                    "note": "observations live in shared memory; the kernel is FP32-issue bound, not HBM bound -- see `issue`"}
-        n_obs = getattr(meta, "N", 0)
-        issue = {"grad_evals_per_s_per_gpu": value / world, "obs_terms_per_s_per_gpu": value / world * n_obs,
-                 "avg_launch_ms": launch_ms}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "clocks": clock_info, "gpu_launches": int(launches),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "call": f"hmc(num_warmup={n_warm_e2e}, num_samples={ITERS}, num_chains={C})" if wl["method"] == "hmc"
-                        else f"metropolis_hastings(num_samples={ITERS}, num_chains={C})"},
-                "roofline": roofline, "issue": issue}
-        if not args.no_ess and wl["method"] == "hmc":
-            # min-ESS/s of a full run() through the API (1000 warm-up + 1000 draws), wall clock incl. D2H
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            s, rate = B.hmc(fn, init, num_samples=1000, num_warmup=1000, step_size=wl["step_size"], num_leapfrog_steps=wl["L"],
-                            key=mx.random.key(99), num_chains=C)
-            wall = time.perf_counter() - t0
-            line["ess"] = {"min_ess_per_s_geyer": min_ess(s, C, ess_geyer) / wall,
-                           "min_ess_per_s_reference_estimator": min_ess(s, C, compute_ess) / wall,
-                           "accept_rate": rate, "run": "1000 warm-up + 1000 draws", "wall_s": wall, "chains": C,
-                           "note": "ESS summed over a strided subset of 256 chains scaled to all chains; per GPU"}
+        config.update(res.pop("config_extra"))
+        line = {"metric": METRIC, "value": res.pop("value"), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config}
+        line.update(res)
+        if world == 1 and not args.no_others:
+            others = {}
+            small = argparse.Namespace(**vars(args))
+            small.steps, small.warmup, small.chains, small.no_ess = 5, 3, 0, True
+            for name in ("c3", "c2", "c5"):
+                if name == args.workload:
+                    continue
+                w2 = WORKLOADS[name]
+                r2 = (bench_glm if w2["kind"] == "glm" else bench_pointwise)(torch, dist, B, lib, small, w2, name, 0, 1,
+                                                                             local_rank, full=False)
+                others[name] = {"workload": w2["desc"], "value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms_per_step"],
+                                "e2e": r2["e2e"]["value"], "roofline": {k: r2["roofline"][k] for k in
+                                                                       ("bound", "achieved", "peak", "unit", "frac", "kernel")},
+                                "config": r2["config_extra"]}
+            line["other_workloads"] = others
+        log("device part done; cpu baseline")
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.workload, 1)
+            line["cpu_baseline"] = cpu_baseline(args.workload, (os.cpu_count() or 1) if wl["kind"] == "glm" else 1)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -203,6 +203,12 @@ void b2m_comm_destroy(b2m_comm *c);
 int b2m_model_set_comm(b2m_model *m, b2m_comm *c, void *stream); /* collective (sums the shard row counts); c may be NULL */
 int b2m_comm_allreduce_f32(b2m_comm *c, float *buf, int64_t n, void *stream);   /* in place, sum */
 
+/* Instrumentation: CUDA-event timing of every GEMM launch of the GLM class, on the launching stream.
+ * b2m_profile(1) resets and starts recording, b2m_profile(0) stops; b2m_profile_read synchronises the device and
+ * returns {K5 total ms, K5 launches, K6 total ms, K6 launches}. */
+int b2m_profile(int32_t enable);
+int b2m_profile_read(double *out4);
+
 /* number of kernel launches this library has issued since load (bench.py's gpu_launches) */
 int64_t b2m_launch_count(void);
 

@@ -134,6 +134,16 @@ int b2m_debug_tc_gemm(const float *A, const float *Bm, int M, int N, int K, floa
   return b2m::debug_tc_gemm(A, Bm, M, N, K, C, chunk_kb, mma_mask, static_cast<cudaStream_t>(stream));
 }
 
+int b2m_profile(int32_t enable) {
+  b2m::tc_profile(enable != 0);
+  return 0;
+}
+
+int b2m_profile_read(double *out4) {
+  B2M_REQUIRE(out4 != nullptr, "b2m_profile_read: NULL argument");
+  return b2m::tc_profile_read(out4);
+}
+
 int b2m_struct_sizes(int32_t *out6) {
   out6[0] = (int32_t)sizeof(b2m_term);
   out6[1] = (int32_t)sizeof(b2m_operand);

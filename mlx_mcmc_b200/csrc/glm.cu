@@ -23,6 +23,10 @@ void glm_free(GlmModel &g) {
   free_workspace(g);
   FREE(g.X); FREE(g.XT); FREE(g.Xh); FREE(g.Xl); FREE(g.XTh); FREE(g.XTl); FREE(g.y);
   FREE(g.y0); FREE(g.beta0); FREE(g.center_part);
+  FREE(g.ws);
+  g.ws_cap = 0;
+  if (g.h_flag) cudaFreeHost(g.h_flag);
+  g.h_flag = nullptr;
 }
 
 int glm_reserve(GlmModel &g, int64_t n_chains) {

@@ -49,6 +49,10 @@ struct GlmModel {
   float *ss_part = nullptr;                                  // [Np / 64, cap] per-column-tile partial sum of squares
   float *inv_var = nullptr;                                  // [cap]
   int use_tc = 0;                                            // 1: tcgen05 path, 0: SIMT path
+  // sampler workspace (glm_samplers.cu): one arena reused across calls, plus a pinned host flag
+  char *ws = nullptr;
+  size_t ws_cap = 0;
+  int *h_flag = nullptr;
   // observation sharding (comm.cu): this handle holds rows [r0, r0 + N) of a model with N_total rows
   Comm *comm = nullptr;
   int64_t N_total = 0;
@@ -73,6 +77,8 @@ int simt_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st);    // R -> G
 int tc_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st);
 int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st);
 bool tc_available();
+void tc_profile(bool enable);
+int tc_profile_read(double *out4);
 int grad_splits(const GlmModel &g, int64_t Cp);
 
 int glm_hmc_run(GlmModel &g, const b2m_hmc_args &a, cudaStream_t st);

@@ -150,27 +150,46 @@ __global__ void __launch_bounds__(32 * WPB) hmc_end_kernel(b2m_hmc_args A, HmcBu
   }
 }
 
-template <typename T>
-static int tmp_alloc(std::vector<void *> &pool, T **p, size_t n) {
-  B2M_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(p), sizeof(T) * (n ? n : 1)));
-  pool.push_back(*p);
+// Workspace: carved from one arena owned by the model handle and reused across calls (a sampler call per
+// iteration must not pay for dozens of cudaMalloc / cudaFree).  `take` is run twice: once on an empty arena to
+// measure, once on the real one to assign.
+struct Arena {
+  char *base = nullptr;
+  size_t off = 0;
+  template <typename T>
+  void take(T **p, size_t n) {
+    off = (off + 255) & ~size_t(255);
+    *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+    off += sizeof(T) * (n ? n : 1);
+  }
+};
+
+static int arena_reserve(GlmModel &g, size_t bytes) {
+  if (bytes > g.ws_cap) {
+    if (g.ws) cudaFree(g.ws);
+    g.ws = nullptr;
+    g.ws_cap = 0;
+    B2M_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(&g.ws), bytes));
+    g.ws_cap = bytes;
+  }
+  if (!g.h_flag) B2M_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void **>(&g.h_flag), sizeof(int)));
   return 0;
-}
-static void tmp_free(std::vector<void *> &pool) {
-  for (void *p : pool) cudaFree(p);
-  pool.clear();
 }
 
 int glm_hmc_run(GlmModel &gm, const b2m_hmc_args &a, cudaStream_t st) {
   const int64_t C = a.n_chains;
   const int D = gm.Dtot;
-  std::vector<void *> pool;
   HmcBufs W{};
-  if (tmp_alloc(pool, &W.p, C * D) || tmp_alloc(pool, &W.g, C * D) || tmp_alloc(pool, &W.qn, C * D) ||
-      tmp_alloc(pool, &W.gn, C * D) || tmp_alloc(pool, &W.lp, C) || tmp_alloc(pool, &W.lpn, C) || tmp_alloc(pool, &W.h0, C)) {
-    tmp_free(pool);
-    return 2;
-  }
+  auto layout = [&](Arena &A) {
+    A.take(&W.p, C * D); A.take(&W.g, C * D); A.take(&W.qn, C * D); A.take(&W.gn, C * D);
+    A.take(&W.lp, C); A.take(&W.lpn, C); A.take(&W.h0, C);
+  };
+  Arena probe;
+  layout(probe);
+  if (int rc0 = arena_reserve(gm, probe.off)) return rc0;
+  Arena real;
+  real.base = gm.ws;
+  layout(real);
   const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
   int rc = glm_logp_grad(gm, a.theta, C, W.lp, W.g, st, true);
   for (int it = 0; it < a.n_iter && !rc; ++it) {
@@ -188,7 +207,6 @@ int glm_hmc_run(GlmModel &gm, const b2m_hmc_args &a, cudaStream_t st) {
     ++g_launches;
   }
   cudaError_t e = cudaStreamSynchronize(st);
-  tmp_free(pool);
   if (rc) return rc;
   B2M_CHECK_CUDA(e);
   B2M_CHECK_CUDA(cudaGetLastError());
@@ -233,9 +251,14 @@ __global__ void __launch_bounds__(32 * WPB) mh_accept_kernel(b2m_mh_args A, cons
 int glm_mh_run(GlmModel &gm, const b2m_mh_args &a, cudaStream_t st) {
   const int64_t C = a.n_chains;
   const int D = gm.Dtot;
-  std::vector<void *> pool;
-  float *qn, *lpn;
-  if (tmp_alloc(pool, &qn, C * D) || tmp_alloc(pool, &lpn, C)) { tmp_free(pool); return 2; }
+  float *qn = nullptr, *lpn = nullptr;
+  auto layout = [&](Arena &A) { A.take(&qn, C * D); A.take(&lpn, C); };
+  Arena probe;
+  layout(probe);
+  if (int rc0 = arena_reserve(gm, probe.off)) return rc0;
+  Arena real;
+  real.base = gm.ws;
+  layout(real);
   const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
   // the cached current log-prob is recomputed at the start of every call, as metropolis.py:55 does
   int rc = glm_logp_grad(gm, a.theta, C, a.logp, nullptr, st, true);
@@ -247,7 +270,6 @@ int glm_mh_run(GlmModel &gm, const b2m_mh_args &a, cudaStream_t st) {
     g_launches += 2;
   }
   cudaError_t e = cudaStreamSynchronize(st);
-  tmp_free(pool);
   if (rc) return rc;
   B2M_CHECK_CUDA(e);
   B2M_CHECK_CUDA(cudaGetLastError());
@@ -514,26 +536,31 @@ __global__ void __launch_bounds__(32 * WPB) nuts_end_kernel(b2m_nuts_args A, Nut
 int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   const int64_t C = a.n_chains;
   const int D = gm.Dtot, MD = a.max_tree_depth;
-  std::vector<void *> pool;
   NutsBufs W{};
   const size_t cd = (size_t)C * D;
-  float **vecs[] = {&W.g, &W.p0, &W.q_lo, &W.p_lo, &W.g_lo, &W.q_hi, &W.p_hi, &W.g_hi, &W.cq, &W.cg,
-                    &W.fq, &W.fp, &W.fg, &W.sfq, &W.sfp, &W.scq, &W.scg};
+  auto layout = [&](Arena &A) {
+    float **vecs[] = {&W.g, &W.p0, &W.q_lo, &W.p_lo, &W.g_lo, &W.q_hi, &W.p_hi, &W.g_hi, &W.cq, &W.cg,
+                      &W.fq, &W.fp, &W.fg, &W.sfq, &W.sfp, &W.scq, &W.scg};
+    for (auto v : vecs) A.take(v, cd);
+    float **stk[] = {&W.st_fq, &W.st_fp, &W.st_cq, &W.st_cg};
+    for (auto v : stk) A.take(v, cd * MD);
+    float **fs[] = {&W.lp, &W.clp, &W.h0, &W.log_slice, &W.flp, &W.sclp, &W.feps, &W.heps};
+    for (auto v : fs) A.take(v, C);
+    int **is[] = {&W.n, &W.s, &W.v, &W.leaf, &W.building, &W.sub_n, &W.sub_na, &W.sub_s, &W.alpha_cnt, &W.depth};
+    for (auto v : is) A.take(v, C);
+    A.take(&W.alpha_sum, C); A.take(&W.sub_alpha, C);
+    A.take(&W.st_clp, (size_t)C * MD); A.take(&W.st_n, (size_t)C * MD); A.take(&W.st_na, (size_t)C * MD);
+    A.take(&W.st_alpha, (size_t)C * MD);
+    A.take(&W.any_active, 1);
+  };
+  Arena probe;
+  layout(probe);
+  if (int rc0 = arena_reserve(gm, probe.off)) return rc0;
+  Arena real;
+  real.base = gm.ws;
+  layout(real);
+  int *h_flag = gm.h_flag;
   int rc = 0;
-  for (auto v : vecs) rc |= tmp_alloc(pool, v, cd);
-  float **stk[] = {&W.st_fq, &W.st_fp, &W.st_cq, &W.st_cg};
-  for (auto v : stk) rc |= tmp_alloc(pool, v, cd * MD);
-  float **fs[] = {&W.lp, &W.clp, &W.h0, &W.log_slice, &W.flp, &W.sclp, &W.feps, &W.heps};
-  for (auto v : fs) rc |= tmp_alloc(pool, v, C);
-  int **is[] = {&W.n, &W.s, &W.v, &W.leaf, &W.building, &W.sub_n, &W.sub_na, &W.sub_s, &W.alpha_cnt, &W.depth};
-  for (auto v : is) rc |= tmp_alloc(pool, v, C);
-  rc |= tmp_alloc(pool, &W.alpha_sum, C) | tmp_alloc(pool, &W.sub_alpha, C);
-  rc |= tmp_alloc(pool, &W.st_clp, (size_t)C * MD) | tmp_alloc(pool, &W.st_n, (size_t)C * MD) |
-        tmp_alloc(pool, &W.st_na, (size_t)C * MD) | tmp_alloc(pool, &W.st_alpha, (size_t)C * MD);
-  rc |= tmp_alloc(pool, &W.any_active, 1);
-  if (rc) { tmp_free(pool); return 2; }
-  int *h_flag = nullptr;
-  if (cudaMallocHost(&h_flag, sizeof(int)) != cudaSuccess) { tmp_free(pool); set_error("cudaMallocHost failed"); return 2; }
 
   const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
   const int T = 32 * WPB;
@@ -562,8 +589,6 @@ int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     ++g_launches;
   }
   cudaError_t e = cudaStreamSynchronize(st);
-  cudaFreeHost(h_flag);
-  tmp_free(pool);
   if (rc) return rc;
   B2M_CHECK_CUDA(e);
   B2M_CHECK_CUDA(cudaGetLastError());

@@ -21,6 +21,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "glm.cuh"
 
 namespace b2m {
@@ -311,6 +313,12 @@ int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, in
   return 0;
 }
 
+// ---------------------------------------------------------------- per-launch timing (bench.py's roofline)
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> ev[2];   // [0] = K5 (residual epilogue), [1] = K6 (split-K gradient): start, stop, start, ...
+} g_prof;
+
 template <int BLOCK_N, bool RESID>
 int launch_tc(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &Bh, const CUtensorMap &Bl, dim3 grid,
               int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st, int chunk_kb = DEFAULT_CHUNK_KB,
@@ -322,7 +330,18 @@ int launch_tc(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &B
     B2M_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof.on) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+  }
   kernel<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(Ah, Al, Bh, Bl, kb_total, kb_per_split, chunk_kb, mma_mask, E);
+  if (g_prof.on) {
+    cudaEventRecord(e1, st);
+    g_prof.ev[RESID ? 0 : 1].push_back(e0);
+    g_prof.ev[RESID ? 0 : 1].push_back(e1);
+  }
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -331,6 +350,30 @@ int launch_tc(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &B
 }  // namespace
 
 bool tc_available() { return encode_fn() != nullptr; }
+
+void tc_profile(bool enable) {
+  for (auto &v : g_prof.ev) {
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
+    v.clear();
+  }
+  g_prof.on = enable;
+}
+
+// out4 = {K5 total ms, K5 launches, K6 total ms, K6 launches} since tc_profile(true); synchronises the device
+int tc_profile_read(double *out4) {
+  B2M_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < 2; ++k) {
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < g_prof.ev[k].size(); i += 2) {
+      float t = 0.f;
+      B2M_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof.ev[k][i], g_prof.ev[k][i + 1]));
+      ms += t;
+    }
+    out4[2 * k] = ms;
+    out4[2 * k + 1] = (double)(g_prof.ev[k].size() / 2);
+  }
+  return 0;
+}
 
 // k-blocks (of 32) accumulated inside the tensor core between two fp32 promotions; tunable for experiments
 static int chunk_kb(const char *env, int dflt) {

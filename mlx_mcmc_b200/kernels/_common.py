@@ -22,9 +22,15 @@ def prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, mo
     overrides the common starting point -- used to hand the warm-up's final positions to the sampling call."""
     model = model if isinstance(model, DeviceModel) else compile_model(log_prob_fn, initial_params)
     if theta0 is not None:
+        theta0 = torch.as_tensor(theta0)          # a host array is copied to the device here (pinned staging)
         if tuple(theta0.shape) != (num_chains, model.D):
             raise ValueError(f"theta0 has shape {tuple(theta0.shape)}, expected {(num_chains, model.D)}")
-        theta = theta0.to(device=model.device, dtype=torch.float32).clone()
+        if not theta0.is_cuda:
+            staged = torch.empty(theta0.shape, dtype=torch.float32, pin_memory=True)
+            staged.copy_(theta0)
+            theta = staged.to(model.device, non_blocking=True)
+        else:
+            theta = theta0.to(device=model.device, dtype=torch.float32).clone()
     else:
         theta = model.pack(initial_params, num_chains)
     return model, ChainState(model, theta, step_size, chain_offset)

@@ -29,6 +29,7 @@ def nuts(
     return_torch: bool = False,
     return_info: bool = False,
     model=None,
+    theta0=None,
 ) -> Tuple[Dict[str, object], float]:
     """Same arguments and return value as the reference's ``nuts``: ``(samples, rate)`` where rate is the
     fraction of sampling iterations whose mean acceptance statistic exceeded 0.5 (nuts.py:341,353) and
@@ -46,7 +47,7 @@ def nuts(
         raise ValueError(f"max_tree_depth must be in 1..{_cabi.MAX_TREE_DEPTH}")
     cmode = _cabi.COMPAT_REFERENCE if compat == "reference" else _cabi.COMPAT_CORRECT
     seed = philox_seed(key, 0)
-    model, st = prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, model)
+    model, st = prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, model, theta0)
     st.da_state[:, 0] = 0.0                                           # H_bar
     st.da_state[:, 1] = 1.0                                           # eps_bar
     st.da_state[:, 2] = float(np.log(np.float32(10.0 * step_size)))   # mu, a float32 in the reference
