@@ -287,7 +287,7 @@ def glm_setup(torch, B, wl, C, chain_offset, seed):
     log(f"{wl['desc'][:40]}: model on device, mode found; adapting step sizes ({wl['adapt_iters']} iterations)")
     # adaptation runs with a shallower tree cap: the reference's dual averaging starts at 10 x eps0 and
     # overshoots down before settling, and a depth-10 tree of lock-step leaves is ~9 s at C4
-    launch_nuts(st, wl["adapt_iters"], min(6, wl["max_tree_depth"]), _cabi.ADAPT_DUAL_AVERAGING, _cabi.COMPAT_CORRECT, 0.65, seed, 0)
+    launch_nuts(st, wl["adapt_iters"], min(6, wl["max_tree_depth"]), _cabi.ADAPT_POOLED, _cabi.COMPAT_CORRECT, 0.65, seed, 0)
     st.step_size.copy_(st.da_state[:, 1])
     torch.cuda.synchronize()
     log(f"adapted: median step size {float(st.step_size.median()):.3e}")
@@ -327,9 +327,14 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
     clocks.start()
     leaves0 = int(st.n_leaves.sum().item())
     n0 = lib.b2m_launch_count()
+    import ctypes
+    four = (ctypes.c_double * 4)()
+    lib.b2m_profile(1)          # CUDA events around every GEMM launch of the timed region, on the launching stream
     barrier()
     timed.run(one_step)
     barrier()
+    lib.b2m_profile_read(four)
+    lib.b2m_profile(0)
     launches = lib.b2m_launch_count() - n0
     leaves = int(st.n_leaves.sum().item()) - leaves0
     total_ms = timed.total_ms()
@@ -376,19 +381,13 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
     if rank != 0:
         return out
 
-    # ---- roofline of the dominant kernels: every GEMM launch of a few lock-step evaluations timed with CUDA events
+    # ---- roofline of the dominant kernels: every GEMM launch of the timed region was timed with CUDA events
     peaks = load_peaks()
     tf32_probe = tf32_peak_probe(torch)
-    lib.b2m_profile(1)
-    reps = 6
-    for _ in range(reps):
-        model.logp_grad(st.theta)
-    import ctypes
-    four = (ctypes.c_double * 4)()
-    lib.b2m_profile_read(four)
-    lib.b2m_profile(0)
     k5_ms, k5_n, k6_ms, k6_n = [float(x) for x in four]
-    useful_per_gemm = 2.0 * N * D * C                        # flops of one contraction for all chains
+    # flops of one contraction for a full batch of C chains (compacted batches are smaller: the timed launches
+    # are all full-size here only if every chain reaches the same depth -- use the measured leaves instead)
+    useful_per_gemm = 2.0 * N * D * (leaves / max(k5_n, 1))
     k5 = k5_ms / max(k5_n, 1)
     k6 = k6_ms / max(k6_n, 1)
     both = k5 + k6
@@ -396,18 +395,20 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
     bf16_half = 0.5 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 0.0)) or 0.0)
     peak = max(tf32_probe, bf16_half) if bf16_half else tf32_probe
     alg_bytes = 4.0 * (N * D + N + 2 * C * D)
+    useful_full = 2.0 * N * D * C
     traffic = NCU_TRAFFIC.get(wl_name)
     out["roofline"] = {
         "bound": "tensor", "achieved": executed_tflops, "peak": peak, "unit": "TFLOP/s", "frac": executed_tflops / peak,
         "traffic": traffic["bytes"] if traffic else None,
         "kernel": "tc_gemm_kernel<256,RESID> (K5: M = (beta-beta0) X^T + residual epilogue) + tc_gemm_kernel<*,PLAIN> (K6: G = R X)",
         "avg_launch_ms": {"K5": k5, "K6": k6}, "launches_timed": int(k5_n + k6_n),
+        "gemm_share_of_step": (k5_ms + k6_ms) / total_ms,
         "executed_tf32_tflops": {"K5": 3 * useful_per_gemm / (k5 * 1e-3) / 1e12, "K6": 3 * useful_per_gemm / (k6 * 1e-3) / 1e12},
         "useful_tflops": 2 * useful_per_gemm / (both * 1e-3) / 1e12,
         "peak_source": f"max(cuBLAS tf32 8192^3 probe in this run = {tf32_probe:.1f}, 0.5 x bf16_tflops_sustained of "
                        f"MEASURED_PEAKS.json = {bf16_half:.1f})",
         "algorithmic_bytes_per_eval": alg_bytes,
-        "logical_GBps_per_chain_view": 4.0 * N * D * C / (both * 1e-3) / 1e9,
+        "logical_GBps_per_chain_view": 2 * useful_per_gemm / (both * 1e-3) / 1e9,
         "hbm_peak_GBps": float(peaks.get("hbm_gbs", 6650.0)),
         "traffic_source": traffic["source"] if traffic else None,
         "note": "achieved = executed tf32 flops (3 MMAs per useful product: 3xTF32 is what north_star prescribes to hold "
@@ -564,7 +565,8 @@ def main():
               "l2": "flushed between timed steps (256 MiB write)"}
     if wl["kind"] == "glm":
         config.update({"n_obs": wl["n"], "n_params": wl["d"], "sampler": "NUTS (iterative lock-step tree, compat=correct, "
-                       f"max_tree_depth={wl['max_tree_depth']}, per-chain dual-averaged step size, identity mass matrix)",
+                       f"max_tree_depth={wl['max_tree_depth']}, step size from pooled dual averaging over the rank's chains, "
+                       "identity mass matrix; finished chains are compacted out of the lock-step batch)",
                        "arithmetic": "3xTF32 tcgen05 GEMMs, fp32 accumulate, centred contraction"})
 
     if args.impl == "reference":

@@ -85,7 +85,14 @@ typedef struct b2m_model b2m_model;
 
 /* ---- sampler arguments ---- */
 
-enum { B2M_ADAPT_NONE = 0, B2M_ADAPT_REFERENCE = 1, B2M_ADAPT_DUAL_AVERAGING = 2 };
+enum {
+  B2M_ADAPT_NONE = 0,
+  B2M_ADAPT_REFERENCE = 1,      /* HMC: the +-5 % rule of hmc.py:164-170, per chain */
+  B2M_ADAPT_DUAL_AVERAGING = 2, /* per chain: every chain is an independent replica of the reference's recurrences */
+  B2M_ADAPT_POOLED = 3          /* NUTS, GLM class: ONE dual-averaging state driven by the mean acceptance statistic
+                                   over the chains of the call; all chains share the step size (keeps a lock-step
+                                   batch at one tree depth).  An extension: the reference has a single chain. */
+};
 enum { B2M_COMPAT_REFERENCE = 0, B2M_COMPAT_CORRECT = 1 };
 
 /* Replaces hmc()'s warm-up and sampling loops, kernels/hmc.py:155-198, with hmc_step :113-153,
@@ -139,7 +146,7 @@ typedef struct {
   int64_t iter_offset;
   int32_t n_iter;
   int32_t max_tree_depth; /* <= B2M_MAX_TREE_DEPTH */
-  int32_t adapt;          /* B2M_ADAPT_NONE or B2M_ADAPT_DUAL_AVERAGING (the reference's recurrences) */
+  int32_t adapt;          /* B2M_ADAPT_NONE, B2M_ADAPT_DUAL_AVERAGING (the reference's recurrences) or B2M_ADAPT_POOLED */
   int32_t compat;         /* B2M_COMPAT_REFERENCE: float32 slice underflow + NaN => alpha 1 (nuts.py:236-237,173)
                              B2M_COMPAT_CORRECT:   log-space slice, NaN => divergent, alpha 0 */
   int32_t lanes;

@@ -57,7 +57,7 @@ class NutsArgs(C.Structure):
                 ("trace_doubling", c_p), ("trace_energy", c_p)]
 
 
-ADAPT_NONE, ADAPT_REFERENCE, ADAPT_DUAL_AVERAGING = 0, 1, 2
+ADAPT_NONE, ADAPT_REFERENCE, ADAPT_DUAL_AVERAGING, ADAPT_POOLED = 0, 1, 2, 3
 COMPAT_REFERENCE, COMPAT_CORRECT = 0, 1
 MAX_TREE_DEPTH = 12
 ABI_VERSION = 1

@@ -313,6 +313,10 @@ int b2m_nuts_run(b2m_model *m, const b2m_nuts_args *a, void *stream) {
   B2M_REQUIRE(a->theta && a->step_size && a->da_state && a->n_accept && a->n_leaves && a->n_diverge,
               "b2m_nuts_run: NULL state pointer");
   B2M_REQUIRE(valid_lanes(a->lanes), "b2m_nuts_run: lanes must be 0 or a power of two <= 32");
+  B2M_REQUIRE(a->adapt == B2M_ADAPT_NONE || a->adapt == B2M_ADAPT_DUAL_AVERAGING || a->adapt == B2M_ADAPT_POOLED,
+              "b2m_nuts_run: bad adapt mode");
+  B2M_REQUIRE(a->adapt != B2M_ADAPT_POOLED || m->model_class == 1,
+              "b2m_nuts_run: pooled step-size adaptation needs a GLM-class model (lock-step kernels)");
   if (a->n_iter == 0) return 0;
   if (m->model_class == 1) return b2m::glm_nuts_run(m->glm, *a, static_cast<cudaStream_t>(stream));
   return b2m::launch_nuts(m->km, *a, static_cast<cudaStream_t>(stream));

@@ -33,8 +33,15 @@ int glm_reserve(GlmModel &g, int64_t n_chains) {
   const int64_t cp = (n_chains + 127) / 128 * 128;
   if (cp <= g.cap) return 0;
   free_workspace(g);
-  g.g_splits_cap = g.use_tc ? grad_splits(g, cp) : 1;
-  if (dev_alloc(&g.B, cp * g.Dp) || dev_alloc(&g.G, (size_t)g.g_splits_cap * cp * g.Dp) || dev_alloc(&g.R, cp * (size_t)g.Np) ||
+  // split-K partials: a compacted batch of fewer rows may use more splits -- size G for the worst case
+  size_t g_rows = (size_t)cp;
+  if (g.use_tc)
+    for (int64_t c = 128; c <= cp; c += 128) {
+      const size_t need = (size_t)grad_splits(g, c) * (size_t)c;
+      if (need > g_rows) g_rows = need;
+    }
+  g.g_splits_cap = (int)((g_rows + cp - 1) / cp);
+  if (dev_alloc(&g.B, cp * g.Dp) || dev_alloc(&g.G, g_rows * g.Dp) || dev_alloc(&g.R, cp * (size_t)g.Np) ||
       dev_alloc(&g.ss_part, (size_t)(g.Np / 64) * cp) || dev_alloc(&g.inv_var, cp) ||
       dev_alloc(&g.red, (size_t)cp * g.Dp + cp))
     return 2;
@@ -161,14 +168,17 @@ int glm_recenter(GlmModel &g, const float *theta, int64_t C, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- pack: theta -> B = beta - beta0 (+ tf32 split), 1/sigma^2
-__global__ void glm_pack_kernel(const float *__restrict__ theta, const float *__restrict__ beta0, int64_t C, int64_t Cp,
+// `idx` (optional) lists the chains of a compacted batch: row c of the batch is chain idx[c] of `theta`.
+__global__ void glm_pack_kernel(const float *__restrict__ theta, const float *__restrict__ beta0,
+                                const int *__restrict__ idx, int64_t C, int64_t Cp,
                                 int Dtot, int beta_off, int D, int Dp, int sigma_param, float sigma_const, float *B,
                                 float *Bh, float *Bl, float *inv_var) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cp * Dp) return;
-  const int64_t c = i / Dp;
+  const int64_t row = i / Dp;
   const int d = int(i % Dp);
-  const float v = (c < C && d < D) ? __fsub_rn(theta[c * Dtot + beta_off + d], beta0[d]) : 0.f;
+  const int64_t c = (row < C && idx) ? idx[row] : row;
+  const float v = (row < C && d < D) ? __fsub_rn(theta[c * Dtot + beta_off + d], beta0[d]) : 0.f;
   B[i] = v;
   if (Bh) {
     float hi, lo;
@@ -176,8 +186,8 @@ __global__ void glm_pack_kernel(const float *__restrict__ theta, const float *__
     Bh[i] = hi; Bl[i] = lo;
   }
   if (d == 0) {
-    const float s = (c < C && sigma_param >= 0) ? theta[c * Dtot + sigma_param] : sigma_const;
-    inv_var[c] = 1.0f / (s * s);
+    const float s = (row < C && sigma_param >= 0) ? theta[c * Dtot + sigma_param] : sigma_const;
+    inv_var[row] = 1.0f / (s * s);
   }
 }
 
@@ -310,7 +320,7 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
                                                           int sigma_param, float sigma_const, float weight, int N,
                                                           int n_tiles, const float *__restrict__ ss_part,
                                                           const float *__restrict__ G, int g_splits, float *__restrict__ logp,
-                                                          float *__restrict__ grad) {
+                                                          float *__restrict__ grad, const int *__restrict__ idx) {
   extern __shared__ __align__(16) unsigned char smem[];
   SModel sm;
   sm.n_terms = 0;
@@ -318,14 +328,15 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t c = (int64_t)blockIdx.x * (blockDim.x / 32) + warp;
   if (c >= C) return;
-  const float *th = theta + c * Dtot;
+  const int64_t src = idx ? idx[c] : c;       // chain served by row c of a compacted batch
+  const float *th = theta + src * Dtot;
   float ss = 0.f;
   for (int t = lane; t < n_tiles; t += 32) ss += ss_part[(int64_t)t * Cp + c];
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float sg = sigma_param >= 0 ? th[sigma_param] : sigma_const;
   const float iv = 1.0f / (sg * sg);
   float lp = weight * ((float)N * (-kHalfLog2Pi - logf(sg)) - 0.5f * ss * iv);
-  float *gr = grad ? grad + c * Dtot : nullptr;
+  float *gr = grad ? grad + src * Dtot : nullptr;
   if (gr) {
     for (int d = lane; d < Dtot; d += 32) {
       float v = 0.f;
@@ -365,16 +376,18 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
     }
     __syncwarp();
   }
-  if (lane == 0) logp[c] = lp + pl;
+  if (lane == 0) logp[src] = lp + pl;
 }
 
-int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st, bool recenter) {
+int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st, bool recenter,
+                  const int *idx, int64_t n_rows) {
   if (int rc = glm_reserve(g, C)) return rc;
   if (recenter)
     if (int rc = glm_recenter(g, theta, C, st)) return rc;
+  if (idx) C = n_rows;   // compacted batch: rows 0..n_rows-1 are the chains idx[0..n_rows-1]
   const int64_t Cp = (C + 127) / 128 * 128;
   const int64_t tot = Cp * g.Dp;
-  glm_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, g.beta0, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
+  glm_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, g.beta0, idx, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
                                                                   g.sigma_param, g.sigma_const, g.B, g.Bh, g.Bl, g.inv_var);
   ++g_launches;
   int n_tiles;
@@ -400,7 +413,7 @@ int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float
   }
   glm_finish_kernel<<<(unsigned)((C + 3) / 4), 128, smem, st>>>(g.prior, g.has_prior ? 1 : 0, theta, C, Cp, g.Dtot, g.beta_off,
                                                                  g.D, g.Dp, g.sigma_param, g.sigma_const, g.weight,
-                                                                 (int)g.N_total, n_tiles, ssp, Gp, splits, logp, grad);
+                                                                 (int)g.N_total, n_tiles, ssp, Gp, splits, logp, grad, idx);
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;

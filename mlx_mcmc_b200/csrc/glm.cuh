@@ -66,8 +66,9 @@ void glm_free(GlmModel &g);
 
 // log p and gradient for `theta` [C, Dtot] (device).  grad may be NULL.  recenter: move the reference point of
 // the contraction to the mean of `theta` first (the samplers do it once per iteration, from the current states).
+// idx / n_rows: evaluate only the chains idx[0..n_rows) (a compacted lock-step batch); outputs land at the chains' rows.
 int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st,
-                  bool recenter = false);
+                  bool recenter = false, const int *idx = nullptr, int64_t n_rows = 0);
 int glm_recenter(GlmModel &g, const float *theta, int64_t C, cudaStream_t st);
 
 // the two contractions (SIMT implementation)

@@ -289,7 +289,9 @@ struct NutsBufs {
   float *st_clp;
   int *st_n, *st_na;
   double *st_alpha;
-  int *any_active;  // device flag
+  int *n_active;    // device: number of chains building in the current doubling
+  int *active;      // [C] ordered list of those chains (the compacted lock-step batch)
+  float *alpha_it;  // [C] this iteration's mean acceptance statistic (pooled adaptation)
 };
 
 __device__ __forceinline__ void vcopy(float *dst, const float *src, int D, int lane) {
@@ -494,7 +496,6 @@ __global__ void __launch_bounds__(32 * WPB) nuts_doubling_end_kernel(b2m_nuts_ar
     W.alpha_sum[c] += W.sub_alpha[c];
     W.alpha_cnt[c] += W.sub_na[c];
     W.depth[c] = j + 1;
-    if (s_new && j + 1 < A.max_tree_depth) atomicOr(W.any_active, 1);
     if (A.trace_doubling) {
       int32_t *tr = A.trace_doubling + ((size_t)row * A.max_tree_depth + j) * 6;
       tr[0] = v; tr[1] = sub_n; tr[2] = sub_s; tr[3] = took; tr[4] = s_new; tr[5] = n + sub_n;
@@ -514,6 +515,7 @@ __global__ void __launch_bounds__(32 * WPB) nuts_end_kernel(b2m_nuts_args A, Nut
     W.lp[c] = W.clp[c];
     const double mean_alpha = W.alpha_sum[c] / fmax((double)W.alpha_cnt[c], 1.0);
     A.n_accept[c] += mean_alpha > 0.5 ? 1 : 0;
+    if (A.adapt == B2M_ADAPT_POOLED) W.alpha_it[c] = (float)mean_alpha;
     if (A.adapt == B2M_ADAPT_DUAL_AVERAGING) {
       double h_bar = A.da_state[c * 3 + 0], eps_bar = A.da_state[c * 3 + 1];
       const float mu = (float)A.da_state[c * 3 + 2];
@@ -530,6 +532,74 @@ __global__ void __launch_bounds__(32 * WPB) nuts_end_kernel(b2m_nuts_args A, Nut
     }
     if (A.depths) A.depths[row] = W.depth[c];
     if (A.alphas) A.alphas[row] = (float)mean_alpha;
+  }
+}
+
+// Ordered compaction of the chains still building in this doubling: active[0..n) = their ids, ascending.
+// One block; the list drives the compacted lock-step evaluations (glm_logp_grad with idx).
+__global__ void __launch_bounds__(1024) nuts_compact_kernel(const int *__restrict__ building, int64_t C,
+                                                            int *__restrict__ active, int *__restrict__ n_active) {
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int64_t c0 = 0; c0 < C; c0 += 1024) {
+    const int64_t c = c0 + threadIdx.x;
+    const int f = (c < C && building[c]) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    const int pre = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int t = warp_tot[w];
+      if (w < warp) off += t;
+      tot += t;
+    }
+    if (f) active[base + off + pre] = (int)c;
+    __syncthreads();
+    if (threadIdx.x == 0) base += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_active = base;
+}
+
+// Pooled dual averaging (B2M_ADAPT_POOLED): the recurrences of nuts.py:298-310 driven by the mean acceptance
+// statistic over all chains of the call; every chain receives the same step size.  Deterministic reduction.
+__global__ void __launch_bounds__(1024) nuts_pool_adapt_kernel(b2m_nuts_args A, const float *__restrict__ alpha_it, int it) {
+  __shared__ double red[1024];
+  __shared__ double eps_sh, hbar_sh, ebar_sh;
+  const int64_t C = A.n_chains;
+  double s = 0.0;
+  for (int64_t c = threadIdx.x; c < C; c += 1024) {
+    const float a = alpha_it[c];
+    s += (a == a) ? (double)a : 0.0;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean_alpha = red[0] / (double)C;
+    double h_bar = A.da_state[0], eps_bar = A.da_state[1];
+    const float mu = (float)A.da_state[2];
+    const double m = (double)(uint32_t)(A.iter_offset + it), eta = 1.0 / (m + 10.0);
+    h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - mean_alpha);
+    float log_eps = __fsub_rn(mu, (float)((sqrt(m + 1.0) / 0.05) * h_bar));
+    log_eps = fmaxf(fminf(log_eps, 10.0f), -10.0f);
+    const double eps = (double)expf(log_eps);
+    const double wgt = pow(m + 1.0, -0.75);
+    eps_bar = (double)expf((float)(wgt * log(eps) + (1.0 - wgt) * log(eps_bar)));
+    eps_sh = eps; hbar_sh = h_bar; ebar_sh = eps_bar;
+  }
+  __syncthreads();
+  for (int64_t c = threadIdx.x; c < C; c += 1024) {
+    A.step_size[c] = eps_sh;
+    A.da_state[c * 3 + 0] = hbar_sh;
+    A.da_state[c * 3 + 1] = ebar_sh;
   }
 }
 
@@ -551,7 +621,9 @@ int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     A.take(&W.alpha_sum, C); A.take(&W.sub_alpha, C);
     A.take(&W.st_clp, (size_t)C * MD); A.take(&W.st_n, (size_t)C * MD); A.take(&W.st_na, (size_t)C * MD);
     A.take(&W.st_alpha, (size_t)C * MD);
-    A.take(&W.any_active, 1);
+    A.take(&W.n_active, 1);
+    A.take(&W.active, C);
+    A.take(&W.alpha_it, C);
   };
   Arena probe;
   layout(probe);
@@ -570,23 +642,31 @@ int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     nuts_begin_kernel<<<grid, T, 0, st>>>(a, W, D, it);
     ++g_launches;
     for (int j = 0; j < MD && !rc; ++j) {
-      cudaMemsetAsync(W.any_active, 0, sizeof(int), st);
       nuts_doubling_begin_kernel<<<grid, T, 0, st>>>(a, W, D, it, j);
-      ++g_launches;
+      nuts_compact_kernel<<<1, 1024, 0, st>>>(W.building, C, W.active, W.n_active);
+      g_launches += 2;
+      cudaMemcpyAsync(h_flag, W.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) { rc = 2; set_error("NUTS lock-step: stream error"); break; }
+      const int n_act = *h_flag;
+      if (n_act == 0) break;   // every chain's trajectory has ended
+      // chains that stopped growing are compacted out of the batch: the two contractions of each leaf run over
+      // the n_act building chains only (rounded up to the 128-row tile)
+      const bool compact = n_act < C;
       for (int leaf = 0; leaf < (1 << j) && !rc; ++leaf) {
         nuts_leaf_pre_kernel<<<grid, T, 0, st>>>(a, W, D);
-        rc = glm_logp_grad(gm, W.fq, C, W.flp, W.fg, st);
+        rc = glm_logp_grad(gm, W.fq, C, W.flp, W.fg, st, false, compact ? W.active : nullptr, n_act);
         nuts_leaf_post_kernel<<<grid, T, 0, st>>>(a, W, D, it, j);
         g_launches += 2;
       }
       nuts_doubling_end_kernel<<<grid, T, 0, st>>>(a, W, D, it, j);
       ++g_launches;
-      cudaMemcpyAsync(h_flag, W.any_active, sizeof(int), cudaMemcpyDeviceToHost, st);
-      if (cudaStreamSynchronize(st) != cudaSuccess) { rc = 2; set_error("NUTS lock-step: stream error"); break; }
-      if (!*h_flag) break;
     }
     nuts_end_kernel<<<grid, T, 0, st>>>(a, W, D, it);
     ++g_launches;
+    if (a.adapt == B2M_ADAPT_POOLED) {
+      nuts_pool_adapt_kernel<<<1, 1024, 0, st>>>(a, W.alpha_it, it);
+      ++g_launches;
+    }
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc) return rc;

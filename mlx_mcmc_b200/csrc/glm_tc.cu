@@ -245,21 +245,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     const int nb = n0 + half * CW;
     if (RESID) {
+      // Residual epilogue.  The thread owns row m (a chain) and CW consecutive columns (observations); written
+      // straight from registers each store instruction would touch 32 different rows (16 B per row: uncoalesced,
+      // partial-sector writes -- the first version spent more time here than in the MMAs).  Each warp therefore
+      // transposes 32x32 blocks through a private shared-memory scratch (33-float pitch: conflict-free both ways;
+      // it aliases pipeline stage 0, which is idle once the last chunk has been committed) and stores whole
+      // 128-byte row segments.
       float ss = 0.f;
       const float ivw = E.inv_var[m] * E.weight;
-      float *rh = E.Rh + (int64_t)m * E.Np + nb, *rl = E.Rl + (int64_t)m * E.Np + nb;
+      float *scratch = reinterpret_cast<float *>(smem) + (warp - 2) * (32 * 33);
+      const int64_t row0 = (int64_t)(m0 + q * 32);
 #pragma unroll
-      for (int j = 0; j < CW; j += 4) {
-        float hi[4], lo[4];
+      for (int b = 0; b < CW / 32; ++b) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int n = nb + j + t;
-          const float z = (n < E.N_valid) ? (__ldg(E.y + n) - E.loc_const) - acc[j + t] : 0.f;
+        for (int j = 0; j < 32; ++j) {
+          const int n = nb + b * 32 + j;
+          const float z = (n < E.N_valid) ? (__ldg(E.y + n) - E.loc_const) - acc[b * 32 + j] : 0.f;
           ss = fmaf(z, z, ss);
-          split_tf32(z * ivw, hi[t], lo[t]);
+          scratch[lane * 33 + j] = z * ivw;
         }
-        *reinterpret_cast<float4 *>(rh + j) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4 *>(rl + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        __syncwarp();
+        float *rh = E.Rh + row0 * E.Np + nb + b * 32 + lane, *rl = E.Rl + row0 * E.Np + nb + b * 32 + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          float hi, lo;
+          split_tf32(scratch[r * 33 + lane], hi, lo);
+          rh[(int64_t)r * E.Np] = hi;
+          rl[(int64_t)r * E.Np] = lo;
+        }
+        __syncwarp();
       }
       E.ss_part[((int64_t)blockIdx.y * 2 + half) * E.Cp + m] = ss;
     } else {

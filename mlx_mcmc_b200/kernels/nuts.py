@@ -24,6 +24,7 @@ def nuts(
     *,
     num_chains: int = 1,
     compat: str = "reference",
+    step_size_adaptation: str = "per_chain",
     chain_offset: int = 0,
     lanes: int = 0,
     return_torch: bool = False,
@@ -38,11 +39,18 @@ def nuts(
     ``compat='reference'`` reproduces the reference's float32 slice round trip and NaN handling
     (SURVEY.md F6/F7); ``compat='correct'`` keeps the slice in log space (see csrc/nuts_pointwise.cu).
     Dual averaging follows nuts.py:62-68,298-310 per chain on device; after warm-up every chain
-    switches to its averaged step size (nuts.py:317-320)."""
+    switches to its averaged step size (nuts.py:317-320).
+
+    ``step_size_adaptation='pooled'`` (an extension for ``num_chains > 1``; the reference has one chain):
+    all chains share one step size, so a lock-step batch stays at one tree depth.  GLM-class models run ONE
+    dual-averaging recurrence on the mean acceptance statistic over the chains, on device, every iteration;
+    pointwise models adapt per chain and every chain then takes the median of the averaged step sizes."""
     if num_warmup == 0:
         raise ZeroDivisionError("division by zero")   # nuts.py:322-323
     if compat not in ("reference", "correct"):
         raise ValueError(f"Unknown compat mode: {compat}")
+    if step_size_adaptation not in ("per_chain", "pooled"):
+        raise ValueError(f"Unknown step_size_adaptation: {step_size_adaptation}")
     if not 1 <= max_tree_depth <= _cabi.MAX_TREE_DEPTH:
         raise ValueError(f"max_tree_depth must be in 1..{_cabi.MAX_TREE_DEPTH}")
     cmode = _cabi.COMPAT_REFERENCE if compat == "reference" else _cabi.COMPAT_CORRECT
@@ -52,10 +60,15 @@ def nuts(
     st.da_state[:, 1] = 1.0                                           # eps_bar
     st.da_state[:, 2] = float(np.log(np.float32(10.0 * step_size)))   # mu, a float32 in the reference
     amode = _cabi.ADAPT_DUAL_AVERAGING if adapt_step_size else _cabi.ADAPT_NONE
+    pooled = adapt_step_size and step_size_adaptation == "pooled"
+    if pooled and model.model_class == 1:
+        amode = _cabi.ADAPT_POOLED
     warm_depths = torch.empty((num_warmup, num_chains), dtype=torch.int32, device=model.device) if return_info else None
     launch_nuts(st, num_warmup, max_tree_depth, amode, cmode, target_accept, seed, 0, depths=warm_depths, lanes=lanes)
     if adapt_step_size:
         st.step_size.copy_(st.da_state[:, 1])
+        if pooled and model.model_class != 1:
+            st.step_size.fill_(float(st.da_state[:, 1].median().item()))
     warm_leaves = st.n_leaves.clone()
     st.n_accept.zero_()
     draws = alloc_draws(model, num_samples, num_chains)

@@ -220,6 +220,32 @@ def test_regression_nuts_matches_closed_form_posterior(cuda):
     assert info.grad_evals > 0
 
 
+def test_regression_nuts_pooled_step_size_and_compaction(cuda):
+    """Pooled dual averaging: every chain ends warm-up with the same step size, the posterior still matches the
+    closed form; and a chain's draws do not depend on which other chains share its (compacted) lock-step batch."""
+    fn, init, meta = W.regression(B.ns, 800, 12, seed=7)
+    m, V = W.regression_posterior(meta)
+    s, rate, info = B.nuts(fn, init, num_samples=200, num_warmup=200, step_size=0.02, num_chains=384, compat="correct",
+                           step_size_adaptation="pooled", return_info=True, key=mx.random.key(8))
+    assert np.all(info.step_size == info.step_size[0]) and 1e-3 < info.step_size[0] < 1.0
+    sd = np.sqrt(np.diag(V))
+    for d in range(12):
+        assert mcse_ok(s["beta"][:, :, d], m[d], sd[d]), d
+    depths = info.depths
+    assert depths.min() < depths.max()          # chains do stop at different depths, so batches were compacted
+    # fixed step size, no adaptation: chains 0..127 alone vs inside a 384-chain batch.  A GLM-class chain's
+    # arithmetic depends on its batch only through the centring point and the split-K order (float32 rounding),
+    # so the first draws agree to rounding (later ones drift apart: the trajectories are chaotic)
+    kw = dict(num_samples=2, num_warmup=1, step_size=float(info.step_size[0]), adapt_step_size=False, compat="correct",
+              key=mx.random.key(9))
+    a, _ = B.nuts(fn, init, num_chains=128, **kw)
+    b, _ = B.nuts(fn, init, num_chains=384, **kw)
+    close = np.all(np.abs(a["beta"][:, 0] - b["beta"][:128, 0]) < 1e-4 * (1 + np.abs(a["beta"][:, 0])), axis=1)
+    assert close.mean() > 0.95, close.mean()
+    with pytest.raises(ValueError):
+        B.nuts(fn, init, num_chains=4, step_size_adaptation="global")
+
+
 def test_regression_hmc_and_metropolis_run(cuda):
     fn, init, meta = W.regression(B.ns, 300, 4, seed=6)
     m, V = W.regression_posterior(meta)
