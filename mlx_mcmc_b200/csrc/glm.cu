@@ -30,7 +30,7 @@ void glm_free(GlmModel &g) {
 }
 
 int glm_reserve(GlmModel &g, int64_t n_chains) {
-  const int64_t cp = (n_chains + 127) / 128 * 128;
+  const int64_t cp = (n_chains + 255) / 256 * 256;   // whole CTA-pair tiles (glm_tc.cu)
   if (cp <= g.cap) return 0;
   free_workspace(g);
   // split-K partials: a compacted batch of fewer rows may use more splits -- size G for the worst case
@@ -385,7 +385,7 @@ int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float
   if (recenter)
     if (int rc = glm_recenter(g, theta, C, st)) return rc;
   if (idx) C = n_rows;   // compacted batch: rows 0..n_rows-1 are the chains idx[0..n_rows-1]
-  const int64_t Cp = (C + 127) / 128 * 128;
+  const int64_t Cp = C <= 128 ? 128 : (C + 255) / 256 * 256;   // one 128-row tile, or whole 256-row CTA-pair tiles
   const int64_t tot = Cp * g.Dp;
   glm_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, g.beta0, idx, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
                                                                   g.sigma_param, g.sigma_const, g.B, g.Bh, g.Bl, g.inv_var);

@@ -5,7 +5,14 @@
 // Every operand is K-major fp32 holding tf32-representable values (round-to-nearest hi/lo split, glm.cuh), so
 // the dropped Al.Bl term is ~2^-22 relative: the two contractions hold the 1e-5 log-prob / gradient tolerance.
 //
-// Kernel anatomy (one 128 x BLOCK_N output tile per CTA, 192 threads):
+// Two launch shapes share the kernel body (template NCTA):
+//   NCTA = 1   one CTA = one 128 x BLOCK_N tile                                   (small / compacted batches)
+//   NCTA = 2   a CTA pair (cluster of 2, tcgen05 cta_group::2) = one 256 x BLOCK_N tile: each CTA stages its own
+//              128 rows of A and HALF of the B tile, the leader CTA issues the MMAs for both, each CTA's TMEM
+//              receives its own 128 rows.  Per k-block a CTA pulls 64 KB instead of 96 KB through L2 -- the v1
+//              kernel was pinned at the ~6300 B/clk L2->SM return path (profiles/r01_tc_gemm_c4_v1_ncu_summary.md).
+//
+// Kernel anatomy (one 128 x BLOCK_N output tile per CTA, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the four operand tiles of a k-block
 //               (BLOCK_K = 32 floats = one 128-byte swizzle row) into a ring of shared-memory stages
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs x 4 k-steps per stage),
@@ -63,6 +70,51 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- cluster / CTA-pair helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by one CTA of a pair; completion bytes are signalled on the LEADER's mbarrier (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint32_t leader_bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives on the mbarrier at the same offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -105,8 +157,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m = BLOCK_M) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct EpiParams {
@@ -122,22 +174,23 @@ struct EpiParams {
   int Dp;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int NCTA>
 struct Cfg {
-  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;
+  static constexpr int B_ROWS = BLOCK_N / NCTA;         // rows of the B tile staged by one CTA
+  static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 6 ? 6 : (192 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;        // two chunk accumulators (power of two >= 32)
   static constexpr int COLS_PER_WARP = BLOCK_N / 2;    // each promotion warp owns 32 rows x half of the columns
 };
 
-template <int BLOCK_N, bool RESID>
+template <int BLOCK_N, bool RESID, int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int k_blocks_total,
                int k_blocks_per_split, int CHUNK_KB, int mma_mask, EpiParams E) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, NCTA>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES);
@@ -147,6 +200,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = NCTA == 2 ? cluster_ctarank() : 0u;   // rank inside the CTA pair; 0 = leader (issues the MMAs)
   const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N;
   const int kb0 = blockIdx.z * k_blocks_per_split;
   const int kb1 = min(kb0 + k_blocks_per_split, k_blocks_total);
@@ -158,16 +212,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * NUM_EPI_WARPS); }
+    // pair: the leader's `full` collects one arrival per producer (2) and the bytes of both CTAs' loads; the leader's
+    // `tmem_empty` collects the promotion threads of both CTAs; `empty` / `tmem_full` are signalled in both CTAs by
+    // the multicast tcgen05.commit
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], NCTA); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], NCTA * NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();   // barriers initialised and TMEM allocated in both CTAs
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -179,18 +241,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         unsigned char *st = smem + stage * C::STAGE_BYTES;
-        mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-        tma_load_2d(st, &tmAh, &full[stage], kb * BLOCK_K, m0);
-        tma_load_2d(st + A_TILE_BYTES, &tmAl, &full[stage], kb * BLOCK_K, m0);
-        tma_load_2d(st + 2 * A_TILE_BYTES, &tmBh, &full[stage], kb * BLOCK_K, n0);
-        tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tmBl, &full[stage], kb * BLOCK_K, n0);
+        if (NCTA == 2) {
+          const uint32_t lbar = mapa(smem_u32(&full[stage]), 0);   // the leader's barrier
+          if (cta == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+          else mbar_arrive_cluster(lbar);
+          const int nb = n0 + (int)cta * C::B_ROWS;               // this CTA's half of the B tile
+          tma_load_2d_pair(st, &tmAh, lbar, kb * BLOCK_K, m0);
+          tma_load_2d_pair(st + A_TILE_BYTES, &tmAl, lbar, kb * BLOCK_K, m0);
+          tma_load_2d_pair(st + 2 * A_TILE_BYTES, &tmBh, lbar, kb * BLOCK_K, nb);
+          tma_load_2d_pair(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tmBl, lbar, kb * BLOCK_K, nb);
+        } else {
+          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          tma_load_2d(st, &tmAh, &full[stage], kb * BLOCK_K, m0);
+          tma_load_2d(st + A_TILE_BYTES, &tmAl, &full[stage], kb * BLOCK_K, m0);
+          tma_load_2d(st + 2 * A_TILE_BYTES, &tmBh, &full[stage], kb * BLOCK_K, n0);
+          tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tmBl, &full[stage], kb * BLOCK_K, n0);
+        }
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+    if (lane == 0 && cta == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N, BLOCK_M * NCTA);
       int stage = 0;
       uint32_t phase = 0;
       int kb = 0;
@@ -209,14 +282,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // start-address advance inside the swizzle row
-            umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, (kc | k) != 0 ? 1u : 0u);
-            if (mma_mask & 2) umma_tf32(tmem_d, dAh + adv, dBl + adv, idesc, 1u);
-            if (mma_mask & 4) umma_tf32(tmem_d, dAl + adv, dBh + adv, idesc, 1u);
+            if (NCTA == 2) {
+              umma_tf32_pair(tmem_d, dAh + adv, dBh + adv, idesc, (kc | k) != 0 ? 1u : 0u);
+              if (mma_mask & 2) umma_tf32_pair(tmem_d, dAh + adv, dBl + adv, idesc, 1u);
+              if (mma_mask & 4) umma_tf32_pair(tmem_d, dAl + adv, dBh + adv, idesc, 1u);
+            } else {
+              umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, (kc | k) != 0 ? 1u : 0u);
+              if (mma_mask & 2) umma_tf32(tmem_d, dAh + adv, dBl + adv, idesc, 1u);
+              if (mma_mask & 4) umma_tf32(tmem_d, dAl + adv, dBh + adv, idesc, 1u);
+            }
           }
-          umma_commit(&empty[stage]);  // frees the stage once the MMAs above have read it
+          // frees the stage (in both CTAs of a pair) once the MMAs above have read it
+          if (NCTA == 2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[buf]);  // chunk accumulator complete
+        // chunk accumulator complete (in both CTAs' TMEM)
+        if (NCTA == 2) umma_commit_pair(&tmem_full[buf]); else umma_commit(&tmem_full[buf]);
       }
     }
   } else {
@@ -241,7 +322,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         for (int j = 0; j < 32; ++j) acc[cb * 32 + j] += __uint_as_float(v[j]);   // round-to-nearest promotion
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&tmem_empty[buf]);
+      __syncwarp();
+      if (lane == 0) {   // one arrival per warp: a cluster-scope release per thread was 13 % of the v2 stall samples
+        if (NCTA == 2) mbar_arrive_cluster(mapa(smem_u32(&tmem_empty[buf]), 0));   // the leader's MMA warp waits on it
+        else mbar_arrive(&tmem_empty[buf]);
+      }
     }
     const int nb = n0 + half * CW;
     if (RESID) {
@@ -255,12 +340,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const float ivw = E.inv_var[m] * E.weight;
       float *scratch = reinterpret_cast<float *>(smem) + (warp - 2) * (32 * 33);
       const int64_t row0 = (int64_t)(m0 + q * 32);
+      // the observations of this warp's columns: one coalesced load per 32-column block (lane = column), handed to
+      // the row-owning threads by shuffle (a per-element __ldg serialised 128 L2 round trips per thread)
+      float yv[CW / 32];
+#pragma unroll
+      for (int b = 0; b < CW / 32; ++b) {
+        const int n = nb + b * 32 + lane;
+        yv[b] = (n < E.N_valid) ? __ldg(E.y + n) - E.loc_const : 0.f;
+      }
 #pragma unroll
       for (int b = 0; b < CW / 32; ++b) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = nb + b * 32 + j;
-          const float z = (n < E.N_valid) ? (__ldg(E.y + n) - E.loc_const) - acc[b * 32 + j] : 0.f;
+          const float yj = __shfl_sync(0xffffffffu, yv[b], j);
+          const float z = (n < E.N_valid) ? yj - acc[b * 32 + j] : 0.f;
           ss = fmaf(z, z, ss);
           scratch[lane * 33 + j] = z * ivw;
         }
@@ -284,9 +378,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();   // no CTA of a pair may leave while its peer still signals it
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS));
+    if (NCTA == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS));
   }
 }
 
@@ -333,12 +430,11 @@ struct Prof {
   std::vector<cudaEvent_t> ev[2];   // [0] = K5 (residual epilogue), [1] = K6 (split-K gradient): start, stop, start, ...
 } g_prof;
 
-template <int BLOCK_N, bool RESID>
-int launch_tc(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &Bh, const CUtensorMap &Bl, dim3 grid,
-              int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st, int chunk_kb = DEFAULT_CHUNK_KB,
-              int mma_mask = 7) {
-  using C = Cfg<BLOCK_N>;
-  auto kernel = tc_gemm_kernel<BLOCK_N, RESID>;
+template <int BLOCK_N, bool RESID, int NCTA>
+int launch_tc_n(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &Bh, const CUtensorMap &Bl, dim3 grid,
+                int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st, int chunk_kb, int mma_mask) {
+  using C = Cfg<BLOCK_N, NCTA>;
+  auto kernel = tc_gemm_kernel<BLOCK_N, RESID, NCTA>;
   static bool configured = false;
   if (!configured) {
     B2M_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -350,7 +446,19 @@ int launch_tc(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &B
     cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
   }
-  kernel<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(Ah, Al, Bh, Bl, kb_total, kb_per_split, chunk_kb, mma_mask, E);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = NCTA == 2 ? 1 : 0;
+  B2M_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, Ah, Al, Bh, Bl, kb_total, kb_per_split, chunk_kb, mma_mask, E));
   if (g_prof.on) {
     cudaEventRecord(e1, st);
     g_prof.ev[RESID ? 0 : 1].push_back(e0);
@@ -359,6 +467,14 @@ int launch_tc(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &B
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int BLOCK_N, bool RESID>
+int launch_tc(int ncta, const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &Bh, const CUtensorMap &Bl,
+              dim3 grid, int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st,
+              int chunk_kb = DEFAULT_CHUNK_KB, int mma_mask = 7) {
+  if (ncta == 2) return launch_tc_n<BLOCK_N, RESID, 2>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
+  return launch_tc_n<BLOCK_N, RESID, 1>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
 }
 
 }  // namespace
@@ -398,46 +514,63 @@ static int chunk_kb(const char *env, int dflt) {
 
 int grad_block_n(const GlmModel &g) { return g.Dp % 256 == 0 ? 256 : (g.Dp % 128 == 0 ? 128 : 64); }
 
+// CTA pairs need whole 256-row tiles of chains; B2M_TC_PAIR=0 forces the single-CTA kernel (experiments)
+static int pair_mode(int64_t Cp) {
+  const char *v = getenv("B2M_TC_PAIR");
+  if (v && atoi(v) == 0) return 1;
+  return (Cp % 256 == 0) ? 2 : 1;
+}
+
+// split-K factor of K6: enough CTAs to fill the 148 SMs in whole waves, each split at least 8 k-blocks deep
 int grad_splits(const GlmModel &g, int64_t Cp) {
-  const int64_t tiles = (Cp / BLOCK_M) * (g.Dp / grad_block_n(g));
+  const int64_t tiles = (Cp / BLOCK_M) * (g.Dp / grad_block_n(g));   // CTAs per split
   const int kb = g.Np / BLOCK_K;
-  int64_t s = 148 / (tiles > 0 ? tiles : 1);
-  if (s < 1) s = 1;
-  if (s > kb / 8) s = kb / 8 > 0 ? kb / 8 : 1;
-  if (s > 32) s = 32;
-  return (int)s;
+  int max_s = kb / 8 > 0 ? kb / 8 : 1;
+  if (max_s > 32) max_s = 32;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= max_s; ++s) {
+    const int64_t ctas = tiles * s;
+    const int64_t waves = (ctas + 147) / 148;
+    // efficiency of the last wave, minus a small charge per split for writing / re-reading the partials
+    const double eff = (double)ctas / (double)(waves * 148) - 0.004 * (s - 1);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  return best;
 }
 
 int tc_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st) {
+  const int ncta = pair_mode(Cp);
   CUtensorMap Ah, Al, Bh, Bl;
   if (make_map(&Ah, g.Bh, Cp, g.Dp, BLOCK_M) || make_map(&Al, g.Bl, Cp, g.Dp, BLOCK_M) ||
-      make_map(&Bh, g.Xh, g.Np, g.Dp, 256) || make_map(&Bl, g.Xl, g.Np, g.Dp, 256))
+      make_map(&Bh, g.Xh, g.Np, g.Dp, 256 / ncta) || make_map(&Bl, g.Xl, g.Np, g.Dp, 256 / ncta))
     return 2;
   EpiParams E{};
   E.y = g.y0; E.inv_var = g.inv_var; E.Rh = g.Rh; E.Rl = g.Rl; E.ss_part = g.ss_part; E.Cp = Cp; E.Np = g.Np;
   E.N_valid = g.N; E.loc_const = 0.f; E.weight = g.weight;   // y0 is already centred and shifted (glm.cu)
   dim3 grid((unsigned)(Cp / BLOCK_M), g.Np / 256, 1);
-  return launch_tc<256, true>(Ah, Al, Bh, Bl, grid, g.Dp / BLOCK_K, g.Dp / BLOCK_K, E, st,
+  return launch_tc<256, true>(ncta, Ah, Al, Bh, Bl, grid, g.Dp / BLOCK_K, g.Dp / BLOCK_K, E, st,
                               chunk_kb("B2M_TC_CHUNK_RESID", DEFAULT_CHUNK_KB));
 }
 
 int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
+  const int ncta = pair_mode(Cp);
   const int bn = grad_block_n(g);
   const int splits = grad_splits(g, Cp);
   const int kb_total = g.Np / BLOCK_K;
   const int kb_per = (kb_total + splits - 1) / splits;
   CUtensorMap Ah, Al, Bh, Bl;
   if (make_map(&Ah, g.Rh, Cp, g.Np, BLOCK_M) || make_map(&Al, g.Rl, Cp, g.Np, BLOCK_M) ||
-      make_map(&Bh, g.XTh, g.Dp, g.Np, bn) || make_map(&Bl, g.XTl, g.Dp, g.Np, bn))
+      make_map(&Bh, g.XTh, g.Dp, g.Np, bn / ncta) || make_map(&Bl, g.XTl, g.Dp, g.Np, bn / ncta))
     return 2;
   EpiParams E{};
   E.Gpart = g.G; E.Cp = Cp; E.Dp = g.Dp;
   dim3 grid((unsigned)(Cp / BLOCK_M), g.Dp / bn, (unsigned)((kb_total + kb_per - 1) / kb_per));
   g.g_splits = (int)grid.z;
   const int ck = chunk_kb("B2M_TC_CHUNK_GRAD", DEFAULT_CHUNK_KB);
-  if (bn == 256) return launch_tc<256, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
-  if (bn == 128) return launch_tc<128, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
-  return launch_tc<64, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
+  if (bn == 256) return launch_tc<256, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
+  if (bn == 128) return launch_tc<128, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
+  return launch_tc<64, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
 }
 
 
@@ -458,16 +591,17 @@ int debug_tc_gemm(const float *A, const float *Bm, int M, int N, int K, float *C
   split_kernel<<<(unsigned)(((size_t)M * K + 255) / 256), 256, 0, st>>>(A, (int64_t)M * K, Ah, Al);
   split_kernel<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(Bm, (int64_t)N * K, Bh, Bl);
   const int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+  const int ncta = pair_mode(M);
   CUtensorMap mAh, mAl, mBh, mBl;
-  int rc = make_map(&mAh, Ah, M, K, BLOCK_M) || make_map(&mAl, Al, M, K, BLOCK_M) || make_map(&mBh, Bh, N, K, bn) ||
-           make_map(&mBl, Bl, N, K, bn);
+  int rc = make_map(&mAh, Ah, M, K, BLOCK_M) || make_map(&mAl, Al, M, K, BLOCK_M) || make_map(&mBh, Bh, N, K, bn / ncta) ||
+           make_map(&mBl, Bl, N, K, bn / ncta);
   if (!rc) {
     EpiParams E{};
     E.Gpart = Cout; E.Cp = M; E.Dp = N;
     dim3 grid(M / BLOCK_M, N / bn, 1);
-    if (bn == 256) rc = launch_tc<256, false>(mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
-    else if (bn == 128) rc = launch_tc<128, false>(mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
-    else rc = launch_tc<64, false>(mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
+    if (bn == 256) rc = launch_tc<256, false>(ncta, mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
+    else if (bn == 128) rc = launch_tc<128, false>(ncta, mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
+    else rc = launch_tc<64, false>(ncta, mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
   }
   cudaStreamSynchronize(st);
   cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl);

@@ -16,8 +16,8 @@ def run(A, B, chunk, mask):
     return c.cpu().numpy()
 
 rng = np.random.default_rng(0)
-M, N = 128, 256
-for K in (1024, 8192):
+M, N = 256, 256
+for K in (1024,):
     for kind in ("random", "positive"):
         A = rng.standard_normal((M, K)).astype(np.float32)
         B = rng.standard_normal((N, K)).astype(np.float32)
@@ -28,7 +28,7 @@ for K in (1024, 8192):
         scale = np.max(np.abs(ref))
         row = [f"K={K} {kind:8s} scale={scale:9.1f} fp32-cpu err={np.max(np.abs(f32-ref))/scale:.2e}"]
         for mask in (1, 7):
-            for chunk in (1, 2, 4, 16, 100000):
+            for chunk in (1, 4):
                 out = run(A, B, chunk, mask)
                 err = out - ref
                 row.append(f"m{mask}c{chunk}: max {np.max(np.abs(err))/scale:.2e} bias {np.mean(err*np.sign(ref))/scale:+.2e}")
