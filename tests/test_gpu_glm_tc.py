@@ -65,3 +65,72 @@ def test_tc_value_only_and_repeatability(cuda):
     c, gc = tc.logp_grad(theta)
     assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(ga, gc)      # deterministic, bit for bit
     assert torch.equal(a, a[0].expand_as(a))                                     # identical rows -> identical results
+
+
+# ------------------------------------------------------------------------------------------------ full size (C4)
+@pytest.fixture(scope="module")
+def c4(cuda):
+    """BASELINE.json's Target configuration: 1000 coefficients x 100,000 observations."""
+    fn, init, meta = W.regression(B.ns, 100000, 1000, seed=0)
+    model = compile_model(fn, init, cache=False)
+    X64 = torch.from_numpy(meta.X).cuda().double()
+    y64 = torch.from_numpy(meta.y).cuda().double()
+    return model, meta, X64, y64
+
+
+def _float64_gpu(X64, y64, theta):
+    """float64 arbiter on the device (torch used as a calculator for the test, not by the product)"""
+    b = theta.double()
+    n, d = X64.shape
+    r = y64[None, :] - b @ X64.T
+    lp = (-0.5 * (r ** 2).sum(1) - n * 0.5 * math.log(2 * math.pi)
+          - 0.5 * (b ** 2).sum(1) / 100.0 - d * (0.5 * math.log(2 * math.pi) + math.log(10.0)))
+    return lp, r @ X64 - b / 100.0
+
+
+@pytest.mark.parametrize("where,spread", [("mode", 0.003), ("mode", 0.2), ("zero", 0.0), ("far", 3.0)])
+def test_c4_full_size_logp_grad_within_1e5_of_float64(c4, where, spread):
+    """parity check 1 at full size: |lp - lp64| / |lp64| and max|g - g64| / max|g64| below 1e-5, per chain too"""
+    model, meta, X64, y64 = c4
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    base = torch.from_numpy(meta.beta_true).cuda()[None, :] if where != "zero" else torch.zeros(1, 1000, device="cuda")
+    theta = (base + spread * torch.randn(256, 1000, device="cuda", generator=gen)).contiguous()
+    lp, g = model.logp_grad(theta)
+    lp64, g64 = _float64_gpu(X64, y64, theta)
+    e_lp = float(((lp.double() - lp64).abs() / lp64.abs()).max())
+    e_g = float((g.double() - g64).abs().max() / g64.abs().max())
+    e_chain = float(((g.double() - g64).abs().amax(1) / g64.abs().amax(1)).max())
+    print(f"C4 {where} spread={spread}: logp {e_lp:.2e} grad {e_g:.2e} per-chain {e_chain:.2e}")
+    assert e_lp < 1e-5 and e_g < 1e-5 and e_chain < 1e-5
+
+
+def test_c4_full_size_properties(c4):
+    """size-independent properties at full size: the gradient is affine in beta with slope -(X'X + I/100); the
+    value-only path, a repeat and a sub-batch give the same numbers."""
+    model, meta, X64, y64 = c4
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    b0 = torch.from_numpy(meta.beta_true).cuda()[None, :] + 0.003 * torch.randn(128, 1000, device="cuda", generator=gen)
+    delta = 0.002 * torch.randn(128, 1000, device="cuda", generator=gen)
+    both = torch.cat([b0, b0 + delta]).contiguous()            # one batch => one centring point for both halves
+    lp, g = model.logp_grad(both)
+    dg = (g[128:] - g[:128]).double()
+    want = -((delta.double() @ X64.T) @ X64) - delta.double() / 100.0
+    assert float((dg - want).abs().max() / want.abs().max()) < 2e-5
+    lp2, _ = model.logp_grad(both, want_grad=False)
+    lp3, g3 = model.logp_grad(both)
+    assert torch.equal(lp, lp2) and torch.equal(lp, lp3) and torch.equal(g, g3)
+    # energy-like check of the value: lp(b + d) - lp(b) = g(b).d - 0.5 d'(X'X + I/100)d  (exact for a quadratic)
+    quad = (g[:128].double() * delta.double()).sum(1) + 0.5 * (want * delta.double()).sum(1)
+    assert float(((lp[128:] - lp[:128]).double() - quad).abs().max()) < 2e-5 * float(lp.abs().max())
+
+
+@pytest.mark.parametrize("n,d,c", [(257, 65, 1), (255, 63, 129), (513, 1, 300), (4097, 129, 257)])
+def test_tc_ragged_shapes(cuda, n, d, c):
+    """padding edges: N, D, C just off the 256 / 64 / 128 tile sizes, a single chain, a single coefficient"""
+    tc, meta = _model("tc", n, d, seed=n * 7 + d)
+    rng = np.random.default_rng(2)
+    theta = (meta.beta_true[None, :] + 0.1 * rng.standard_normal((c, d))).astype(np.float32)
+    lp, g = tc.logp_grad(torch.from_numpy(theta).cuda())
+    lp64, g64 = _float64(meta, theta)
+    assert np.max(np.abs(lp.cpu().numpy() - lp64) / np.abs(lp64)) < 1e-5
+    assert np.max(np.abs(g.cpu().numpy() - g64)) / np.max(np.abs(g64)) < 1e-5
