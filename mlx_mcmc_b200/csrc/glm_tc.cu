@@ -189,11 +189,13 @@ template <int BLOCK_N, bool RESID, int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int k_blocks_total,
-               int k_blocks_per_split, int CHUNK_KB, int mma_mask, EpiParams E) {
+               int k_blocks_per_split, int CHUNK_KB, int mma_mask, int Tm, int Tn, int n_tiles, EpiParams E) {
   using C = Cfg<BLOCK_N, NCTA>;
+  constexpr int SCRATCH_BYTES = RESID ? NUM_EPI_WARPS * 32 * 33 * 4 : 0;   // per-warp transpose scratch of the K5 epilogue
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES);
+  float *scratch_base = reinterpret_cast<float *>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::STAGES * C::STAGE_BYTES + SCRATCH_BYTES);
   uint64_t *empty = full + C::STAGES;
   uint64_t *tmem_full = empty + C::STAGES;   // [2]
   uint64_t *tmem_empty = tmem_full + 2;      // [2]
@@ -201,11 +203,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta = NCTA == 2 ? cluster_ctarank() : 0u;   // rank inside the CTA pair; 0 = leader (issues the MMAs)
-  const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N;
-  const int kb0 = blockIdx.z * k_blocks_per_split;
-  const int kb1 = min(kb0 + k_blocks_per_split, k_blocks_total);
-  const int nkb = kb1 - kb0;
-  const int n_chunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+  // Persistent tile loop: CTA group g (a CTA, or a pair) takes tiles g, g + G, g + 2G, ...  Tile t = (pair-row
+  // t % Tm, column tile (t / Tm) % Tn, K split t / (Tm Tn)): neighbours in time share the B tile.  Barriers and TMEM
+  // are set up once; the producer and the MMA issuer run ahead into the next tile while the promotion warps are
+  // still in the epilogue of the previous one (both TMEM chunk buffers are free by then).
+  const int group = blockIdx.x / NCTA, n_groups = gridDim.x / NCTA;
+#define B2M_DECODE_TILE(t)                                                         \
+  const int mp_ = (t) % Tm, r_ = (t) / Tm, nt = r_ % Tn, zs = r_ / Tn;             \
+  const int m0 = (mp_ * NCTA + (int)cta) * BLOCK_M, n0 = nt * BLOCK_N;             \
+  const int kb0 = zs * k_blocks_per_split;                                         \
+  const int kb1 = min(kb0 + k_blocks_per_split, k_blocks_total);                   \
+  const int nkb = kb1 - kb0;                                                       \
+  const int n_chunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;                            \
+  (void)m0; (void)n0; (void)nt; (void)zs; (void)nkb; (void)n_chunks;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
@@ -238,6 +248,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      for (int t = group; t < n_tiles; t += n_groups) {
+      B2M_DECODE_TILE(t)
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         unsigned char *st = smem + stage * C::STAGE_BYTES;
@@ -259,6 +271,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
@@ -266,10 +279,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       constexpr uint32_t idesc = make_idesc(BLOCK_N, BLOCK_M * NCTA);
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t gch = 0;   // chunk counter across tiles: buffer = gch & 1, barrier parity = (gch >> 1) & 1
+      for (int t = group; t < n_tiles; t += n_groups) {
+      B2M_DECODE_TILE(t)
       int kb = 0;
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        const int buf = ch & 1;
-        mbar_wait(&tmem_empty[buf], ((ch >> 1) & 1) ^ 1);   // the promotion warps have drained this buffer
+      for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
+        const int buf = gch & 1;
+        mbar_wait(&tmem_empty[buf], ((gch >> 1) & 1) ^ 1);   // the promotion warps have drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
         const int kb_end = min(kb + CHUNK_KB, nkb);
@@ -299,18 +315,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         // chunk accumulator complete (in both CTAs' TMEM)
         if (NCTA == 2) umma_commit_pair(&tmem_full[buf]); else umma_commit(&tmem_full[buf]);
       }
+      }
     }
   } else {
     // ===== promotion + epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const int m = m0 + q * 32 + lane;
     constexpr int CW = C::COLS_PER_WARP;
+    uint32_t gch = 0;
+    for (int t = group; t < n_tiles; t += n_groups) {
+    B2M_DECODE_TILE(t)
+    const int m = m0 + q * 32 + lane;
     float acc[CW];
 #pragma unroll
     for (int j = 0; j < CW; ++j) acc[j] = 0.f;
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const int buf = ch & 1;
-      mbar_wait(&tmem_full[buf], (ch >> 1) & 1);
+    for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
+      const int buf = gch & 1;
+      mbar_wait(&tmem_full[buf], (gch >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BLOCK_N + half * CW;
 #pragma unroll
@@ -333,12 +353,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       // Residual epilogue.  The thread owns row m (a chain) and CW consecutive columns (observations); written
       // straight from registers each store instruction would touch 32 different rows (16 B per row: uncoalesced,
       // partial-sector writes -- the first version spent more time here than in the MMAs).  Each warp therefore
-      // transposes 32x32 blocks through a private shared-memory scratch (33-float pitch: conflict-free both ways;
-      // it aliases pipeline stage 0, which is idle once the last chunk has been committed) and stores whole
-      // 128-byte row segments.
+      // transposes 32x32 blocks through a private shared-memory scratch (33-float pitch: conflict-free both ways)
+      // and stores whole 128-byte row segments.
       float ss = 0.f;
       const float ivw = E.inv_var[m] * E.weight;
-      float *scratch = reinterpret_cast<float *>(smem) + (warp - 2) * (32 * 33);
+      float *scratch = scratch_base + (warp - 2) * (32 * 33);
       const int64_t row0 = (int64_t)(m0 + q * 32);
       // the observations of this warp's columns: one coalesced load per 32-column block (lane = column), handed to
       // the row-owning threads by shuffle (a per-element __ldg serialised 128 L2 round trips per thread)
@@ -369,13 +388,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
         __syncwarp();
       }
-      E.ss_part[((int64_t)blockIdx.y * 2 + half) * E.Cp + m] = ss;
+      E.ss_part[((int64_t)nt * 2 + half) * E.Cp + m] = ss;
     } else {
-      float *g = E.Gpart + ((int64_t)blockIdx.z * E.Cp + m) * E.Dp + nb;
+      float *g = E.Gpart + ((int64_t)zs * E.Cp + m) * E.Dp + nb;
 #pragma unroll
       for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4 *>(g + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
     }
+    }
   }
+#undef B2M_DECODE_TILE
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (NCTA == 2) cluster_sync_all(); else __syncthreads();   // no CTA of a pair may leave while its peer still signals it
@@ -435,11 +456,15 @@ int launch_tc_n(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap 
                 int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st, int chunk_kb, int mma_mask) {
   using C = Cfg<BLOCK_N, NCTA>;
   auto kernel = tc_gemm_kernel<BLOCK_N, RESID, NCTA>;
+  constexpr int SMEM = C::SMEM_BYTES + (RESID ? NUM_EPI_WARPS * 32 * 33 * 4 : 0);
   static bool configured = false;
   if (!configured) {
-    B2M_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    B2M_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
+  // `grid` arrives as (128-row tiles, column tiles, K splits); the launch is one persistent CTA group per SM (pair)
+  const int Tm = (int)grid.x / NCTA, Tn = (int)grid.y, n_tiles = Tm * Tn * (int)grid.z;
+  const int n_groups = n_tiles < 148 / NCTA ? n_tiles : 148 / NCTA;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
     cudaEventCreate(&e0);
@@ -447,9 +472,9 @@ int launch_tc_n(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap 
     cudaEventRecord(e0, st);
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
+  cfg.gridDim = dim3((unsigned)(n_groups * NCTA), 1, 1);
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -458,7 +483,7 @@ int launch_tc_n(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = NCTA == 2 ? 1 : 0;
-  B2M_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, Ah, Al, Bh, Bl, kb_total, kb_per_split, chunk_kb, mma_mask, E));
+  B2M_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, Ah, Al, Bh, Bl, kb_total, kb_per_split, chunk_kb, mma_mask, Tm, Tn, n_tiles, E));
   if (g_prof.on) {
     cudaEventRecord(e1, st);
     g_prof.ev[RESID ? 0 : 1].push_back(e0);
