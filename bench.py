@@ -265,12 +265,13 @@ class Timed:
 
 
 # ----------------------------------------------------------------------------------------- GLM workloads (c4, c3)
-def glm_setup(torch, B, wl, C, chain_offset, seed):
-    """model + chains started in the posterior's typical set + dual-averaging warm-up (all untimed)."""
-    from mlx_mcmc_b200 import _cabi, workloads as W
+def glm_setup(torch, B, wl, C, chain_offset, seed, obs_sharded=False):
+    """model + chains started in the posterior's typical set + dual-averaging warm-up (all untimed).
+    obs_sharded: every rank holds all C chains (same ids, same seed) and a row shard of (X, y)."""
+    from mlx_mcmc_b200 import _cabi, dist as D_, workloads as W
     from mlx_mcmc_b200.engine import ChainState, compile_model, launch_nuts
     fn, init, meta = W.regression(B.ns, wl["n"], wl["d"], seed=0)
-    model = compile_model(fn, init)
+    model = D_.compile_obs_sharded(fn, init) if obs_sharded else compile_model(fn, init)
     N, D = wl["n"], wl["d"]
     # posterior mode by Richardson iteration on the device gradient (X'X ~ N I for this synthetic X)
     th = torch.zeros(128, D, device="cuda")
@@ -379,6 +380,33 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
            "config_extra": {"chains_per_gpu": C, "iters_per_step": 1, "mean_tree_depth": mean_depth,
                             "grad_evals_per_step_per_gpu": leaves / args.steps,
                             "adapted_step_size_median": eps_host}}
+    # ---- N > 1: the same 4096 chains in TOTAL with the observations sharded over the ranks (BASELINE configs[3] as
+    # written: strong scaling, one NCCL all-reduce of the [C, D+1] gradient || sum z^2 buffer per gradient)
+    if world > 1 and full:
+        fn_o, _, model_o, st_o, _ = glm_setup(torch, B, wl, C, 0, seed, obs_sharded=True)
+        it_o = [wl["adapt_iters"]]
+
+        def obs_step():
+            launch_nuts(st_o, 1, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, it_o[0], draws=draws, depths=depths)
+            it_o[0] += 1
+
+        timed_o = Timed(torch, args.steps)
+        for _ in range(warm):
+            obs_step()
+        barrier()
+        l0 = int(st_o.n_leaves.sum().item())
+        barrier()
+        timed_o.run(obs_step)
+        barrier()
+        l1 = int(st_o.n_leaves.sum().item())
+        to = torch.tensor([timed_o.total_ms()], dtype=torch.float64, device="cuda")
+        dist.all_reduce(to, op=dist.ReduceOp.MAX)
+        out["obs_sharded"] = {"value": (l1 - l0) / (float(to[0]) * 1e-3), "unit": UNIT, "scaling": "strong",
+                              "chains_total": C, "rows_per_gpu": -(-N // world), "ms_per_step": float(to[0]) / args.steps,
+                              "collective": f"ncclAllReduce(sum, f32) of [C, D+1] = {4 * C * (D + 1) / 1e6:.1f} MB per gradient, "
+                                            "on the compute stream between K6 and finish",
+                              "note": "every rank holds all chains and takes identical decisions; grad-evals counted once"}
+        log(f"obs-sharded: {out['obs_sharded']['ms_per_step']:.1f} ms/step")
     if rank != 0:
         return out
 
@@ -580,6 +608,7 @@ def main():
     import mlx_mcmc_b200 as B
     from mlx_mcmc_b200 import _cabi
 
+    os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
