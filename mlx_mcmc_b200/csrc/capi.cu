@@ -213,6 +213,15 @@ int b2m_model_create(const b2m_term *terms, int32_t n_terms, const b2m_lin_entry
   m->km.n_arrays = n_arrays;
   m->km.D = D;
   m->km.max_len = max_len;
+  // compact models: the table rides in the kernel parameters (model.cuh)
+  bool compact = n_terms <= b2m::kCompactTerms && D <= b2m::kCompactDim && n_matvec == 0;
+  for (int t = 0; t < n_terms && compact; ++t)
+    compact = terms[t].x.kind != B2M_OP_LIN && terms[t].p0.kind != B2M_OP_LIN && terms[t].p1.kind != B2M_OP_LIN;
+  const char *force = getenv("B2M_POINTWISE_PATH");
+  if (force && std::string(force) == "general") compact = false;
+  m->km.compact = compact ? 1 : 0;
+  memset(m->km.cterms, 0, sizeof(m->km.cterms));
+  if (compact) memcpy(m->km.cterms, terms, sizeof(b2m_term) * n_terms);
   // observation vectors are staged in shared memory when they fit beside the mailboxes
   m->km.stage_floats = (stage * 4 <= 96 * 1024) ? (int32_t)stage : 0;
   if (m->model_class == 1) {

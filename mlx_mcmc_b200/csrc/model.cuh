@@ -17,6 +17,9 @@ struct DevArray {
   int64_t cols;
 };
 
+constexpr int kCompactTerms = 8;   // terms a "compact" model may have (their table rides in the kernel parameters)
+constexpr int kCompactDim = 4;     // scalar parameters a compact model may have (theta / gradient stay in registers)
+
 // What the host passes by value to every kernel.
 struct KModel {
   const b2m_term *terms;
@@ -25,6 +28,12 @@ struct KModel {
   int32_t n_terms, n_lin, n_arrays, D;
   int32_t stage_floats;  // total floats of the 1-D arrays staged in shared memory (0 = no staging)
   int32_t max_len;       // longest term
+  // Compact models (<= kCompactTerms terms, D <= kCompactDim, no affine operands -- every model of the reference's
+  // examples and tests): the term table is part of the kernel parameters, i.e. lives in the constant bank, so the
+  // evaluation reads term fields as instruction operands instead of re-loading them from shared memory on every
+  // gradient evaluation, and theta / gradient never leave registers (no shared-memory mailbox).
+  int32_t compact;
+  b2m_term cterms[kCompactTerms];
 };
 
 // Per-CTA copy in shared memory.
@@ -338,6 +347,160 @@ __device__ inline float eval_model(const SModel &sm, const float *th, float *gr,
       float v = gr[d * TS];
       for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
       gr[d * TS] = v;
+    }
+  }
+  return total;
+}
+
+// ---------------------------------------------------------------- compact models: registers + constant bank
+template <int DMAX>
+__device__ __forceinline__ float reg_get(const float (&q)[DMAX], int i) {
+  float v = q[0];
+#pragma unroll
+  for (int d = 1; d < DMAX; ++d) v = (i == d) ? q[d] : v;
+  return v;
+}
+template <int DMAX>
+__device__ __forceinline__ void reg_add(float (&g)[DMAX], int i, float v) {
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d)
+    if (i == d) g[d] += v;
+}
+
+template <int DMAX>
+__device__ __forceinline__ float op_fetch_c(const b2m_operand &o, int n, const float (&q)[DMAX], const SModel &sm) {
+  switch (o.kind) {
+    case B2M_OP_PARAM: return reg_get<DMAX>(q, o.a);
+    case B2M_OP_DATA: return sm.arrays[o.a].ptr[n];
+    case B2M_OP_PARAMVEC: return reg_get<DMAX>(q, o.a + n);
+    default: return o.c;
+  }
+}
+template <int DMAX>
+__device__ __forceinline__ void op_scatter_c(const b2m_operand &o, int n, float adj, float (&g)[DMAX]) {
+  if (o.kind == B2M_OP_PARAM) reg_add<DMAX>(g, o.a, adj);
+  else if (o.kind == B2M_OP_PARAMVEC) reg_add<DMAX>(g, o.a + n, adj);
+}
+
+// Same arithmetic, in the same order, as eval_model (so the two paths agree bit for bit); `km` must be the
+// kernel's __grid_constant__ parameter so that km.cterms[t] resolves to constant-bank operands.
+template <bool GRAD, int DMAX>
+__device__ __forceinline__ float eval_model_c(const KModel &km, const SModel &sm, const float (&q)[DMAX], float (&g)[DMAX],
+                                              int lane, int G, unsigned gmask) {
+  float total = 0.f;
+  if (GRAD) {
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) g[d] = 0.f;
+  }
+#pragma unroll
+  for (int t = 0; t < kCompactTerms; ++t) {
+    if (t >= km.n_terms) break;
+    const b2m_term &T = km.cterms[t];
+    const int dist = T.dist, len = T.length;
+    const float k0 = T.k0, k1 = T.k1, k2 = T.k2, w = T.weight;
+    float acc = 0.f, ax = 0.f, a0 = 0.f, a1 = 0.f;
+    const bool params_fixed = !op_varies(T.p0) && !op_varies(T.p1);
+    if (params_fixed && T.x.kind == B2M_OP_DATA && dist == B2M_NORMAL) {
+      const float mu = op_fetch_c<DMAX>(T.p0, 0, q, sm), sg = op_fetch_c<DMAX>(T.p1, 0, q, sm);
+      const float inv_var = 1.0f / (sg * sg), base = -kHalfLog2Pi - logf(sg);
+      const float *y = sm.arrays[T.x.a].ptr;
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+      int n = lane;
+      if (G == 1 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        const float4 *y4 = reinterpret_cast<const float4 *>(y);
+        for (; n + 3 < len; n += 4) {
+          const float4 v = y4[n >> 2];
+          const float z0 = v.x - mu, z1 = v.y - mu, z2 = v.z - mu, z3 = v.w - mu;
+          s1[0] += z0; s1[1] += z1; s1[2] += z2; s1[3] += z3;
+          s2[0] = fmaf(z0, z0, s2[0]); s2[1] = fmaf(z1, z1, s2[1]);
+          s2[2] = fmaf(z2, z2, s2[2]); s2[3] = fmaf(z3, z3, s2[3]);
+        }
+      } else {
+        for (; n + 3 * G < len; n += 4 * G) {
+          const float z0 = y[n] - mu, z1 = y[n + G] - mu, z2 = y[n + 2 * G] - mu, z3 = y[n + 3 * G] - mu;
+          s1[0] += z0; s1[1] += z1; s1[2] += z2; s1[3] += z3;
+          s2[0] = fmaf(z0, z0, s2[0]); s2[1] = fmaf(z1, z1, s2[1]);
+          s2[2] = fmaf(z2, z2, s2[2]); s2[3] = fmaf(z3, z3, s2[3]);
+        }
+      }
+      for (; n < len; n += G) {
+        const float z = y[n] - mu;
+        s1[0] += z;
+        s2[0] = fmaf(z, z, s2[0]);
+      }
+      const float t1 = (s1[0] + s1[1]) + (s1[2] + s1[3]), t2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+      const float cnt = (float)((len - lane + G - 1) / G);
+      acc = cnt * base - 0.5f * t2 * inv_var;
+      a0 = t1 * inv_var;
+      a1 = (t2 * inv_var - cnt) / sg;
+    } else if (params_fixed && T.x.kind == B2M_OP_DATA && dist == B2M_EXPONENTIAL) {
+      const float rate = op_fetch_c<DMAX>(T.p0, 0, q, sm);
+      const float lr = logf(rate), ir = 1.0f / rate;
+      const float *y = sm.arrays[T.x.a].ptr;
+      float s1[4] = {0.f, 0.f, 0.f, 0.f};
+      float lo = INFINITY;
+      int n = lane;
+      if (G == 1 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        const float4 *y4 = reinterpret_cast<const float4 *>(y);
+        for (; n + 3 < len; n += 4) {
+          const float4 v = y4[n >> 2];
+          s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+          lo = fminf(fminf(lo, fminf(v.x, v.y)), fminf(v.z, v.w));
+        }
+      } else {
+        for (; n + 3 * G < len; n += 4 * G) {
+          const float v0 = y[n], v1 = y[n + G], v2 = y[n + 2 * G], v3 = y[n + 3 * G];
+          s1[0] += v0; s1[1] += v1; s1[2] += v2; s1[3] += v3;
+          lo = fminf(fminf(lo, fminf(v0, v1)), fminf(v2, v3));
+        }
+      }
+      for (; n < len; n += G) {
+        const float v = y[n];
+        s1[0] += v;
+        lo = fminf(lo, v);
+      }
+      const float t1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+      const float cnt = (float)((len - lane + G - 1) / G);
+      const bool bad = !(lo >= 0.f) || !(t1 == t1);
+      if (!bad) {
+        acc = cnt * lr - rate * t1;
+        a0 = cnt * ir - t1;
+      } else {
+        acc = -INFINITY;
+        a0 = 0.f;
+        for (int m = lane; m < len; m += G) {
+          const float v = y[m];
+          if (v >= 0.f) a0 += ir - v;
+        }
+      }
+    } else {
+      for (int n = lane; n < len; n += G) {
+        const float x = op_fetch_c<DMAX>(T.x, n, q, sm);
+        const float p0 = op_fetch_c<DMAX>(T.p0, n, q, sm);
+        const float p1 = op_fetch_c<DMAX>(T.p1, n, q, sm);
+        Elem e = dist_eval<GRAD>(dist, x, p0, p1, k0, k1, k2);
+        acc += e.lp;
+        if (GRAD) {
+          if (T.x.kind == B2M_OP_PARAM) ax += e.dx; else op_scatter_c<DMAX>(T.x, n, w * e.dx, g);
+          if (T.p0.kind == B2M_OP_PARAM) a0 += e.d0; else op_scatter_c<DMAX>(T.p0, n, w * e.d0, g);
+          if (T.p1.kind == B2M_OP_PARAM) a1 += e.d1; else op_scatter_c<DMAX>(T.p1, n, w * e.d1, g);
+        }
+      }
+    }
+    total += w * acc;
+    if (GRAD) {
+      if (T.x.kind == B2M_OP_PARAM) reg_add<DMAX>(g, T.x.a, w * ax);
+      if (T.p0.kind == B2M_OP_PARAM) reg_add<DMAX>(g, T.p0.a, w * a0);
+      if (T.p1.kind == B2M_OP_PARAM) reg_add<DMAX>(g, T.p1.a, w * a1);
+    }
+  }
+  for (int o = G >> 1; o > 0; o >>= 1) total += __shfl_xor_sync(gmask, total, o);
+  if (GRAD && G > 1) {
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) {
+      float v = g[d];
+      for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+      g[d] = v;
     }
   }
   return total;

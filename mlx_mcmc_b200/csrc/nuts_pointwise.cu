@@ -48,8 +48,8 @@ struct StackEntry {  // a finished LEFT subtree waiting for its sibling
   double alpha;
 };
 
-template <int DMAX>
-__global__ void __launch_bounds__(64) nuts_kernel(KModel km, b2m_nuts_args A) {
+template <int DMAX, bool COMPACT>
+__global__ void __launch_bounds__(64) nuts_kernel(const __grid_constant__ KModel km, b2m_nuts_args A) {
   extern __shared__ __align__(16) unsigned char smem[];
   SModel sm;
   unsigned char *mail = model_to_smem(km, smem, sm);
@@ -69,9 +69,7 @@ __global__ void __launch_bounds__(64) nuts_kernel(KModel km, b2m_nuts_args A) {
   const float mu = (float)A.da_state[c * 3 + 2];
   int64_t n_acc = A.n_accept[c], n_leaves = A.n_leaves[c], n_div = A.n_diverge[c];
 
-  to_mailbox<DMAX>(q, L.th, L.TS, D);
-  float lp = eval_model<true>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
-  from_mailbox<DMAX>(g, L.gr, L.TS, D);
+  float lp = evaluate<DMAX, COMPACT, true>(km, sm, L, q, g);
 
   StackEntry<DMAX> stack[B2M_MAX_TREE_DEPTH];
 
@@ -128,9 +126,7 @@ __global__ void __launch_bounds__(64) nuts_kernel(KModel km, b2m_nuts_args A) {
           fp[d] = __fadd_rn(fp[d], __fmul_rn(half_eps, fg[d]));
           fq[d] = __fadd_rn(fq[d], __fmul_rn(feps, fp[d]));
         }
-        to_mailbox<DMAX>(fq, L.th, L.TS, D);
-        const float flp = eval_model<true>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
-        from_mailbox<DMAX>(fg, L.gr, L.TS, D);
+        const float flp = evaluate<DMAX, COMPACT, true>(km, sm, L, fq, fg);
 #pragma unroll
         for (int d = 0; d < DMAX; ++d) fp[d] = __fadd_rn(fp[d], __fmul_rn(half_eps, fg[d]));
         ++n_leaves;
@@ -254,9 +250,9 @@ int launch_nuts(const KModel &km, b2m_nuts_args a, cudaStream_t st) {
   const int dmax = pick_dmax(km.D);
   a.lanes = pick_lanes(km, a.n_chains, a.lanes);
   Geometry ge = geometry(km, a.n_chains, a.lanes, dmax ? dmax : 2);
-  B2M_DISPATCH_DMAX(dmax, {
-    if (int rc = prep(nuts_kernel<DM>, ge.smem)) return rc;
-    nuts_kernel<DM><<<ge.grid, ge.block, ge.smem, st>>>(km, a);
+  B2M_DISPATCH_DMAX(dmax, km.compact, {
+    if (int rc = prep(nuts_kernel<DM, CP>, ge.smem)) return rc;
+    nuts_kernel<DM, CP><<<ge.grid, ge.block, ge.smem, st>>>(km, a);
   });
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());

@@ -11,9 +11,10 @@
 namespace b2m {
 
 // ---------------------------------------------------------------- K1: log p and gradient
-template <int DMAX>
-__global__ void __launch_bounds__(128) logp_grad_kernel(KModel km, const float *__restrict__ theta, int64_t C,
-                                                         float *__restrict__ logp, float *__restrict__ grad, int G) {
+template <int DMAX, bool COMPACT>
+__global__ void __launch_bounds__(128) logp_grad_kernel(const __grid_constant__ KModel km, const float *__restrict__ theta,
+                                                         int64_t C, float *__restrict__ logp, float *__restrict__ grad,
+                                                         int G) {
   extern __shared__ __align__(16) unsigned char smem[];
   SModel sm;
   unsigned char *mail = model_to_smem(km, smem, sm);
@@ -22,16 +23,15 @@ __global__ void __launch_bounds__(128) logp_grad_kernel(KModel km, const float *
   float q[DMAX];
 #pragma unroll
   for (int d = 0; d < DMAX; ++d) q[d] = (d < D) ? theta[L.chain * D + d] : 0.f;
-  to_mailbox<DMAX>(q, L.th, L.TS, D);
+  float gq[DMAX];
   float lp;
   if (grad)
-    lp = eval_model<true>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
+    lp = evaluate<DMAX, COMPACT, true>(km, sm, L, q, gq);
   else
-    lp = eval_model<false>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
+    lp = evaluate<DMAX, COMPACT, false>(km, sm, L, q, gq);
   if (L.writer) {
     logp[L.chain] = lp;
-    if (grad)
-      for (int d = 0; d < D; ++d) grad[L.chain * D + d] = L.gr[d * L.TS];
+    if (grad) store_vec<DMAX>(grad + L.chain * D, gq, D);
   }
 }
 
@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(128) logp_grad_kernel(KModel km, const float *
 // The gradient at the trajectory start is the cached gradient of the current state (the reference
 // recomputes it: same number).  Warm-up rule (:164-170): for i > 10, eps *= 0.95 if the cumulative
 // acceptance rate is below target else 1.05, per chain, in float64 like the python float it replaces.
-template <int DMAX>
-__global__ void __launch_bounds__(128) hmc_kernel(KModel km, b2m_hmc_args A) {
+template <int DMAX, bool COMPACT>
+__global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ KModel km, b2m_hmc_args A) {
   extern __shared__ __align__(16) unsigned char smem[];
   SModel sm;
   unsigned char *mail = model_to_smem(km, smem, sm);
@@ -64,9 +64,7 @@ __global__ void __launch_bounds__(128) hmc_kernel(KModel km, b2m_hmc_args A) {
     da_mu = A.da_state[c * 3 + 2];
   }
 
-  to_mailbox<DMAX>(q, L.th, L.TS, D);
-  float lp = eval_model<true>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
-  from_mailbox<DMAX>(g, L.gr, L.TS, D);
+  float lp = evaluate<DMAX, COMPACT, true>(km, sm, L, q, g);
 
   for (int it = 0; it < A.n_iter; ++it) {
     const uint32_t giter = (uint32_t)(A.iter_offset + it);
@@ -89,9 +87,7 @@ __global__ void __launch_bounds__(128) hmc_kernel(KModel km, b2m_hmc_args A) {
         p[d] = __fadd_rn(p[d], __fmul_rn(half_eps, gn[d]));
         qn[d] = __fadd_rn(qn[d], __fmul_rn(feps, p[d]));
       }
-      to_mailbox<DMAX>(qn, L.th, L.TS, D);
-      lpn = eval_model<true>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
-      from_mailbox<DMAX>(gn, L.gr, L.TS, D);
+      lpn = evaluate<DMAX, COMPACT, true>(km, sm, L, qn, gn);
 #pragma unroll
       for (int d = 0; d < DMAX; ++d) p[d] = __fadd_rn(p[d], __fmul_rn(half_eps, gn[d]));
     }
@@ -145,8 +141,8 @@ __global__ void __launch_bounds__(128) hmc_kernel(KModel km, b2m_hmc_args A) {
 // ---------------------------------------------------------------- K3: random-walk Metropolis
 // metropolis.py:64-92: theta' = theta + scale * N(0,I) (multiply, then add); accept iff
 // log U < lp' - lp with the current log-prob cached; NaN => reject.
-template <int DMAX>
-__global__ void __launch_bounds__(128) mh_kernel(KModel km, b2m_mh_args A) {
+template <int DMAX, bool COMPACT>
+__global__ void __launch_bounds__(128) mh_kernel(const __grid_constant__ KModel km, b2m_mh_args A) {
   extern __shared__ __align__(16) unsigned char smem[];
   SModel sm;
   unsigned char *mail = model_to_smem(km, smem, sm);
@@ -160,10 +156,8 @@ __global__ void __launch_bounds__(128) mh_kernel(KModel km, b2m_mh_args A) {
 #pragma unroll
   for (int d = 0; d < DMAX; ++d) q[d] = (d < D) ? A.theta[c * D + d] : 0.f;
   float lp = A.logp[c];
-  if (lp != lp) {
-    to_mailbox<DMAX>(q, L.th, L.TS, D);
-    lp = eval_model<false>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
-  }
+  float gdummy[DMAX];
+  if (lp != lp) lp = evaluate<DMAX, COMPACT, false>(km, sm, L, q, gdummy);
   int64_t n_acc = A.n_accept[c];
 
   for (int it = 0; it < A.n_iter; ++it) {
@@ -175,8 +169,7 @@ __global__ void __launch_bounds__(128) mh_kernel(KModel km, b2m_mh_args A) {
     draw_normals<DMAX>(z, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0);
 #pragma unroll
     for (int d = 0; d < DMAX; ++d) qn[d] = __fadd_rn(q[d], __fmul_rn(z[d], A.proposal_scale));
-    to_mailbox<DMAX>(qn, L.th, L.TS, D);
-    const float lpn = eval_model<false>(sm, L.th, L.gr, L.TS, L.lane, G, L.gmask);
+    const float lpn = evaluate<DMAX, COMPACT, false>(km, sm, L, qn, gdummy);
     const float u = A.inj_uniform ? A.inj_uniform[row] : u01(w0.z);
     const bool accept = logf(u) < __fsub_rn(lpn, lp);
     if (accept) {
@@ -213,9 +206,9 @@ int launch_logp_grad(const KModel &km, const float *theta, int64_t C, float *log
   const int dmax = pick_dmax(km.D);
   const int G = pick_lanes(km, C, lanes);
   Geometry ge = geometry(km, C, G, dmax ? dmax : 2);
-  B2M_DISPATCH_DMAX(dmax, {
-    if (int rc = prep(logp_grad_kernel<DM>, ge.smem)) return rc;
-    logp_grad_kernel<DM><<<ge.grid, ge.block, ge.smem, st>>>(km, theta, C, logp, grad, G);
+  B2M_DISPATCH_DMAX(dmax, km.compact, {
+    if (int rc = prep(logp_grad_kernel<DM, CP>, ge.smem)) return rc;
+    logp_grad_kernel<DM, CP><<<ge.grid, ge.block, ge.smem, st>>>(km, theta, C, logp, grad, G);
   });
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
@@ -226,9 +219,9 @@ int launch_hmc(const KModel &km, b2m_hmc_args a, cudaStream_t st) {
   const int dmax = pick_dmax(km.D);
   a.lanes = pick_lanes(km, a.n_chains, a.lanes);
   Geometry ge = geometry(km, a.n_chains, a.lanes, dmax ? dmax : 2);
-  B2M_DISPATCH_DMAX(dmax, {
-    if (int rc = prep(hmc_kernel<DM>, ge.smem)) return rc;
-    hmc_kernel<DM><<<ge.grid, ge.block, ge.smem, st>>>(km, a);
+  B2M_DISPATCH_DMAX(dmax, km.compact, {
+    if (int rc = prep(hmc_kernel<DM, CP>, ge.smem)) return rc;
+    hmc_kernel<DM, CP><<<ge.grid, ge.block, ge.smem, st>>>(km, a);
   });
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
@@ -239,9 +232,9 @@ int launch_mh(const KModel &km, b2m_mh_args a, cudaStream_t st) {
   const int dmax = pick_dmax(km.D);
   a.lanes = pick_lanes(km, a.n_chains, a.lanes);
   Geometry ge = geometry(km, a.n_chains, a.lanes, dmax ? dmax : 2);
-  B2M_DISPATCH_DMAX(dmax, {
-    if (int rc = prep(mh_kernel<DM>, ge.smem)) return rc;
-    mh_kernel<DM><<<ge.grid, ge.block, ge.smem, st>>>(km, a);
+  B2M_DISPATCH_DMAX(dmax, km.compact, {
+    if (int rc = prep(mh_kernel<DM, CP>, ge.smem)) return rc;
+    mh_kernel<DM, CP><<<ge.grid, ge.block, ge.smem, st>>>(km, a);
   });
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());

@@ -70,6 +70,11 @@ __device__ __forceinline__ void draw_normals(float (&z)[DMAX], int D, const floa
   }
 }
 
+struct Lane;
+template <int DMAX, bool COMPACT, bool GRAD>
+__device__ __forceinline__ float evaluate(const KModel &km, const SModel &sm, const Lane &L, const float (&q)[DMAX],
+                                          float (&g)[DMAX]);
+
 struct Lane {
   int64_t chain;   // clamped local chain index
   bool writer;     // lane 0 of an in-range chain
@@ -94,6 +99,21 @@ __device__ __forceinline__ Lane make_lane(int64_t n_chains, int G, unsigned char
   return L;
 }
 
+// One fused value(+gradient): compact models evaluate from registers and the constant bank, the general path goes
+// through the shared-memory mailbox.  Identical arithmetic either way.
+template <int DMAX, bool COMPACT, bool GRAD>
+__device__ __forceinline__ float evaluate(const KModel &km, const SModel &sm, const Lane &L, const float (&q)[DMAX],
+                                          float (&g)[DMAX]) {
+  if constexpr (COMPACT) {
+    return eval_model_c<GRAD, DMAX>(km, sm, q, g, L.lane, L.G, L.gmask);
+  } else {
+    to_mailbox<DMAX>(q, L.th, L.TS, sm.D);
+    const float lp = eval_model<GRAD>(sm, L.th, L.gr, L.TS, L.lane, L.G, L.gmask);
+    if (GRAD) from_mailbox<DMAX>(g, L.gr, L.TS, sm.D);
+    return lp;
+  }
+}
+
 // ---------------------------------------------------------------- host-side launchers
 inline int pick_dmax(int D) { return D <= 2 ? 2 : D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 0; }
 
@@ -111,7 +131,7 @@ inline Geometry geometry(const KModel &km, int64_t n_chains, int G, int dmax) {
   const int64_t total = n_chains * G;
   ge.block = dim3(threads);
   ge.grid = dim3((unsigned)((total + threads - 1) / threads));
-  ge.smem = model_smem_bytes(km) + sizeof(float) * 2 * (size_t)dmax * threads;
+  ge.smem = model_smem_bytes(km) + (km.compact ? 0 : sizeof(float) * 2 * (size_t)dmax * threads);
   return ge;
 }
 
@@ -121,12 +141,14 @@ static int prep(K kernel, size_t smem) {
   return 0;
 }
 
-#define B2M_DISPATCH_DMAX(dmax, ...)                       \
-  switch (dmax) {                                           \
-    case 2: { constexpr int DM = 2; __VA_ARGS__; } break;          \
-    case 4: { constexpr int DM = 4; __VA_ARGS__; } break;          \
-    case 8: { constexpr int DM = 8; __VA_ARGS__; } break;          \
-    case 16: { constexpr int DM = 16; __VA_ARGS__; } break;        \
+#define B2M_DISPATCH_DMAX(dmax, compact, ...)                                        \
+  switch ((dmax) + ((compact) ? 100 : 0)) {                                           \
+    case 102: { constexpr int DM = 2; constexpr bool CP = true; __VA_ARGS__; } break;  \
+    case 104: { constexpr int DM = 4; constexpr bool CP = true; __VA_ARGS__; } break;  \
+    case 2: { constexpr int DM = 2; constexpr bool CP = false; __VA_ARGS__; } break;   \
+    case 4: { constexpr int DM = 4; constexpr bool CP = false; __VA_ARGS__; } break;   \
+    case 8: { constexpr int DM = 8; constexpr bool CP = false; __VA_ARGS__; } break;   \
+    case 16: { constexpr int DM = 16; constexpr bool CP = false; __VA_ARGS__; } break; \
     default: b2m::set_error("pointwise models support at most 16 scalar parameters"); return 1; \
   }
 
