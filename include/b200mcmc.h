@@ -210,6 +210,18 @@ void b2m_comm_destroy(b2m_comm *c);
 int b2m_model_set_comm(b2m_model *m, b2m_comm *c, void *stream); /* collective (sums the shard row counts); c may be NULL */
 int b2m_comm_allreduce_f32(b2m_comm *c, float *buf, int64_t n, void *stream);   /* in place, sum */
 
+/* ---- diagnostics on the device ----
+ * draws is [S, C, D] as written by the samplers.
+ * b2m_diag_series: per (chain, parameter) series -> mean [C, D], variance (ddof 0) [C, D], effective sample size by
+ *   the reference's estimator (ess_mode 0: examples/06_nuts_comparison.py:22-41, 1: examples/02_hmc_comparison.py:111-128)
+ *   and by Geyer's initial positive sequence; the two ESS outputs may be NULL.
+ * b2m_diag_params: per parameter -> out[d][5] = pooled mean, pooled std (np.mean / np.std of
+ *   mlx_mcmc/inference/mcmc.py:219-220 over all chains), Gelman-Rubin R-hat, ESS summed over chains (both estimators). */
+int b2m_diag_series(const float *draws, int64_t S, int64_t C, int64_t D, int32_t ess_mode, float *mean, float *var,
+                    float *ess_ref, float *ess_geyer, void *stream);
+int b2m_diag_params(const float *mean, const float *var, const float *ess_ref, const float *ess_geyer, int64_t S,
+                    int64_t C, int64_t D, double *out, void *stream);
+
 /* Instrumentation: CUDA-event timing of every GEMM launch of the GLM class, on the launching stream.
  * b2m_profile(1) resets and starts recording, b2m_profile(0) stops; b2m_profile_read synchronises the device and
  * returns {K5 total ms, K5 launches, K6 total ms, K6 launches}. */

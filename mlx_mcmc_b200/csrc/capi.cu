@@ -23,6 +23,11 @@ int glm_build(GlmModel &g, const float *X, const float *y, int N, int D);
 int debug_tc_gemm(const float *A, const float *Bm, int M, int N, int K, float *Cout, int chunk_kb, int mma_mask,
                   cudaStream_t st);
 
+int diag_series(const float *draws, int64_t S, int64_t C, int64_t D, int ess_mode, float *mean, float *var, float *ess_ref,
+                float *ess_geyer, cudaStream_t st);
+int diag_params(const float *mean, const float *var, const float *ess_ref, const float *ess_geyer, int64_t S, int64_t C,
+                int64_t D, double *out, cudaStream_t st);
+
 }  // namespace b2m
 
 struct b2m_model {
@@ -132,6 +137,21 @@ int64_t b2m_launch_count(void) { return b2m::g_launches; }
 int b2m_debug_tc_gemm(const float *A, const float *Bm, int M, int N, int K, float *C, int chunk_kb, int mma_mask,
                       void *stream) {
   return b2m::debug_tc_gemm(A, Bm, M, N, K, C, chunk_kb, mma_mask, static_cast<cudaStream_t>(stream));
+}
+
+int b2m_diag_series(const float *draws, int64_t S, int64_t C, int64_t D, int32_t ess_mode, float *mean, float *var,
+                    float *ess_ref, float *ess_geyer, void *stream) {
+  B2M_REQUIRE(draws && mean && var, "b2m_diag_series: NULL argument");
+  B2M_REQUIRE(S > 0 && C > 0 && D > 0, "b2m_diag_series: sizes must be positive");
+  B2M_REQUIRE(ess_mode == 0 || ess_mode == 1, "b2m_diag_series: ess_mode must be 0 or 1");
+  return b2m::diag_series(draws, S, C, D, ess_mode, mean, var, ess_ref, ess_geyer, static_cast<cudaStream_t>(stream));
+}
+
+int b2m_diag_params(const float *mean, const float *var, const float *ess_ref, const float *ess_geyer, int64_t S,
+                    int64_t C, int64_t D, double *out, void *stream) {
+  B2M_REQUIRE(mean && var && out, "b2m_diag_params: NULL argument");
+  B2M_REQUIRE(S > 0 && C > 0 && D > 0, "b2m_diag_params: sizes must be positive");
+  return b2m::diag_params(mean, var, ess_ref, ess_geyer, S, C, D, out, static_cast<cudaStream_t>(stream));
 }
 
 int b2m_profile(int32_t enable) {

@@ -5,6 +5,8 @@ reported verbatim; `ess_geyer` is the standard initial-positive-sequence estimat
 two disagree in sign (the reference's estimator goes negative on antithetic chains)."""
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
 
@@ -67,3 +69,53 @@ def min_ess(draws: dict, num_chains: int = 1, estimator=ess_geyer, max_chains: i
             tot = sum(estimator(a[c, :, j]) for c in idx) * (C / len(idx))
             best = tot if best is None else min(best, tot)
     return float(best)
+
+
+# ------------------------------------------------------------------------------------------ on the device
+def device_series_stats(draws, ess: bool = True, ess_mode: int = 0):
+    """Per (chain, parameter) statistics of `draws` [S, C, D] (float32 CUDA tensor, the samplers' own layout),
+    computed by libb200mcmc.so without moving the draws: dict of [C, D] tensors `mean`, `var` (ddof 0) and, with
+    ``ess``, `ess` (the reference examples' estimator: examples/06_nuts_comparison.py:22-41 for ess_mode 0,
+    examples/02_hmc_comparison.py:111-128 for 1) and `ess_geyer`."""
+    import torch
+    from . import _cabi
+    if not (draws.is_cuda and draws.dtype == torch.float32 and draws.dim() == 3):
+        raise ValueError("device_series_stats expects a float32 CUDA tensor of shape [S, C, D]")
+    draws = draws.contiguous()
+    S, Cn, D = draws.shape
+    lib = _cabi.load()
+    out = {k: torch.empty((Cn, D), dtype=torch.float32, device=draws.device)
+           for k in (("mean", "var", "ess", "ess_geyer") if ess else ("mean", "var"))}
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    with torch.cuda.device(draws.device):
+        _cabi.check(lib.b2m_diag_series(ptr(draws), S, Cn, D, ess_mode, ptr(out["mean"]), ptr(out["var"]),
+                                        ptr(out.get("ess")), ptr(out.get("ess_geyer")),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out
+
+
+def device_summary(draws, layout=None, ess: bool = True, ess_mode: int = 0):
+    """Per-parameter posterior diagnostics of `draws` [S, C, D] on the device: pooled `mean` and `std` (what
+    ``MCMC.summary`` reports, mcmc.py:219-220), Gelman-Rubin `rhat` across the C chains, and `ess` / `ess_geyer`
+    summed over chains.  Returns ``{name: {stat: float | np.ndarray}}`` when `layout` (the model's parameter
+    layout) is given, else a dict of [D] numpy arrays.  Only D x 5 doubles travel to the host."""
+    import torch
+    from . import _cabi
+    st = device_series_stats(draws, ess, ess_mode)
+    S, Cn, D = draws.shape
+    lib = _cabi.load()
+    out = torch.empty((D, 5), dtype=torch.float64, device=draws.device)
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    with torch.cuda.device(draws.device):
+        _cabi.check(lib.b2m_diag_params(ptr(st["mean"]), ptr(st["var"]), ptr(st.get("ess")), ptr(st.get("ess_geyer")),
+                                        S, Cn, D, ptr(out), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    h = out.cpu().numpy()
+    cols = {"mean": h[:, 0], "std": h[:, 1], "rhat": h[:, 2]}
+    if ess:
+        cols.update(ess=h[:, 3], ess_geyer=h[:, 4])
+    if layout is None:
+        return cols
+    table = {}
+    for name, (off, n, shp) in layout.items():
+        table[name] = {k: (float(v[off]) if not shp else v[off:off + n].copy()) for k, v in cols.items()}
+    return table

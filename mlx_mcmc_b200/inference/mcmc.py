@@ -25,6 +25,7 @@ class MCMC:
         self.samples = None
         self.acceptance_rate = None
         self.info = None
+        self._single_chain = True
 
     def run(self, initial_params, num_samples=1000, num_warmup=1000, method='metropolis', proposal_scale=0.1,
             random_seed=0, verbose=True, **kwargs):
@@ -32,6 +33,7 @@ class MCMC:
         sampler verbatim (mcmc.py:96,122,156,177), so e.g. ``step_size`` with ``method='metropolis'``
         raises TypeError exactly as there.  Extra keyword-only sampler options (``num_chains``,
         ``adapt``, ``compat``, ``return_torch`` ...) ride in ``kwargs`` too."""
+        self._single_chain = int(kwargs.get("num_chains", 1)) == 1
         if method in ('hmc', 'nuts'):
             if verbose:
                 print(f"\n{_RULE}\nB200-MCMC: {method.upper()} Sampling\n{_RULE}\n")
@@ -89,6 +91,26 @@ class MCMC:
                 'mean': float(np.mean(x)), 'std': float(np.std(x)), 'median': float(np.median(x)),
                 f'{lo:.1f}%': float(np.percentile(x, lo)), f'{hi:.1f}%': float(np.percentile(x, hi)),
             }
+        return table
+
+    def diagnostics(self, ess=True):
+        """Per-parameter `mean`, `std`, `rhat`, `ess` (the reference examples' estimator summed over chains) and
+        `ess_geyer`, computed on the device from the draws of the last ``run(..., return_torch=True)`` -- nothing but
+        the table travels to the host.  (Not in the reference: README.md:212-216 lists R-hat / ESS as planned; the
+        ESS definition is examples/06_nuts_comparison.py:22-41.)  Vector parameters give arrays."""
+        import torch
+        from ..diagnostics import device_summary
+        if self.samples is None:
+            raise ValueError("Must run sampling first. Call run() method.")
+        table = {}
+        for name, x in self.samples.items():
+            if not (hasattr(x, "is_cuda") and x.is_cuda):
+                raise ValueError("diagnostics() works on device draws: call run(..., return_torch=True)")
+            if self._single_chain:
+                x = x[None]                                   # (S,) | (S, n) -> (1, S[, n])
+            d = x.reshape(x.shape[0], x.shape[1], -1).permute(1, 0, 2).contiguous().float()   # [S, C, n]
+            cols = device_summary(d, None, ess)
+            table[name] = {k: (float(v[0]) if x.dim() == 2 else v.copy()) for k, v in cols.items()}
         return table
 
     def print_summary(self, credible_interval=0.95):

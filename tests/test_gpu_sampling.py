@@ -271,3 +271,47 @@ def test_multi_gpu_sharding_when_two_gpus_are_visible(cuda):
                         "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(root, "tests", "mgpu_check.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MGPU_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_device_diagnostics_match_the_oracle(cuda):
+    """SURVEY.md 8(f) rows 1-2 on the device: per-series mean / var / ESS (both reference estimators, Geyer), pooled
+    mean / std, R-hat -- against the oracle restatement of the reference's compute_ess / summary on the fixture series
+    and on random multi-chain draws."""
+    from oracle.refport import diagnostics as OD
+    from mlx_mcmc_b200.diagnostics import device_series_stats, device_summary
+    from util import golden
+    g = golden("diagnostics")
+    for n in (8, 57, 400, 1500):                                  # ragged lengths incl. the shortest the estimator takes
+        rows = [r for r in g["ess"] if r["n"] == n]
+        x = np.stack([np.asarray(r["x"], dtype=np.float32) for r in rows], axis=1)       # [S, series]
+        d = torch.from_numpy(x[:, :, None].copy()).cuda()                                 # [S, C = series, D = 1]
+        for mode, key in ((0, "ess06"), (1, "ess02")):
+            st = device_series_stats(d, ess=True, ess_mode=mode)
+            got = st["ess"][:, 0].cpu().numpy()
+            for j, r in enumerate(rows):
+                if r[key] is None:
+                    continue
+                assert abs(got[j] - r[key]) <= 2e-3 * abs(r[key]) + 1e-3, (n, r["kind"], mode, got[j], r[key])
+        assert np.allclose(st["mean"][:, 0].cpu().numpy(), x.mean(0), rtol=1e-6, atol=1e-6)
+        assert np.allclose(st["var"][:, 0].cpu().numpy(), x.astype(np.float64).var(0), rtol=1e-5, atol=1e-7)
+        gey = st["ess_geyer"][:, 0].cpu().numpy()
+        for j in range(x.shape[1]):
+            want = ess_geyer(x[:, j])
+            assert abs(gey[j] - want) <= 1e-3 * abs(want) + 1e-3, (n, rows[j]["kind"], gey[j], want)
+    rng = np.random.default_rng(0)
+    S, C, D = 300, 37, 5
+    x = (rng.standard_normal((S, C, D)) * np.arange(1, D + 1) + 0.3 * rng.standard_normal((1, C, 1))).astype(np.float32)
+    tab = device_summary(torch.from_numpy(x).cuda())
+    for dd in range(D):
+        assert abs(tab["mean"][dd] - x[:, :, dd].mean()) < 1e-5
+        assert abs(tab["std"][dd] - x[:, :, dd].astype(np.float64).std()) < 1e-5 * (dd + 1)
+        assert abs(tab["rhat"][dd] - OD.rhat(x[:, :, dd].T)) < 1e-5
+        want = sum(float(OD.compute_ess(x[:, c, dd])) for c in range(C))
+        assert abs(tab["ess"][dd] - want) <= 2e-3 * want
+    # through the API: run(..., return_torch=True) then diagnostics()
+    fn, init, meta = W.c2_event_rate(B.ns)
+    m = B.MCMC(fn)
+    m.run(init, num_samples=400, num_warmup=300, method="hmc", num_chains=64, return_torch=True, verbose=False,
+          adapt="dual_averaging")
+    t = m.diagnostics()["rate"]
+    assert abs(t["mean"] - meta.post_shape / meta.post_rate) < 0.05 and 0.99 < t["rhat"] < 1.05 and t["ess_geyer"] > 64 * 50, t

@@ -75,3 +75,23 @@ def test_known_answers_on_oracle():
         ns.Categorical()
     with pytest.raises(ValueError):
         ns.Categorical(probs=[0.5, 0.5], logits=[0.0, 0.0])
+
+
+def test_diagnostics_restatement_matches_reference_fixture():
+    """oracle/refport/diagnostics.py against the answers the reference's own function bodies gave
+    (tests/golden/diagnostics.json, written by oracle/make_golden_diag.py)."""
+    from oracle.refport import diagnostics as D
+    g = golden("diagnostics")
+    for row in g["ess"]:
+        x = np.asarray(row["x"], dtype=np.float32)
+        assert float(D.compute_ess(x)) == row["ess06"], (row["kind"], row["n"])
+        if row["ess02"] is not None:
+            assert float(D.compute_ess_example02(x)) == row["ess02"], (row["kind"], row["n"])
+    smp = {"mu": np.asarray(g["summary"]["samples"]["mu"], dtype=np.float32),
+           "beta": np.asarray(g["summary"]["samples"]["beta"], dtype=np.float32)}
+    assert D.summary(smp, g["summary"]["credible_interval"]) == g["summary"]["table"]
+    # the product's host-side estimator is the same function
+    from mlx_mcmc_b200.diagnostics import compute_ess
+    for row in g["ess"]:
+        x = np.asarray(row["x"], dtype=np.float32)
+        assert abs(compute_ess(x) - row["ess06"]) <= 1e-4 * abs(row["ess06"])
