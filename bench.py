@@ -556,7 +556,7 @@ def bench_pointwise(torch, dist, B, lib, args, wl, wl_name, rank, world, local_r
                        "traffic": None, "kernel": "hmc_kernel" if wl["method"] == "hmc" else "mh_kernel",
                        "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                        "note": "observations live in shared memory; the kernel is FP32-issue bound, not HBM bound -- see `issue` "
-                               "and profiles/r01_hmc_kernel_c2_v1_ncu_summary.md"}
+                               "and profiles/r01_hmc_kernel_c2_v2_ncu_summary.md"}
     out["issue"] = {"grad_evals_per_s_per_gpu": value / world, "obs_terms_per_s_per_gpu": value / world * getattr(meta, "N", 0),
                     "avg_launch_ms": launch_ms}
     if full and not args.no_ess and wl["method"] == "hmc":

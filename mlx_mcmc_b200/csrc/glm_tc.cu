@@ -427,8 +427,37 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows, cols] row-major fp32, box = 32 columns (128 bytes) x box_rows rows, 128-byte swizzle
+// [rows, cols] row-major fp32, box = 32 columns (128 bytes) x box_rows rows, 128-byte swizzle.
+// Encoded maps are cached by (base, rows, cols, box): a NUTS leaf would otherwise pay eight driver calls per
+// value+gradient, which is visible at the small configurations where a leaf is ~100 us of device time.
+int make_map_uncached(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_rows);
+
+struct MapKey {
+  const float *base;
+  int64_t rows, cols;
+  int box;
+  bool operator==(const MapKey &o) const { return base == o.base && rows == o.rows && cols == o.cols && box == o.box; }
+};
+struct MapSlot {
+  MapKey key;
+  CUtensorMap map;
+};
+static thread_local std::vector<MapSlot> tl_maps;
+
 int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_rows) {
+  const MapKey key{base, rows, cols, box_rows};
+  for (const MapSlot &s : tl_maps)
+    if (s.key == key) {
+      *map = s.map;
+      return 0;
+    }
+  if (int rc = make_map_uncached(map, base, rows, cols, box_rows)) return rc;
+  if (tl_maps.size() >= 256) tl_maps.clear();   // workspaces were reallocated many times: start over
+  tl_maps.push_back(MapSlot{key, *map});
+  return 0;
+}
+
+int make_map_uncached(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   B2M_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
