@@ -614,7 +614,8 @@ def main():
     import mlx_mcmc_b200 as B
     from mlx_mcmc_b200 import _cabi
 
-    os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    # NCCL writes its version banner / debug lines to stdout by default; rank 0 must print exactly one JSON line there
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
