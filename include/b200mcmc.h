@@ -188,6 +188,10 @@ void b2m_model_destroy(b2m_model *m);
 int b2m_model_dim(const b2m_model *m);
 /* 0 = pointwise class (persistent register-resident kernels), 1 = GLM class (X @ beta, GEMM kernels) */
 int b2m_model_class(const b2m_model *m);
+/* GLM class: arithmetic of the two contractions -- 0 fp32 FMA tiles, 1 tcgen05 3xTF32, 2 tcgen05 3xFP16 (operands scaled
+ * by powers of two into fp16's range, chosen automatically unless the data's dynamic range is too wide); -1 otherwise.
+ * The environment variable B2M_GLM_PATH = simt | tc | tc16 forces one. */
+int b2m_model_glm_path(const b2m_model *m);
 
 /* log p(theta_c) and d/dtheta for C chains.  Replaces mx.grad(log_prob_flat)(*params) plus the
  * separate value call in hamiltonian() (kernels/hmc.py:53-67,102-111).  grad may be NULL. */

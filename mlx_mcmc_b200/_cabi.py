@@ -63,7 +63,7 @@ MAX_TREE_DEPTH = 12
 ABI_VERSION = 1
 
 EXPORTS = ["b2m_last_error", "b2m_abi_version", "b2m_struct_sizes", "b2m_model_create", "b2m_model_destroy",
-           "b2m_model_dim", "b2m_model_class", "b2m_logp_grad", "b2m_hmc_run", "b2m_mh_run", "b2m_nuts_run",
+           "b2m_model_dim", "b2m_model_class", "b2m_model_glm_path", "b2m_logp_grad", "b2m_hmc_run", "b2m_mh_run", "b2m_nuts_run",
            "b2m_launch_count", "b2m_comm_unique_id", "b2m_comm_init", "b2m_comm_destroy", "b2m_model_set_comm",
            "b2m_comm_allreduce_f32", "b2m_profile", "b2m_profile_read", "b2m_diag_series", "b2m_diag_params"]
 
@@ -104,6 +104,7 @@ def load(build_if_missing: bool = True):
     lib.b2m_model_destroy.restype = None
     lib.b2m_model_dim.argtypes = [c_p]
     lib.b2m_model_class.argtypes = [c_p]
+    lib.b2m_model_glm_path.argtypes = [c_p]
     lib.b2m_logp_grad.argtypes = [c_p, c_p, C.c_int64, c_p, c_p, C.c_int32, c_p]
     lib.b2m_hmc_run.argtypes = [c_p, C.POINTER(HmcArgs), c_p]
     lib.b2m_mh_run.argtypes = [c_p, C.POINTER(MhArgs), c_p]

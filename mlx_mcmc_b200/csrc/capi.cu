@@ -102,8 +102,11 @@ static int setup_glm(b2m_model *m, int D) {
   g.weight = L.weight;
   g.sigma_param = L.p1.kind == B2M_OP_PARAM ? L.p1.a : -1;
   g.sigma_const = L.p1.kind == B2M_OP_CONST ? L.p1.c : 1.f;
+  // B2M_GLM_PATH: simt (fp32 FMA tiles) | tc (tcgen05 3xTF32) | tc16 (tcgen05 3xFP16 with scaled operands);
+  // default: the fp16 encoding when the data's dynamic range allows it (checked in glm_build), else tf32
   const char *path = getenv("B2M_GLM_PATH");
-  g.use_tc = b2m::tc_available() && !(path && std::string(path) == "simt");
+  const std::string want = path ? path : "auto";
+  g.use_tc = (!b2m::tc_available() || want == "simt") ? 0 : (want == "tc" ? 1 : 2);
   if (int rc = b2m::glm_build(g, X.data, Y.data, (int)L.length, (int)X.cols)) return rc;
   // prior = all other terms
   std::vector<b2m_term> prior;
@@ -266,6 +269,7 @@ void b2m_model_destroy(b2m_model *m) {
 
 int b2m_model_dim(const b2m_model *m) { return m ? m->km.D : -1; }
 int b2m_model_class(const b2m_model *m) { return m ? m->model_class : -1; }
+int b2m_model_glm_path(const b2m_model *m) { return (m && m->model_class == 1) ? m->glm.use_tc : -1; }
 
 int b2m_logp_grad(b2m_model *m, const float *theta, int64_t n_chains, float *logp, float *grad, int32_t lanes,
                   void *stream) {

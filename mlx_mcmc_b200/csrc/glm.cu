@@ -1,6 +1,11 @@
 // GLM-class evaluation pipeline: pack -> GEMM (B X^T) with residual epilogue -> GEMM (R X) -> finish.
 #include "glm.cuh"
 
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
 #include <vector>
 
 namespace b2m {
@@ -15,7 +20,7 @@ static int dev_alloc(T **p, size_t n) {
 
 static void free_workspace(GlmModel &g) {
   FREE(g.B); FREE(g.Bh); FREE(g.Bl); FREE(g.R); FREE(g.Rh); FREE(g.Rl); FREE(g.G); FREE(g.ss_part); FREE(g.inv_var);
-  FREE(g.red);
+  FREE(g.red); FREE(g.B16h); FREE(g.B16l); FREE(g.R16h); FREE(g.R16l); FREE(g.a_unscale); FREE(g.r_scale); FREE(g.r_unscale);
   g.cap = 0;
 }
 
@@ -23,6 +28,7 @@ void glm_free(GlmModel &g) {
   free_workspace(g);
   FREE(g.X); FREE(g.XT); FREE(g.Xh); FREE(g.Xl); FREE(g.XTh); FREE(g.XTl); FREE(g.y);
   FREE(g.y0); FREE(g.beta0); FREE(g.center_part);
+  FREE(g.X16h); FREE(g.X16l); FREE(g.XT16h); FREE(g.XT16l); FREE(g.col_scale); FREE(g.inv_col_scale); FREE(g.y0max_bits);
   FREE(g.ws);
   g.ws_cap = 0;
   if (g.h_flag) cudaFreeHost(g.h_flag);
@@ -41,13 +47,19 @@ int glm_reserve(GlmModel &g, int64_t n_chains) {
       if (need > g_rows) g_rows = need;
     }
   g.g_splits_cap = (int)((g_rows + cp - 1) / cp);
-  if (dev_alloc(&g.B, cp * g.Dp) || dev_alloc(&g.G, g_rows * g.Dp) || dev_alloc(&g.R, cp * (size_t)g.Np) ||
-      dev_alloc(&g.ss_part, (size_t)(g.Np / 64) * cp) || dev_alloc(&g.inv_var, cp) ||
-      dev_alloc(&g.red, (size_t)cp * g.Dp + cp))
+  if (dev_alloc(&g.B, cp * g.Dp) || dev_alloc(&g.G, g_rows * g.Dp) || dev_alloc(&g.ss_part, (size_t)(g.Np / 64) * cp) ||
+      dev_alloc(&g.inv_var, cp) || dev_alloc(&g.red, (size_t)cp * g.Dp + cp))
     return 2;
-  if (g.use_tc) {
+  if (g.use_tc == 0 && dev_alloc(&g.R, cp * (size_t)g.Np)) return 2;
+  if (g.use_tc == 1) {
     if (dev_alloc(&g.Bh, cp * g.Dp) || dev_alloc(&g.Bl, cp * g.Dp) || dev_alloc(&g.Rh, cp * (size_t)g.Np) ||
         dev_alloc(&g.Rl, cp * (size_t)g.Np))
+      return 2;
+  }
+  if (g.use_tc == 2) {
+    if (dev_alloc(&g.B16h, cp * g.Dp) || dev_alloc(&g.B16l, cp * g.Dp) || dev_alloc(&g.R16h, cp * (size_t)g.Np) ||
+        dev_alloc(&g.R16l, cp * (size_t)g.Np) || dev_alloc(&g.a_unscale, cp) || dev_alloc(&g.r_scale, cp) ||
+        dev_alloc(&g.r_unscale, cp))
       return 2;
   }
   g.cap = cp;
@@ -55,25 +67,95 @@ int glm_reserve(GlmModel &g, int64_t n_chains) {
 }
 
 // ---------------------------------------------------------------- data preparation (once per model)
-__global__ void pad_transpose_split_kernel(const float *__restrict__ X, int N, int D, int Np, int Dp, float *Xp,
-                                           float *XT, float *Xh, float *Xl, float *XTh, float *XTl) {
+__global__ void pad_transpose_kernel(const float *__restrict__ X, int N, int D, int Np, int Dp, float *Xp, float *XT) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)Np * Dp) return;
   const int n = int(i / Dp), d = int(i % Dp);
   const float v = (n < N && d < D) ? X[(int64_t)n * D + d] : 0.f;
-  float hi, lo;
-  split_tf32(v, hi, lo);
   Xp[i] = v;
-  XT[(int64_t)d * Np + n] = v;
-  if (Xh) {
-    Xh[i] = hi; Xl[i] = lo;
-    XTh[(int64_t)d * Np + n] = hi; XTl[(int64_t)d * Np + n] = lo;
-  }
+  if (XT) XT[(int64_t)d * Np + n] = v;
+}
+
+__global__ void split_tf32_kernel(const float *__restrict__ Xp, int Np, int Dp, float *Xh, float *Xl, float *XTh, float *XTl) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)Np * Dp) return;
+  const int n = int(i / Dp), d = int(i % Dp);
+  float hi, lo;
+  split_tf32(Xp[i], hi, lo);
+  Xh[i] = hi; Xl[i] = lo;
+  XTh[(int64_t)d * Np + n] = hi; XTl[(int64_t)d * Np + n] = lo;
 }
 
 __global__ void pad_vector_kernel(const float *__restrict__ y, int N, int Np, float *yp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Np) yp[i] = i < N ? y[i] : 0.f;
+}
+
+// fp16 encoding: column maxima and the largest row norm of the padded X
+__global__ void __launch_bounds__(256) x_stats_kernel(const float *__restrict__ Xp, int Np, int Dp, unsigned *colmax_bits,
+                                                      unsigned *rownorm_bits) {
+  // block (32, 8): 32 columns x 8 row lanes, rows strided by gridDim.y * 8
+  const int d = blockIdx.x * 32 + threadIdx.x;
+  float cm = 0.f;
+  for (int n = blockIdx.y * 8 + threadIdx.y; n < Np; n += gridDim.y * 8) cm = fmaxf(cm, fabsf(Xp[(int64_t)n * Dp + d]));
+  atomicMax(colmax_bits + d, __float_as_uint(cm));   // non-negative floats order like their bit patterns
+  if (blockIdx.x == 0) {                             // row norms: one warp (threadIdx.y) per row, lanes stride the columns
+    for (int n = blockIdx.y * 8 + threadIdx.y; n < Np; n += gridDim.y * 8) {
+      float s = 0.f;
+      for (int c = threadIdx.x; c < Dp; c += 32) { const float v = Xp[(int64_t)n * Dp + c]; s = fmaf(v, v, s); }
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (threadIdx.x == 0) atomicMax(rownorm_bits, __float_as_uint(sqrtf(s)));
+    }
+  }
+}
+
+// Entries of a column below its maximum x 2^-17 land, after the column is scaled to just under 2^14, where the lo half
+// of the fp16 split is subnormal: they keep fewer than the nominal 22 bits.  Count them (zeros are exact and excluded).
+__global__ void __launch_bounds__(256) x_small_count_kernel(const float *__restrict__ Xp, int Np, int Dp,
+                                                            const unsigned *__restrict__ colmax_bits, unsigned *small) {
+  const int d = blockIdx.x * 32 + threadIdx.x;
+  const float thr = __uint_as_float(colmax_bits[d]) * 7.62939453125e-6f;   // 2^-17
+  unsigned cnt = 0;
+  for (int n = blockIdx.y * 8 + threadIdx.y; n < Np; n += gridDim.y * 8) {
+    const float a = fabsf(Xp[(int64_t)n * Dp + d]);
+    cnt += (a > 0.f && a < thr) ? 1u : 0u;
+  }
+  if (cnt) atomicAdd(small + d, cnt);
+}
+
+// power-of-two scale that puts a maximum of `m` just below 2^14 (fp16 overflows at 65504 = 2^16 - 32)
+__host__ __device__ inline float pow2_scale(float m) {
+  if (!(m > 0.f) || !(m < 3.0e38f)) return 1.0f;
+  int e;
+  frexpf(m, &e);                 // m = f * 2^e, f in [0.5, 1)  =>  m < 2^e
+  int k = 14 - e;
+  if (k > 100) k = 100;
+  if (k < -100) k = -100;
+  return ldexpf(1.0f, k);
+}
+
+__global__ void col_scale_kernel(const unsigned *__restrict__ colmax_bits, int Dp, float *col_scale, float *inv_col_scale) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= Dp) return;
+  const float s = pow2_scale(__uint_as_float(colmax_bits[d]));
+  col_scale[d] = s;
+  inv_col_scale[d] = 1.0f / s;
+}
+
+__device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+__global__ void split_f16_kernel(const float *__restrict__ Xp, int Np, int Dp, const float *__restrict__ col_scale,
+                                 __half *Xh, __half *Xl, __half *XTh, __half *XTl) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)Np * Dp) return;
+  const int n = int(i / Dp), d = int(i % Dp);
+  __half hi, lo;
+  split_f16(Xp[i] * col_scale[d], hi, lo);
+  Xh[i] = hi; Xl[i] = lo;
+  XTh[(int64_t)d * Np + n] = hi; XTl[(int64_t)d * Np + n] = lo;
 }
 
 int glm_build(GlmModel &g, const float *X, const float *y, int N, int D) {
@@ -82,13 +164,51 @@ int glm_build(GlmModel &g, const float *X, const float *y, int N, int D) {
   g.Np = (N + 255) / 256 * 256;
   g.Dp = (D + 63) / 64 * 64;
   const size_t nd = (size_t)g.Np * g.Dp;
-  if (dev_alloc(&g.X, nd) || dev_alloc(&g.XT, nd) || dev_alloc(&g.y, g.Np) || dev_alloc(&g.y0, g.Np) ||
-      dev_alloc(&g.beta0, g.Dp) || dev_alloc(&g.center_part, (size_t)kCenterSlices * g.Dp))
+  if (dev_alloc(&g.X, nd) || dev_alloc(&g.y, g.Np) || dev_alloc(&g.y0, g.Np) || dev_alloc(&g.beta0, g.Dp) ||
+      dev_alloc(&g.center_part, (size_t)kCenterSlices * g.Dp) || dev_alloc(&g.y0max_bits, 1))
     return 2;
-  if (g.use_tc && (dev_alloc(&g.Xh, nd) || dev_alloc(&g.Xl, nd) || dev_alloc(&g.XTh, nd) || dev_alloc(&g.XTl, nd))) return 2;
-  pad_transpose_split_kernel<<<(unsigned)((nd + 255) / 256), 256>>>(X, N, D, g.Np, g.Dp, g.X, g.XT, g.Xh, g.Xl, g.XTh, g.XTl);
+  if (g.use_tc == 0 && dev_alloc(&g.XT, nd)) return 2;
+  pad_transpose_kernel<<<(unsigned)((nd + 255) / 256), 256>>>(X, N, D, g.Np, g.Dp, g.X, g.XT);
   pad_vector_kernel<<<(g.Np + 255) / 256, 256>>>(y, N, g.Np, g.y);
   g_launches += 2;
+  if (g.use_tc == 2) {
+    // column maxima and the largest row norm; then, per column, how many entries are so far below the column's
+    // maximum (< 2^-17 of it) that the scaled fp16 split cannot hold them to full precision: data with more than
+    // 0.1 % of such entries in some column (one wild outlier is enough) keeps the tf32 encoding (8-bit exponent)
+    unsigned *stats = nullptr;   // [Dp] column maxima (float bits) + [1] largest row norm + [Dp] small-entry counts
+    if (dev_alloc(&stats, 2 * g.Dp + 1)) return 2;
+    B2M_CHECK_CUDA(cudaMemset(stats, 0, sizeof(unsigned) * (2 * g.Dp + 1)));
+    x_stats_kernel<<<dim3(g.Dp / 32, 64), dim3(32, 8)>>>(g.X, g.Np, g.Dp, stats, stats + g.Dp);
+    x_small_count_kernel<<<dim3(g.Dp / 32, 64), dim3(32, 8)>>>(g.X, g.Np, g.Dp, stats, stats + g.Dp + 1);
+    g_launches += 2;
+    std::vector<unsigned> hmax(2 * g.Dp + 1);
+    B2M_CHECK_CUDA(cudaMemcpy(hmax.data(), stats, sizeof(unsigned) * (2 * g.Dp + 1), cudaMemcpyDeviceToHost));
+    memcpy(&g.x_rownorm_max, &hmax[g.Dp], sizeof(float));
+    bool ok = g.x_rownorm_max < 3.0e38f;
+    for (int d = 0; d < g.Dp && ok; ++d) {
+      float m;
+      memcpy(&m, &hmax[d], sizeof(float));
+      if (!(m < 3.0e38f)) ok = false;                                  // inf / NaN in the data
+      if ((double)hmax[g.Dp + 1 + d] > 1e-3 * (double)(N > 0 ? N : 1)) ok = false;
+    }
+    const char *force = getenv("B2M_GLM_PATH");
+    if (!ok && !(force && std::string(force) == "tc16")) g.use_tc = 1;   // wide-range data: tf32 encoding
+    if (g.use_tc == 2) {
+      if (dev_alloc(&g.X16h, nd) || dev_alloc(&g.X16l, nd) || dev_alloc(&g.XT16h, nd) || dev_alloc(&g.XT16l, nd) ||
+          dev_alloc(&g.col_scale, g.Dp) || dev_alloc(&g.inv_col_scale, g.Dp))
+        return 2;
+      col_scale_kernel<<<(g.Dp + 127) / 128, 128>>>(stats, g.Dp, g.col_scale, g.inv_col_scale);
+      split_f16_kernel<<<(unsigned)((nd + 255) / 256), 256>>>(g.X, g.Np, g.Dp, g.col_scale, g.X16h, g.X16l, g.XT16h, g.XT16l);
+      g_launches += 2;
+    }
+    B2M_CHECK_CUDA(cudaDeviceSynchronize());
+    cudaFree(stats);
+  }
+  if (g.use_tc == 1) {
+    if (dev_alloc(&g.Xh, nd) || dev_alloc(&g.Xl, nd) || dev_alloc(&g.XTh, nd) || dev_alloc(&g.XTl, nd)) return 2;
+    split_tf32_kernel<<<(unsigned)((nd + 255) / 256), 256>>>(g.X, g.Np, g.Dp, g.Xh, g.Xl, g.XTh, g.XTl);
+    ++g_launches;
+  }
   B2M_CHECK_CUDA(cudaGetLastError());
   B2M_CHECK_CUDA(cudaDeviceSynchronize());
   return 0;
@@ -137,7 +257,8 @@ __global__ void glm_center_final_kernel(const double *__restrict__ part, int Dp,
 // y0[n] = (y[n] - c) - sum_d X[n, d] beta0[d], float64 accumulation, one warp per observation row
 __global__ void __launch_bounds__(256) glm_y0_kernel(const float *__restrict__ X, const float *__restrict__ y,
                                                      const float *__restrict__ beta0, int N, int Np, int Dp,
-                                                     float loc_const, float *__restrict__ y0) {
+                                                     float loc_const, float *__restrict__ y0,
+                                                     unsigned *__restrict__ y0max_bits) {
   extern __shared__ float sb[];
   for (int d = threadIdx.x; d < Dp; d += blockDim.x) sb[d] = beta0[d];
   __syncthreads();
@@ -154,14 +275,20 @@ __global__ void __launch_bounds__(256) glm_y0_kernel(const float *__restrict__ X
     }
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) y0[n] = n < N ? (float)(((double)y[n] - (double)loc_const) - acc) : 0.f;
+  if (lane == 0) {
+    const float v = n < N ? (float)(((double)y[n] - (double)loc_const) - acc) : 0.f;
+    y0[n] = v;
+    if (v == v) atomicMax(y0max_bits, __float_as_uint(fabsf(v)));
+  }
 }
 
 int glm_recenter(GlmModel &g, const float *theta, int64_t C, cudaStream_t st) {
   dim3 gp(g.Dp / 32, kCenterSlices), bp(32, 8);
   glm_center_partial_kernel<<<gp, bp, 0, st>>>(theta, C, g.Dtot, g.beta_off, g.D, g.Dp, g.center_part);
   glm_center_final_kernel<<<(g.Dp + 127) / 128, 128, 0, st>>>(g.center_part, g.Dp, C, g.beta0);
-  glm_y0_kernel<<<(g.Np + 7) / 8, 256, sizeof(float) * g.Dp, st>>>(g.X, g.y, g.beta0, g.N, g.Np, g.Dp, g.loc_const, g.y0);
+  cudaMemsetAsync(g.y0max_bits, 0, sizeof(unsigned), st);
+  glm_y0_kernel<<<(g.Np + 7) / 8, 256, sizeof(float) * g.Dp, st>>>(g.X, g.y, g.beta0, g.N, g.Np, g.Dp, g.loc_const, g.y0,
+                                                                   g.y0max_bits);
   g_launches += 3;
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -188,6 +315,55 @@ __global__ void glm_pack_kernel(const float *__restrict__ theta, const float *__
   if (d == 0) {
     const float s = (row < C && sigma_param >= 0) ? theta[c * Dtot + sigma_param] : sigma_const;
     inv_var[row] = 1.0f / (s * s);
+  }
+}
+
+// fp16 encoding of the A operand of K5, one warp per chain row:
+//   delta'_d = (beta_d - beta0_d) / col_scale_d          (X' = X col_scale, so delta' . X' = delta . X exactly)
+//   row scale s_a = 2^k putting max_d |delta'_d| just below 2^14; hi / lo halves of delta' s_a
+// and the row scale of the residual operand of K6 from a bound that is known before K5 runs:
+//   |z_n| = |y0_n - (X delta)_n| <= max|y0| + ||delta||_2 max_n ||X_n||_2      (Cauchy-Schwarz)
+__global__ void __launch_bounds__(128) glm_pack16_kernel(const float *__restrict__ theta, const float *__restrict__ beta0,
+                                                         const int *__restrict__ idx, int64_t C, int64_t Cp, int Dtot,
+                                                         int beta_off, int D, int Dp, int sigma_param, float sigma_const,
+                                                         float weight, const float *__restrict__ inv_col_scale,
+                                                         const unsigned *__restrict__ y0max_bits, float x_rownorm_max,
+                                                         __half *Bh, __half *Bl, float *inv_var, float *a_unscale,
+                                                         float *r_scale, float *r_unscale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= Cp) return;
+  const bool live = row < C;
+  const int64_t c = (live && idx) ? idx[row] : row;
+  float amax = 0.f, n2 = 0.f;
+  if (live)
+    for (int d = lane; d < D; d += 32) {
+      const float dl = __fsub_rn(theta[c * Dtot + beta_off + d], beta0[d]);
+      amax = fmaxf(amax, fabsf(dl * inv_col_scale[d]));
+      n2 = fmaf(dl, dl, n2);
+    }
+  for (int o = 16; o > 0; o >>= 1) {
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  }
+  const float sa = pow2_scale(amax);
+  for (int d = lane; d < Dp; d += 32) {
+    float v = 0.f;
+    if (live && d < D) v = __fsub_rn(theta[c * Dtot + beta_off + d], beta0[d]) * inv_col_scale[d] * sa;
+    __half hi, lo;
+    split_f16(v, hi, lo);
+    Bh[row * Dp + d] = hi;
+    Bl[row * Dp + d] = lo;
+  }
+  if (lane == 0) {
+    const float sg = (live && sigma_param >= 0) ? theta[c * Dtot + sigma_param] : sigma_const;
+    const float iv = 1.0f / (sg * sg);
+    inv_var[row] = iv;
+    const float bound = (__uint_as_float(*y0max_bits) + sqrtf(n2) * x_rownorm_max) * fabsf(iv * weight);
+    const float sr = pow2_scale(bound);
+    a_unscale[row] = 1.0f / sa;
+    r_scale[row] = sr;
+    r_unscale[row] = 1.0f / sr;
   }
 }
 
@@ -279,12 +455,14 @@ int simt_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
 // red[c, d] = sum over split-K partials of G ; red[Cp*Dp + c] = sum over column tiles of ss_part.  Fixed order.
 __global__ void __launch_bounds__(256) glm_reduce_kernel(const float *__restrict__ G, int g_splits,
                                                          const float *__restrict__ ss_part, int n_tiles, int64_t Cp,
-                                                         int Dp, float *__restrict__ red) {
+                                                         int Dp, const float *__restrict__ r_unscale,
+                                                         const float *__restrict__ inv_col_scale, float *__restrict__ red) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nG = Cp * Dp;
   if (i < nG) {
     float v = 0.f;
     for (int s = 0; s < g_splits; ++s) v += G[(int64_t)s * nG + i];
+    if (r_unscale) v *= r_unscale[i / Dp] * inv_col_scale[i % Dp];   // fp16 encoding: the ranks' scales differ
     red[i] = v;
   } else if (i < nG + Cp) {
     const int64_t c = i - nG;
@@ -320,7 +498,9 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
                                                           int sigma_param, float sigma_const, float weight, int N,
                                                           int n_tiles, const float *__restrict__ ss_part,
                                                           const float *__restrict__ G, int g_splits, float *__restrict__ logp,
-                                                          float *__restrict__ grad, const int *__restrict__ idx) {
+                                                          float *__restrict__ grad, const int *__restrict__ idx,
+                                                          const float *__restrict__ r_unscale,
+                                                          const float *__restrict__ inv_col_scale) {
   extern __shared__ __align__(16) unsigned char smem[];
   SModel sm;
   sm.n_terms = 0;
@@ -340,8 +520,10 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
   if (gr) {
     for (int d = lane; d < Dtot; d += 32) {
       float v = 0.f;
-      if (d >= beta_off && d < beta_off + D)
+      if (d >= beta_off && d < beta_off + D) {
         for (int s = 0; s < g_splits; ++s) v += G[((int64_t)s * Cp + c) * Dp + (d - beta_off)];  // fixed order
+        if (r_unscale) v *= r_unscale[c] * inv_col_scale[d - beta_off];   // fp16 encoding: undo the operand scales
+      }
       if (d == sigma_param) v = weight * (ss * iv - (float)N) / sg;
       gr[d] = v;
     }
@@ -387,8 +569,14 @@ int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float
   if (idx) C = n_rows;   // compacted batch: rows 0..n_rows-1 are the chains idx[0..n_rows-1]
   const int64_t Cp = C <= 128 ? 128 : (C + 255) / 256 * 256;   // one 128-row tile, or whole 256-row CTA-pair tiles
   const int64_t tot = Cp * g.Dp;
-  glm_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, g.beta0, idx, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
-                                                                  g.sigma_param, g.sigma_const, g.B, g.Bh, g.Bl, g.inv_var);
+  if (g.use_tc == 2)
+    glm_pack16_kernel<<<(unsigned)((Cp + 3) / 4), 128, 0, st>>>(theta, g.beta0, idx, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
+                                                                g.sigma_param, g.sigma_const, g.weight, g.inv_col_scale,
+                                                                g.y0max_bits, g.x_rownorm_max, g.B16h, g.B16l, g.inv_var,
+                                                                g.a_unscale, g.r_scale, g.r_unscale);
+  else
+    glm_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, g.beta0, idx, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
+                                                                    g.sigma_param, g.sigma_const, g.B, g.Bh, g.Bl, g.inv_var);
   ++g_launches;
   int n_tiles;
   if (g.use_tc) {
@@ -403,17 +591,19 @@ int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float
   const size_t smem = g.has_prior ? model_smem_bytes(g.prior) : 16;
   const float *ssp = g.ss_part, *Gp = g.G;
   int splits = g.use_tc ? g.g_splits : 1;
+  const float *r_un = g.use_tc == 2 ? g.r_unscale : nullptr, *ics = g.use_tc == 2 ? g.inv_col_scale : nullptr;
   if (g.comm) {
     // observation shard: contiguous [Cp, Dp] gradient partial || [Cp] sum z^2, summed over ranks on this stream
     const int64_t n_red = Cp * g.Dp + Cp;
-    glm_reduce_kernel<<<(unsigned)((n_red + 255) / 256), 256, 0, st>>>(g.G, grad ? splits : 0, g.ss_part, n_tiles, Cp, g.Dp, g.red);
+    glm_reduce_kernel<<<(unsigned)((n_red + 255) / 256), 256, 0, st>>>(g.G, grad ? splits : 0, g.ss_part, n_tiles, Cp, g.Dp, r_un, ics, g.red);
     ++g_launches;
     if (int rc = comm_allreduce_f32(g.comm, grad ? g.red : g.red + Cp * g.Dp, grad ? n_red : Cp, st)) return rc;
     Gp = g.red; ssp = g.red + Cp * g.Dp; splits = 1; n_tiles = 1;
+    r_un = nullptr; ics = nullptr;   // already unscaled before the sum over ranks
   }
   glm_finish_kernel<<<(unsigned)((C + 3) / 4), 128, smem, st>>>(g.prior, g.has_prior ? 1 : 0, theta, C, Cp, g.Dtot, g.beta_off,
                                                                  g.D, g.Dp, g.sigma_param, g.sigma_const, g.weight,
-                                                                 (int)g.N_total, n_tiles, ssp, Gp, splits, logp, grad, idx);
+                                                                 (int)g.N_total, n_tiles, ssp, Gp, splits, logp, grad, idx, r_un, ics);
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -8,6 +8,8 @@
 //   * fp32 SIMT tiles (glm_simt.cu)    -- any shape, the validation path
 //   * TMA + tcgen05 3xTF32 (glm_tc.cu) -- B, X, R split into tf32 hi + lo parts, fp32 accumulation in TMEM
 #pragma once
+#include <cuda_fp16.h>
+
 #include "model.cuh"
 
 namespace b2m {
@@ -34,6 +36,12 @@ struct GlmModel {
   float *X = nullptr, *XT = nullptr;                         // [Np, Dp], [Dp, Np] fp32
   float *Xh = nullptr, *Xl = nullptr, *XTh = nullptr, *XTl = nullptr;  // tf32 hi / lo splits
   float *y = nullptr;                                        // [Np]
+  // fp16 hi/lo encoding (use_tc == 2): X' = X * col_scale[d] (power of two, column maximum just below 2^14) split
+  // into two halves, hi = fp16(x'), lo = fp16(x' - hi); same for the transposed copy
+  __half *X16h = nullptr, *X16l = nullptr, *XT16h = nullptr, *XT16l = nullptr;
+  float *col_scale = nullptr, *inv_col_scale = nullptr;      // [Dp]
+  float x_rownorm_max = 0.f;                                 // max_n ||X_n||_2: Cauchy-Schwarz bound of |(X delta)_n|
+  unsigned *y0max_bits = nullptr;                            // device scalar: max_n |y0_n| as float bits (per recentre)
   // centring (glm.cu): beta0 = mean current position of the batch, y0 = y - c - X beta0 (float64 accumulation)
   float *y0 = nullptr, *beta0 = nullptr;                     // [Np], [Dp]
   double *center_part = nullptr;                             // [32, Dp]
@@ -44,11 +52,14 @@ struct GlmModel {
   int64_t cap = 0;
   float *B = nullptr, *Bh = nullptr, *Bl = nullptr;          // [cap, Dp]
   float *R = nullptr, *Rh = nullptr, *Rl = nullptr;          // [cap, Np]
+  __half *B16h = nullptr, *B16l = nullptr;                   // [cap, Dp]  fp16 encoding of (beta - beta0) / col_scale * row scale
+  __half *R16h = nullptr, *R16l = nullptr;                   // [cap, Np]  fp16 encoding of R * row scale
+  float *a_unscale = nullptr, *r_scale = nullptr, *r_unscale = nullptr;   // [cap] per-row scales of the two A operands
   float *G = nullptr;                                        // [g_splits_cap, cap, Dp] split-K partials of the gradient
   int g_splits = 1, g_splits_cap = 1;
   float *ss_part = nullptr;                                  // [Np / 64, cap] per-column-tile partial sum of squares
   float *inv_var = nullptr;                                  // [cap]
-  int use_tc = 0;                                            // 1: tcgen05 path, 0: SIMT path
+  int use_tc = 0;                                            // 0: SIMT fp32 tiles, 1: tcgen05 3xTF32, 2: tcgen05 3xFP16
   // sampler workspace (glm_samplers.cu): one arena reused across calls, plus a pinned host flag
   char *ws = nullptr;
   size_t ws_cap = 0;

@@ -26,6 +26,7 @@
 //                 RESID: z = y - c - acc, per-row sum z^2, R = w z / sigma^2 split into tf32 hi/lo   (K5)
 //                 PLAIN: store the split-K partial of G                                              (K6)
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <vector>
@@ -36,9 +37,13 @@ namespace b2m {
 
 namespace {
 
-constexpr int BLOCK_M = 128, BLOCK_K = 32;            // 32 floats = 128 bytes = SWIZZLE_128B row
-constexpr int UMMA_K = 8;                             // tf32: 32 bytes per MMA k-step
-constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
+constexpr int BLOCK_M = 128;
+constexpr int ROW_BYTES = 128;                        // one SWIZZLE_128B row of K: 32 tf32 values or 64 fp16 values
+constexpr int MMA_K_BYTES = 32;                       // one MMA k-step: 8 tf32 or 16 fp16 values
+constexpr int A_TILE_BYTES = BLOCK_M * ROW_BYTES;     // 16 KB
+// elements of K per k-block (one swizzle row) for the two operand encodings
+template <bool F16> struct Enc { static constexpr int BLOCK_K = F16 ? 64 : 32; static constexpr int ELT = F16 ? 2 : 4; };
+constexpr int BLOCK_K = 32;                           // tf32 k-block (host-side helpers of the tf32 path)
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp, MMA warp, 8 promotion/epilogue warps
 constexpr int DEFAULT_CHUNK_KB = 4;                     // k-blocks accumulated inside the tensor core per chunk
@@ -132,6 +137,34 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool F16, int NCTA>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (F16) {
+    if (NCTA == 2) umma_f16_pair(tmem_d, adesc, bdesc, idesc, accumulate); else umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+  } else {
+    if (NCTA == 2) umma_tf32_pair(tmem_d, adesc, bdesc, idesc, accumulate); else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+  }
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -157,15 +190,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
-__host__ __device__ constexpr uint32_t make_idesc(int n, int m = BLOCK_M) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// a_format / b_format: 0 = F16, 2 = TF32
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m = BLOCK_M, bool f16 = false) {
+  return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct EpiParams {
   // RESID
   const float *y;
   const float *inv_var;
-  float *Rh, *Rl, *ss_part;
+  void *Rh, *Rl;          // [Cp, Np] residual operand of K6: float (tf32 values) or __half
+  float *ss_part;
+  const float *a_unscale; // F16: [Cp] 1 / (row scale of the A operand), applied to the accumulators
+  const float *r_scale;   // F16: [Cp] row scale of R before the fp16 split
   int64_t Cp;
   int Np, N_valid;
   float loc_const, weight;
@@ -177,7 +214,7 @@ struct EpiParams {
 template <int BLOCK_N, int NCTA>
 struct Cfg {
   static constexpr int B_ROWS = BLOCK_N / NCTA;         // rows of the B tile staged by one CTA
-  static constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 4;
+  static constexpr int B_TILE_BYTES = B_ROWS * ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 6 ? 6 : (192 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
@@ -185,12 +222,13 @@ struct Cfg {
   static constexpr int COLS_PER_WARP = BLOCK_N / 2;    // each promotion warp owns 32 rows x half of the columns
 };
 
-template <int BLOCK_N, bool RESID, int NCTA>
+template <int BLOCK_N, bool RESID, int NCTA, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int k_blocks_total,
                int k_blocks_per_split, int CHUNK_KB, int mma_mask, int Tm, int Tn, int n_tiles, EpiParams E) {
   using C = Cfg<BLOCK_N, NCTA>;
+  constexpr int BLOCK_K = Enc<F16>::BLOCK_K;   // K elements per k-block (shadows the tf32 constant)
   constexpr int SCRATCH_BYTES = RESID ? NUM_EPI_WARPS * 32 * 33 * 4 : 0;   // per-warp transpose scratch of the K5 epilogue
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -276,7 +314,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0 && cta == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N, BLOCK_M * NCTA);
+      constexpr uint32_t idesc = make_idesc(BLOCK_N, BLOCK_M * NCTA, F16);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t gch = 0;   // chunk counter across tiles: buffer = gch & 1, barrier parity = (gch >> 1) & 1
@@ -296,17 +334,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           const uint64_t dAh = make_desc(st), dAl = make_desc(st + A_TILE_BYTES);
           const uint64_t dBh = make_desc(st + 2 * A_TILE_BYTES), dBl = make_desc(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // start-address advance inside the swizzle row
-            if (NCTA == 2) {
-              umma_tf32_pair(tmem_d, dAh + adv, dBh + adv, idesc, (kc | k) != 0 ? 1u : 0u);
-              if (mma_mask & 2) umma_tf32_pair(tmem_d, dAh + adv, dBl + adv, idesc, 1u);
-              if (mma_mask & 4) umma_tf32_pair(tmem_d, dAl + adv, dBh + adv, idesc, 1u);
-            } else {
-              umma_tf32(tmem_d, dAh + adv, dBh + adv, idesc, (kc | k) != 0 ? 1u : 0u);
-              if (mma_mask & 2) umma_tf32(tmem_d, dAh + adv, dBl + adv, idesc, 1u);
-              if (mma_mask & 4) umma_tf32(tmem_d, dAl + adv, dBh + adv, idesc, 1u);
-            }
+          for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k) {
+            const uint64_t adv = (uint64_t)((k * MMA_K_BYTES) >> 4);  // start-address advance inside the swizzle row
+            umma<F16, NCTA>(tmem_d, dAh + adv, dBh + adv, idesc, (kc | k) != 0 ? 1u : 0u);
+            if (mma_mask & 2) umma<F16, NCTA>(tmem_d, dAh + adv, dBl + adv, idesc, 1u);
+            if (mma_mask & 4) umma<F16, NCTA>(tmem_d, dAl + adv, dBh + adv, idesc, 1u);
           }
           // frees the stage (in both CTAs of a pair) once the MMAs above have read it
           if (NCTA == 2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
@@ -357,6 +389,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       // and stores whole 128-byte row segments.
       float ss = 0.f;
       const float ivw = E.inv_var[m] * E.weight;
+      // F16: the accumulators carry the row scale of the A operand (delta); R gets its own row scale before the split
+      const float a_un = F16 ? E.a_unscale[m] : 1.0f;
       float *scratch = scratch_base + (warp - 2) * (32 * 33);
       const int64_t row0 = (int64_t)(m0 + q * 32);
       // the observations of this warp's columns: one coalesced load per 32-column block (lane = column), handed to
@@ -373,18 +407,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         for (int j = 0; j < 32; ++j) {
           const int n = nb + b * 32 + j;
           const float yj = __shfl_sync(0xffffffffu, yv[b], j);
-          const float z = (n < E.N_valid) ? yj - acc[b * 32 + j] : 0.f;
+          const float z = (n < E.N_valid) ? yj - (F16 ? acc[b * 32 + j] * a_un : acc[b * 32 + j]) : 0.f;
           ss = fmaf(z, z, ss);
           scratch[lane * 33 + j] = z * ivw;
         }
         __syncwarp();
-        float *rh = E.Rh + row0 * E.Np + nb + b * 32 + lane, *rl = E.Rl + row0 * E.Np + nb + b * 32 + lane;
+        const int64_t off = row0 * E.Np + nb + b * 32 + lane;
+        if (F16) {
+          __half *rh = static_cast<__half *>(E.Rh) + off, *rl = static_cast<__half *>(E.Rl) + off;
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          float hi, lo;
-          split_tf32(scratch[r * 33 + lane], hi, lo);
-          rh[(int64_t)r * E.Np] = hi;
-          rl[(int64_t)r * E.Np] = lo;
+          for (int r = 0; r < 32; ++r) {
+            const float v = scratch[r * 33 + lane] * __ldg(E.r_scale + row0 + r);
+            const __half hi = __float2half_rn(v);
+            rh[(int64_t)r * E.Np] = hi;
+            rl[(int64_t)r * E.Np] = __float2half_rn(v - __half2float(hi));
+          }
+        } else {
+          float *rh = static_cast<float *>(E.Rh) + off, *rl = static_cast<float *>(E.Rl) + off;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            float hi, lo;
+            split_tf32(scratch[r * 33 + lane], hi, lo);
+            rh[(int64_t)r * E.Np] = hi;
+            rl[(int64_t)r * E.Np] = lo;
+          }
         }
         __syncwarp();
       }
@@ -430,10 +476,10 @@ EncodeTiledFn encode_fn() {
 // [rows, cols] row-major fp32, box = 32 columns (128 bytes) x box_rows rows, 128-byte swizzle.
 // Encoded maps are cached by (base, rows, cols, box): a NUTS leaf would otherwise pay eight driver calls per
 // value+gradient, which is visible at the small configurations where a leaf is ~100 us of device time.
-int make_map_uncached(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_rows);
+int make_map_uncached(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int box_rows, bool f16);
 
 struct MapKey {
-  const float *base;
+  const void *base;
   int64_t rows, cols;
   int box;
   bool operator==(const MapKey &o) const { return base == o.base && rows == o.rows && cols == o.cols && box == o.box; }
@@ -444,27 +490,28 @@ struct MapSlot {
 };
 static thread_local std::vector<MapSlot> tl_maps;
 
-int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_rows) {
-  const MapKey key{base, rows, cols, box_rows};
+// `cols` in elements of the operand encoding (float for tf32, __half for f16: box is negative-coded as -box_rows)
+int make_map(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int box_rows, bool f16 = false) {
+  const MapKey key{base, rows, cols, f16 ? -box_rows : box_rows};
   for (const MapSlot &s : tl_maps)
     if (s.key == key) {
       *map = s.map;
       return 0;
     }
-  if (int rc = make_map_uncached(map, base, rows, cols, box_rows)) return rc;
+  if (int rc = make_map_uncached(map, base, rows, cols, box_rows, f16)) return rc;
   if (tl_maps.size() >= 256) tl_maps.clear();   // workspaces were reallocated many times: start over
   tl_maps.push_back(MapSlot{key, *map});
   return 0;
 }
 
-int make_map_uncached(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_rows) {
+int make_map_uncached(CUtensorMap *map, const void *base, int64_t rows, int64_t cols, int box_rows, bool f16) {
   EncodeTiledFn fn = encode_fn();
   B2M_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * (f16 ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)box_rows};   // one 128-byte swizzle row of K
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -480,11 +527,11 @@ struct Prof {
   std::vector<cudaEvent_t> ev[2];   // [0] = K5 (residual epilogue), [1] = K6 (split-K gradient): start, stop, start, ...
 } g_prof;
 
-template <int BLOCK_N, bool RESID, int NCTA>
+template <int BLOCK_N, bool RESID, int NCTA, bool F16>
 int launch_tc_n(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &Bh, const CUtensorMap &Bl, dim3 grid,
                 int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st, int chunk_kb, int mma_mask) {
   using C = Cfg<BLOCK_N, NCTA>;
-  auto kernel = tc_gemm_kernel<BLOCK_N, RESID, NCTA>;
+  auto kernel = tc_gemm_kernel<BLOCK_N, RESID, NCTA, F16>;
   constexpr int SMEM = C::SMEM_BYTES + (RESID ? NUM_EPI_WARPS * 32 * 33 * 4 : 0);
   static bool configured = false;
   if (!configured) {
@@ -526,9 +573,13 @@ int launch_tc_n(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap 
 template <int BLOCK_N, bool RESID>
 int launch_tc(int ncta, const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &Bh, const CUtensorMap &Bl,
               dim3 grid, int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st,
-              int chunk_kb = DEFAULT_CHUNK_KB, int mma_mask = 7) {
-  if (ncta == 2) return launch_tc_n<BLOCK_N, RESID, 2>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
-  return launch_tc_n<BLOCK_N, RESID, 1>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
+              int chunk_kb = DEFAULT_CHUNK_KB, int mma_mask = 7, bool f16 = false) {
+  if (f16) {
+    if (ncta == 2) return launch_tc_n<BLOCK_N, RESID, 2, true>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
+    return launch_tc_n<BLOCK_N, RESID, 1, true>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
+  }
+  if (ncta == 2) return launch_tc_n<BLOCK_N, RESID, 2, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
+  return launch_tc_n<BLOCK_N, RESID, 1, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
 }
 
 }  // namespace
@@ -578,7 +629,7 @@ static int pair_mode(int64_t Cp) {
 // split-K factor of K6: enough CTAs to fill the 148 SMs in whole waves, each split at least 8 k-blocks deep
 int grad_splits(const GlmModel &g, int64_t Cp) {
   const int64_t tiles = (Cp / BLOCK_M) * (g.Dp / grad_block_n(g));   // CTAs per split
-  const int kb = g.Np / BLOCK_K;
+  const int kb = g.Np / (g.use_tc == 2 ? 64 : 32);
   int max_s = kb / 8 > 0 ? kb / 8 : 1;
   if (max_s > 32) max_s = 32;
   int best = 1;
@@ -595,36 +646,50 @@ int grad_splits(const GlmModel &g, int64_t Cp) {
 
 int tc_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st) {
   const int ncta = pair_mode(Cp);
+  const bool f16 = g.use_tc == 2;
+  const int bk = f16 ? 64 : 32;
+  const void *A_h = f16 ? (const void *)g.B16h : (const void *)g.Bh, *A_l = f16 ? (const void *)g.B16l : (const void *)g.Bl;
+  const void *B_h = f16 ? (const void *)g.X16h : (const void *)g.Xh, *B_l = f16 ? (const void *)g.X16l : (const void *)g.Xl;
   CUtensorMap Ah, Al, Bh, Bl;
-  if (make_map(&Ah, g.Bh, Cp, g.Dp, BLOCK_M) || make_map(&Al, g.Bl, Cp, g.Dp, BLOCK_M) ||
-      make_map(&Bh, g.Xh, g.Np, g.Dp, 256 / ncta) || make_map(&Bl, g.Xl, g.Np, g.Dp, 256 / ncta))
+  if (make_map(&Ah, A_h, Cp, g.Dp, BLOCK_M, f16) || make_map(&Al, A_l, Cp, g.Dp, BLOCK_M, f16) ||
+      make_map(&Bh, B_h, g.Np, g.Dp, 256 / ncta, f16) || make_map(&Bl, B_l, g.Np, g.Dp, 256 / ncta, f16))
     return 2;
   EpiParams E{};
-  E.y = g.y0; E.inv_var = g.inv_var; E.Rh = g.Rh; E.Rl = g.Rl; E.ss_part = g.ss_part; E.Cp = Cp; E.Np = g.Np;
+  E.y = g.y0; E.inv_var = g.inv_var; E.ss_part = g.ss_part; E.Cp = Cp; E.Np = g.Np;
+  E.Rh = f16 ? (void *)g.R16h : (void *)g.Rh;
+  E.Rl = f16 ? (void *)g.R16l : (void *)g.Rl;
+  E.a_unscale = g.a_unscale; E.r_scale = g.r_scale;
   E.N_valid = g.N; E.loc_const = 0.f; E.weight = g.weight;   // y0 is already centred and shifted (glm.cu)
   dim3 grid((unsigned)(Cp / BLOCK_M), g.Np / 256, 1);
-  return launch_tc<256, true>(ncta, Ah, Al, Bh, Bl, grid, g.Dp / BLOCK_K, g.Dp / BLOCK_K, E, st,
-                              chunk_kb("B2M_TC_CHUNK_RESID", DEFAULT_CHUNK_KB));
+  // promotion interval: 128 values of K for tf32; 256 for fp16 -- the MMAs of a tile take half as long there, and the
+  // longer chunk lets the issuer run far enough into the next tile to cover the epilogue (measured at C4: 4.28 ->
+  // 4.12 ms per evaluation, gradient error 1.3e-6 -> 2.1e-6; K5's accumulators only hold X (beta - beta0))
+  return launch_tc<256, true>(ncta, Ah, Al, Bh, Bl, grid, g.Dp / bk, g.Dp / bk, E, st,
+                              chunk_kb("B2M_TC_CHUNK_RESID", DEFAULT_CHUNK_KB), 7, f16);
 }
 
 int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
   const int ncta = pair_mode(Cp);
+  const bool f16 = g.use_tc == 2;
+  const int bk = f16 ? 64 : 32;
   const int bn = grad_block_n(g);
   const int splits = grad_splits(g, Cp);
-  const int kb_total = g.Np / BLOCK_K;
+  const int kb_total = g.Np / bk;
   const int kb_per = (kb_total + splits - 1) / splits;
+  const void *A_h = f16 ? (const void *)g.R16h : (const void *)g.Rh, *A_l = f16 ? (const void *)g.R16l : (const void *)g.Rl;
+  const void *B_h = f16 ? (const void *)g.XT16h : (const void *)g.XTh, *B_l = f16 ? (const void *)g.XT16l : (const void *)g.XTl;
   CUtensorMap Ah, Al, Bh, Bl;
-  if (make_map(&Ah, g.Rh, Cp, g.Np, BLOCK_M) || make_map(&Al, g.Rl, Cp, g.Np, BLOCK_M) ||
-      make_map(&Bh, g.XTh, g.Dp, g.Np, bn / ncta) || make_map(&Bl, g.XTl, g.Dp, g.Np, bn / ncta))
+  if (make_map(&Ah, A_h, Cp, g.Np, BLOCK_M, f16) || make_map(&Al, A_l, Cp, g.Np, BLOCK_M, f16) ||
+      make_map(&Bh, B_h, g.Dp, g.Np, bn / ncta, f16) || make_map(&Bl, B_l, g.Dp, g.Np, bn / ncta, f16))
     return 2;
   EpiParams E{};
   E.Gpart = g.G; E.Cp = Cp; E.Dp = g.Dp;
   dim3 grid((unsigned)(Cp / BLOCK_M), g.Dp / bn, (unsigned)((kb_total + kb_per - 1) / kb_per));
   g.g_splits = (int)grid.z;
-  const int ck = chunk_kb("B2M_TC_CHUNK_GRAD", DEFAULT_CHUNK_KB);
-  if (bn == 256) return launch_tc<256, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
-  if (bn == 128) return launch_tc<128, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
-  return launch_tc<64, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck);
+  const int ck = chunk_kb("B2M_TC_CHUNK_GRAD", f16 ? DEFAULT_CHUNK_KB / 2 : DEFAULT_CHUNK_KB);
+  if (bn == 256) return launch_tc<256, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck, 7, f16);
+  if (bn == 128) return launch_tc<128, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck, 7, f16);
+  return launch_tc<64, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck, 7, f16);
 }
 
 

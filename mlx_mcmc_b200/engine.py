@@ -62,6 +62,7 @@ class DeviceModel:
             _cabi.check(self.lib.b2m_model_create(terms, n_t, lin, n_l, arrays, n_a, self.D, C.byref(handle)))
         self.handle = handle
         self.model_class = self.lib.b2m_model_class(handle)
+        self.glm_path = {0: "simt", 1: "tc", 2: "tc16"}.get(self.lib.b2m_model_glm_path(handle))
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None

@@ -1,4 +1,6 @@
-"""GPU: the tcgen05 3xTF32 contractions (K5/K6) against float64 numpy and against the fp32 SIMT path."""
+"""GPU: the tcgen05 contractions (K5/K6) in both operand encodings -- 3xTF32 ("tc") and 3xFP16 with power-of-two
+operand scaling ("tc16", the default when the data's dynamic range allows it) -- against float64 and against the
+fp32 SIMT path."""
 import math
 import os
 
@@ -35,9 +37,11 @@ def _float64(meta, theta):
     return lp, r @ X - b / 100.0
 
 
+@pytest.mark.parametrize("path", ["tc", "tc16"])
 @pytest.mark.parametrize("n,d,c", [(200, 5, 7), (1000, 100, 130), (5000, 96, 300), (3000, 300, 1024), (40000, 64, 256)])
-def test_tc_logp_grad_vs_float64_and_simt(cuda, n, d, c):
-    tc, meta = _model("tc", n, d, seed=n + d)
+def test_tc_logp_grad_vs_float64_and_simt(cuda, n, d, c, path):
+    tc, meta = _model(path, n, d, seed=n + d)
+    assert tc.glm_path == path
     simt, _ = _model("simt", n, d, seed=n + d)
     rng = np.random.default_rng(1)
     theta = (meta.beta_true[None, :] + 0.2 * rng.standard_normal((c, d))).astype(np.float32)
@@ -57,8 +61,9 @@ def test_tc_logp_grad_vs_float64_and_simt(cuda, n, d, c):
     assert e_tc < 3e-6
 
 
-def test_tc_value_only_and_repeatability(cuda):
-    tc, meta = _model("tc", 2000, 40, seed=3)
+@pytest.mark.parametrize("path", ["tc", "tc16"])
+def test_tc_value_only_and_repeatability(cuda, path):
+    tc, meta = _model(path, 2000, 40, seed=3)
     theta = torch.from_numpy(np.tile(meta.beta_true, (64, 1)).astype(np.float32)).cuda()
     a, ga = tc.logp_grad(theta)
     b, _ = tc.logp_grad(theta, want_grad=False)
@@ -68,11 +73,11 @@ def test_tc_value_only_and_repeatability(cuda):
 
 
 # ------------------------------------------------------------------------------------------------ full size (C4)
-@pytest.fixture(scope="module")
-def c4(cuda):
-    """BASELINE.json's Target configuration: 1000 coefficients x 100,000 observations."""
-    fn, init, meta = W.regression(B.ns, 100000, 1000, seed=0)
-    model = compile_model(fn, init, cache=False)
+@pytest.fixture(scope="module", params=["tc16", "tc"])
+def c4(cuda, request):
+    """BASELINE.json's Target configuration: 1000 coefficients x 100,000 observations, both encodings."""
+    model, meta = _model(request.param, 100000, 1000, seed=0)
+    assert model.glm_path == request.param
     X64 = torch.from_numpy(meta.X).cuda().double()
     y64 = torch.from_numpy(meta.y).cuda().double()
     return model, meta, X64, y64
@@ -124,13 +129,56 @@ def test_c4_full_size_properties(c4):
     assert float(((lp[128:] - lp[:128]).double() - quad).abs().max()) < 2e-5 * float(lp.abs().max())
 
 
+@pytest.mark.parametrize("path", ["tc", "tc16"])
 @pytest.mark.parametrize("n,d,c", [(257, 65, 1), (255, 63, 129), (513, 1, 300), (4097, 129, 257)])
-def test_tc_ragged_shapes(cuda, n, d, c):
+def test_tc_ragged_shapes(cuda, n, d, c, path):
     """padding edges: N, D, C just off the 256 / 64 / 128 tile sizes, a single chain, a single coefficient"""
-    tc, meta = _model("tc", n, d, seed=n * 7 + d)
+    tc, meta = _model(path, n, d, seed=n * 7 + d)
     rng = np.random.default_rng(2)
     theta = (meta.beta_true[None, :] + 0.1 * rng.standard_normal((c, d))).astype(np.float32)
     lp, g = tc.logp_grad(torch.from_numpy(theta).cuda())
     lp64, g64 = _float64(meta, theta)
     assert np.max(np.abs(lp.cpu().numpy() - lp64) / np.abs(lp64)) < 1e-5
     assert np.max(np.abs(g.cpu().numpy() - g64)) / np.max(np.abs(g64)) < 1e-5
+
+
+def _custom_model(X, y):
+    mx, Normal = B.ns.mx, B.ns.Normal
+    Xa, ya = mx.array(X), mx.array(y)
+
+    def log_prob(params):
+        beta = params["beta"]
+        return mx.sum(Normal(0, 10.0).log_prob(beta)) + mx.sum(Normal(Xa @ beta, 1.0).log_prob(ya))
+    return compile_model(log_prob, {"beta": np.zeros(X.shape[1], dtype=np.float32)}, cache=False)
+
+
+def test_fp16_encoding_handles_column_scales_and_falls_back_on_outliers(cuda):
+    """Features on wildly different scales (1e-3 .. 1e3) keep the fp16 encoding -- every column gets its own power-of-two
+    scale -- and the 1e-5 gate; a column dominated by one outlier (max / rms > 4096) makes the model fall back to the
+    tf32 encoding at build time."""
+    rng = np.random.default_rng(3)
+    n, d, c = 6000, 48, 200
+    colscale = 10.0 ** rng.uniform(-3, 3, d)
+    X = (rng.standard_normal((n, d)) * colscale).astype(np.float32)
+    beta = (rng.standard_normal(d) / colscale).astype(np.float32)
+    y = (X.astype(np.float64) @ beta.astype(np.float64) + rng.standard_normal(n)).astype(np.float32)
+    model = _custom_model(X, y)
+    assert model.glm_path == "tc16"
+    theta = (beta[None, :] * (1 + 0.01 * rng.standard_normal((c, d)))).astype(np.float32)
+    lp, g = model.logp_grad(torch.from_numpy(theta).cuda())
+    b = theta.astype(np.float64)
+    r = y.astype(np.float64)[None, :] - b @ X.astype(np.float64).T
+    g64 = r @ X.astype(np.float64) - b / 100.0
+    lp64 = (-0.5 * (r ** 2).sum(1) - n * 0.5 * math.log(2 * math.pi) - 0.5 * (b ** 2).sum(1) / 100.0
+            - d * (0.5 * math.log(2 * math.pi) + math.log(10.0)))
+    assert np.max(np.abs(lp.cpu().numpy() - lp64) / np.abs(lp64)) < 1e-5
+    # per coefficient: each gradient component against the scale of ITS column (a norm-wise test over all columns
+    # would only see the largest-scale feature)
+    err = np.max(np.abs(g.cpu().numpy() - g64), axis=0) / np.max(np.abs(g64), axis=0)
+    assert err.max() < 1e-5, err.max()
+    X2 = X.copy()
+    X2[17, 5] = 3e5 * np.abs(X2[:, 5]).mean()              # one wild entry
+    wide = _custom_model(X2, y)
+    assert wide.glm_path == "tc"
+    lp2, g2 = wide.logp_grad(torch.from_numpy(theta).cuda())
+    assert torch.isfinite(lp2).all() and torch.isfinite(g2).all()
