@@ -518,9 +518,11 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
   float lp = weight * ((float)N * (-kHalfLog2Pi - logf(sg)) - 0.5f * ss * iv);
   float *gr = grad ? grad + src * Dtot : nullptr;
   if (gr) {
+#pragma unroll 2
     for (int d = lane; d < Dtot; d += 32) {
       float v = 0.f;
       if (d >= beta_off && d < beta_off + D) {
+#pragma unroll 8
         for (int s = 0; s < g_splits; ++s) v += G[((int64_t)s * Cp + c) * Dp + (d - beta_off)];  // fixed order
         if (r_unscale) v *= r_unscale[c] * inv_col_scale[d - beta_off];   // fp16 encoding: undo the operand scales
       }

@@ -46,10 +46,15 @@ __device__ inline void fill_momentum(float *p, int D, const float *inj, uint64_t
   }
 }
 
-__device__ __forceinline__ float kinetic_w(const float *p, int D, int lane) {
-  float s = 0.f;
-  for (int d = lane; d < D; d += 32) s = fmaf(p[d], p[d], s);
-  return 0.5f * warp_sum(s);
+__device__ __forceinline__ float kinetic_w(const float *__restrict__ p, int D, int lane) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int d = lane;
+  for (; d + 96 < D; d += 128) {
+    const float a = p[d], b = p[d + 32], c = p[d + 64], e = p[d + 96];
+    s0 = fmaf(a, a, s0); s1 = fmaf(b, b, s1); s2 = fmaf(c, c, s2); s3 = fmaf(e, e, s3);
+  }
+  for (; d < D; d += 32) s0 = fmaf(p[d], p[d], s0);
+  return 0.5f * warp_sum((s0 + s1) + (s2 + s3));
 }
 
 #define CHAIN_PROLOGUE(C)                                                        \
@@ -294,14 +299,35 @@ struct NutsBufs {
   float *alpha_it;  // [C] this iteration's mean acceptance statistic (pooled adaptation)
 };
 
-__device__ __forceinline__ void vcopy(float *dst, const float *src, int D, int lane) {
-  for (int d = lane; d < D; d += 32) dst[d] = src[d];
+// One warp copies a [D] vector.  These kernels are pure HBM streaming with one warp per chain: with a scalar loop each
+// lane has a single 4-byte load in flight and the copy is latency bound (the v1 leaf kernels took 120-200 us for
+// ~300 MB of traffic); 16-byte accesses, four independent loads before the first store, put enough bytes in flight.
+__device__ __forceinline__ void vcopy(float *__restrict__ dst, const float *__restrict__ src, int D, int lane) {
+  if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+    const float4 *__restrict__ s4 = reinterpret_cast<const float4 *>(src);
+    float4 *__restrict__ d4 = reinterpret_cast<float4 *>(dst);
+    const int n4 = D >> 2;
+    int i = lane;
+    for (; i + 96 < n4; i += 128) {
+      const float4 a = s4[i], b = s4[i + 32], c = s4[i + 64], e = s4[i + 96];
+      d4[i] = a; d4[i + 32] = b; d4[i + 64] = c; d4[i + 96] = e;
+    }
+    for (; i < n4; i += 32) d4[i] = s4[i];
+  } else {
+    int d = lane;
+    for (; d + 96 < D; d += 128) {
+      const float a = src[d], b = src[d + 32], c = src[d + 64], e = src[d + 96];
+      dst[d] = a; dst[d + 32] = b; dst[d + 64] = c; dst[d + 96] = e;
+    }
+    for (; d < D; d += 32) dst[d] = src[d];
+  }
 }
 
 // continue-straight test of nuts.py:119-135 on [D] vectors (warp reduction)
 __device__ __forceinline__ bool straight_w(const float *q_lo, const float *q_hi, const float *p_lo, const float *p_hi,
                                            int D, int lane) {
   float a = 0.f, b = 0.f;
+#pragma unroll 4
   for (int d = lane; d < D; d += 32) {
     const float dq = q_hi[d] - q_lo[d];
     a = fmaf(dq, p_lo[d], a);
@@ -367,8 +393,9 @@ __global__ void __launch_bounds__(32 * WPB) nuts_leaf_pre_kernel(b2m_nuts_args A
   if (!W.building[c]) return;
   const size_t o = (size_t)c * D;
   const float he = W.heps[c], fe = W.feps[c];
-  float *fq = W.fq + o, *fp = W.fp + o;
-  const float *fg = W.fg + o;
+  float *__restrict__ fq = W.fq + o, *__restrict__ fp = W.fp + o;
+  const float *__restrict__ fg = W.fg + o;
+#pragma unroll 4
   for (int d = lane; d < D; d += 32) {
     const float pv = __fadd_rn(fp[d], __fmul_rn(he, fg[d]));
     fp[d] = pv;
@@ -386,9 +413,10 @@ __global__ void __launch_bounds__(32 * WPB) nuts_leaf_post_kernel(b2m_nuts_args 
   const size_t o = (size_t)c * D;
   const int MD = A.max_tree_depth;
   const bool ref_compat = A.compat == B2M_COMPAT_REFERENCE;
-  float *fq = W.fq + o, *fp = W.fp + o;
-  const float *fg = W.fg + o;
+  float *__restrict__ fq = W.fq + o, *__restrict__ fp = W.fp + o;
+  const float *__restrict__ fg = W.fg + o;
   const float he = W.heps[c];
+#pragma unroll 4
   for (int d = lane; d < D; d += 32) fp[d] = __fadd_rn(fp[d], __fmul_rn(he, fg[d]));
   __syncwarp();
   const float kin = kinetic_w(fp, D, lane);
