@@ -57,8 +57,8 @@ WORKLOADS = {
 METRIC = "leapfrog_grad_evals_per_sec"
 UNIT = "grad-evals/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-NCU_TRAFFIC = {"c4": {"bytes": 6.21e9 + 6.59e9, "source": "profiles/r01_tc_gemm_c4_v2_ncu_summary.md (K5 2.94 GB read + 3.27 GB "
-                      "written, K6 6.47 GB read + 0.12 GB written)"}}
+NCU_TRAFFIC = {"c4": {"bytes": 2.11e9 + 3.34e9, "source": "profiles/r01_tc_gemm_c4_v3_f16_ncu_summary.md (K5 0.49 GB read + 1.61 GB "
+                      "written, K6 3.22 GB read + 0.12 GB written)"}}
 
 
 # ----------------------------------------------------------------------------------------- clocks
