@@ -92,7 +92,10 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): the arrival only says "this
+  // warp has drained its TMEM reads / issued its loads"; a cluster-scope release compiled to MEMBAR.ALL.GPU + ERRBAR
+  // and was 7 % of the K5 stall samples
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by one CTA of a pair; completion bytes are signalled on the LEADER's mbarrier (cluster address)
 __device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint32_t leader_bar, int x, int y) {
@@ -391,6 +394,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const float ivw = E.inv_var[m] * E.weight;
       // F16: the accumulators carry the row scale of the A operand (delta); R gets its own row scale before the split
       const float a_un = F16 ? E.a_unscale[m] : 1.0f;
+      const float rs_lane = F16 ? E.r_scale[m] : 1.0f;   // lane r holds the R scale of row r of this warp's 32 rows
       float *scratch = scratch_base + (warp - 2) * (32 * 33);
       const int64_t row0 = (int64_t)(m0 + q * 32);
       // the observations of this warp's columns: one coalesced load per 32-column block (lane = column), handed to
@@ -417,7 +421,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           __half *rh = static_cast<__half *>(E.Rh) + off, *rl = static_cast<__half *>(E.Rl) + off;
 #pragma unroll 8
           for (int r = 0; r < 32; ++r) {
-            const float v = scratch[r * 33 + lane] * __ldg(E.r_scale + row0 + r);
+            const float v = scratch[r * 33 + lane] * __shfl_sync(0xffffffffu, rs_lane, r);
             const __half hi = __float2half_rn(v);
             rh[(int64_t)r * E.Np] = hi;
             rl[(int64_t)r * E.Np] = __float2half_rn(v - __half2float(hi));
