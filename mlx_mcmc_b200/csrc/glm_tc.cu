@@ -405,28 +405,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int n = nb + b * 32 + lane;
         yv[b] = (n < E.N_valid) ? __ldg(E.y + n) - E.loc_const : 0.f;
       }
+      // (columns n >= N_valid need no test below: the padded rows of X are zero, so acc = 0 there, and yv = 0)
 #pragma unroll
       for (int b = 0; b < CW / 32; ++b) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int n = nb + b * 32 + j;
           const float yj = __shfl_sync(0xffffffffu, yv[b], j);
-          const float z = (n < E.N_valid) ? yj - (F16 ? acc[b * 32 + j] * a_un : acc[b * 32 + j]) : 0.f;
+          const float z = yj - (F16 ? acc[b * 32 + j] * a_un : acc[b * 32 + j]);
           ss = fmaf(z, z, ss);
           scratch[lane * 33 + j] = z * ivw;
         }
         __syncwarp();
-        const int64_t off = row0 * E.Np + nb + b * 32 + lane;
         if (F16) {
-          __half *rh = static_cast<__half *>(E.Rh) + off, *rl = static_cast<__half *>(E.Rl) + off;
+          // two rows per instruction: lanes 0-15 take row r, lanes 16-31 row r + 1, each lane two adjacent columns
+          // (bank = 33 row + 2 col': even banks for one half-warp, odd for the other -- conflict free) packed into
+          // one half2 store per array: half the conversions and half the store instructions of a per-element loop
+          const int hrow = lane >> 4, cl = (lane & 15) * 2;
+          const int64_t off = (row0 + hrow) * E.Np + nb + b * 32 + cl;
+          __half2 *rh = reinterpret_cast<__half2 *>(static_cast<__half *>(E.Rh) + off);
+          __half2 *rl = reinterpret_cast<__half2 *>(static_cast<__half *>(E.Rl) + off);
 #pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            const float v = scratch[r * 33 + lane] * __shfl_sync(0xffffffffu, rs_lane, r);
-            const __half hi = __float2half_rn(v);
-            rh[(int64_t)r * E.Np] = hi;
-            rl[(int64_t)r * E.Np] = __float2half_rn(v - __half2float(hi));
+          for (int r = 0; r < 32; r += 2) {
+            const float sc = __shfl_sync(0xffffffffu, rs_lane, r + hrow);
+            const float v0 = scratch[(r + hrow) * 33 + cl] * sc, v1 = scratch[(r + hrow) * 33 + cl + 1] * sc;
+            const __half2 hi = __floats2half2_rn(v0, v1);
+            const float2 hf = __half22float2(hi);
+            rh[(int64_t)r * (E.Np / 2)] = hi;
+            rl[(int64_t)r * (E.Np / 2)] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
           }
         } else {
+          const int64_t off = row0 * E.Np + nb + b * 32 + lane;
           float *rh = static_cast<float *>(E.Rh) + off, *rl = static_cast<float *>(E.Rl) + off;
 #pragma unroll 8
           for (int r = 0; r < 32; ++r) {
