@@ -307,19 +307,29 @@ __device__ __forceinline__ void vcopy(float *__restrict__ dst, const float *__re
     const float4 *__restrict__ s4 = reinterpret_cast<const float4 *>(src);
     float4 *__restrict__ d4 = reinterpret_cast<float4 *>(dst);
     const int n4 = D >> 2;
-    int i = lane;
-    for (; i + 96 < n4; i += 128) {
-      const float4 a = s4[i], b = s4[i + 32], c = s4[i + 64], e = s4[i + 96];
-      d4[i] = a; d4[i + 32] = b; d4[i + 64] = c; d4[i + 96] = e;
+    for (int i = lane; i < n4; i += 128) {   // up to four predicated 16-byte loads in flight per lane
+      const bool pb = i + 32 < n4, pc = i + 64 < n4, pe = i + 96 < n4;
+      float4 a = s4[i], b = a, c = a, e = a;
+      if (pb) b = s4[i + 32];
+      if (pc) c = s4[i + 64];
+      if (pe) e = s4[i + 96];
+      d4[i] = a;
+      if (pb) d4[i + 32] = b;
+      if (pc) d4[i + 64] = c;
+      if (pe) d4[i + 96] = e;
     }
-    for (; i < n4; i += 32) d4[i] = s4[i];
   } else {
-    int d = lane;
-    for (; d + 96 < D; d += 128) {
-      const float a = src[d], b = src[d + 32], c = src[d + 64], e = src[d + 96];
-      dst[d] = a; dst[d + 32] = b; dst[d + 64] = c; dst[d + 96] = e;
+    for (int d = lane; d < D; d += 128) {
+      const bool pb = d + 32 < D, pc = d + 64 < D, pe = d + 96 < D;
+      float a = src[d], b = 0.f, c = 0.f, e = 0.f;
+      if (pb) b = src[d + 32];
+      if (pc) c = src[d + 64];
+      if (pe) e = src[d + 96];
+      dst[d] = a;
+      if (pb) dst[d + 32] = b;
+      if (pc) dst[d + 64] = c;
+      if (pe) dst[d + 96] = e;
     }
-    for (; d < D; d += 32) dst[d] = src[d];
   }
 }
 
@@ -413,13 +423,32 @@ __global__ void __launch_bounds__(32 * WPB) nuts_leaf_post_kernel(b2m_nuts_args 
   const size_t o = (size_t)c * D;
   const int MD = A.max_tree_depth;
   const bool ref_compat = A.compat == B2M_COMPAT_REFERENCE;
-  float *__restrict__ fq = W.fq + o, *__restrict__ fp = W.fp + o;
-  const float *__restrict__ fg = W.fg + o;
+  float *fq = W.fq + o, *fp = W.fp + o;
+  const float *fg = W.fg + o;
   const float he = W.heps[c];
-#pragma unroll 4
-  for (int d = lane; d < D; d += 32) fp[d] = __fadd_rn(fp[d], __fmul_rn(he, fg[d]));
+  // one pass: second half kick, kinetic energy, and the four copies that make "the subtree being assembled = this
+  // leaf" (first edge = candidate = this state) -- three loads and five stores per element instead of six passes
+  float k0 = 0.f, k1 = 0.f;
+  {
+    float *__restrict__ sfq = W.sfq + o, *__restrict__ sfp = W.sfp + o, *__restrict__ scq = W.scq + o, *__restrict__ scg = W.scg + o;
+    int d = lane;
+    for (; d + 32 < D; d += 64) {
+      const float q0 = fq[d], q1 = fq[d + 32], g0 = fg[d], g1 = fg[d + 32];
+      const float p0 = __fadd_rn(fp[d], __fmul_rn(he, g0)), p1 = __fadd_rn(fp[d + 32], __fmul_rn(he, g1));
+      k0 = fmaf(p0, p0, k0); k1 = fmaf(p1, p1, k1);
+      fp[d] = p0; fp[d + 32] = p1;
+      sfq[d] = q0; sfq[d + 32] = q1; scq[d] = q0; scq[d + 32] = q1;
+      sfp[d] = p0; sfp[d + 32] = p1; scg[d] = g0; scg[d + 32] = g1;
+    }
+    for (; d < D; d += 32) {
+      const float q0 = fq[d], g0 = fg[d];
+      const float p0 = __fadd_rn(fp[d], __fmul_rn(he, g0));
+      k0 = fmaf(p0, p0, k0);
+      fp[d] = p0; sfq[d] = q0; scq[d] = q0; sfp[d] = p0; scg[d] = g0;
+    }
+  }
+  const float kin = 0.5f * warp_sum(k0 + k1);
   __syncwarp();
-  const float kin = kinetic_w(fp, D, lane);
   const float flp = W.flp[c], h0 = W.h0[c], log_slice = W.log_slice[c];
   const float h1 = -flp + kin;
   const int n1 = (log_slice <= -h1) ? 1 : 0;
@@ -432,10 +461,6 @@ __global__ void __launch_bounds__(32 * WPB) nuts_leaf_post_kernel(b2m_nuts_args 
     A.n_leaves[c] += 1;
     if (!s1) A.n_diverge[c] += 1;
   }
-  // the subtree being assembled = this leaf
-  vcopy(W.sfq + o, fq, D, lane); vcopy(W.sfp + o, fp, D, lane);
-  vcopy(W.scq + o, fq, D, lane); vcopy(W.scg + o, fg, D, lane);
-  __syncwarp();
   float sub_clp = flp;
   int sub_n = n1, sub_na = 1;
   bool sub_s = s1;
