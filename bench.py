@@ -203,7 +203,7 @@ def reference_arm(args, wl, config):
             "warmup": min(W_, 1), "ms_per_step": 1e3 * (time.perf_counter() - t0) / len(vals), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": per, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -591,7 +591,21 @@ def bench_pointwise(torch, dist, B, lib, args, wl, wl_name, rank, world, local_r
 
 
 # ----------------------------------------------------------------------------------------- main
+def emit(line: dict):
+    """the ONE JSON line, written to the process's original stdout"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    # Libraries (NCCL's version banner, for one) print to file descriptor 1; rank 0 must print exactly one JSON line
+    # there.  Keep a private copy of stdout for that line and point fd 1 at stderr for everything else.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -627,8 +641,6 @@ def main():
     import mlx_mcmc_b200 as B
     from mlx_mcmc_b200 import _cabi
 
-    # NCCL writes its version banner / debug lines to stdout by default; rank 0 must print exactly one JSON line there
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -663,7 +675,7 @@ def main():
         log("device part done; cpu baseline")
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.workload, (os.cpu_count() or 1) if wl["kind"] == "glm" else 1)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
