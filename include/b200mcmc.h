@@ -214,6 +214,16 @@ void b2m_comm_destroy(b2m_comm *c);
 int b2m_model_set_comm(b2m_model *m, b2m_comm *c, void *stream); /* collective (sums the shard row counts); c may be NULL */
 int b2m_comm_allreduce_f32(b2m_comm *c, float *buf, int64_t n, void *stream);   /* in place, sum */
 
+/* ---- forward sampling on the device ----
+ * n draws from one library distribution into out[n] (device).  Replaces Distribution.sample (distributions/*.py; the
+ * reference's Gamma / Beta fall back to numpy, gamma.py:107-117, beta.py:110-119).  dist = B2M_NORMAL (p0 loc, p1 scale),
+ * B2M_HALFNORMAL (p0 scale), B2M_EXPONENTIAL (p0 rate), B2M_GAMMA (p0 alpha, p1 rate), B2M_BETA (p0 a, p1 b) or
+ * B2M_SAMPLE_CATEGORICAL (cdf = device array of n_cat cumulative probabilities, last = 1; draws are indices as floats).
+ * Output i depends only on (seed, i). */
+#define B2M_SAMPLE_CATEGORICAL 6
+int b2m_sample(int32_t dist, float p0, float p1, const float *cdf, int32_t n_cat, uint64_t seed, int64_t n, float *out,
+               void *stream);
+
 /* ---- diagnostics on the device ----
  * draws is [S, C, D] as written by the samplers.
  * b2m_diag_series: per (chain, parameter) series -> mean [C, D], variance (ddof 0) [C, D], effective sample size by

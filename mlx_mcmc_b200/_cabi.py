@@ -65,7 +65,7 @@ ABI_VERSION = 1
 EXPORTS = ["b2m_last_error", "b2m_abi_version", "b2m_struct_sizes", "b2m_model_create", "b2m_model_destroy",
            "b2m_model_dim", "b2m_model_class", "b2m_model_glm_path", "b2m_logp_grad", "b2m_hmc_run", "b2m_mh_run", "b2m_nuts_run",
            "b2m_launch_count", "b2m_comm_unique_id", "b2m_comm_init", "b2m_comm_destroy", "b2m_model_set_comm",
-           "b2m_comm_allreduce_f32", "b2m_profile", "b2m_profile_read", "b2m_diag_series", "b2m_diag_params"]
+           "b2m_comm_allreduce_f32", "b2m_profile", "b2m_profile_read", "b2m_diag_series", "b2m_diag_params", "b2m_sample"]
 
 _lib = None
 
@@ -111,6 +111,7 @@ def load(build_if_missing: bool = True):
     lib.b2m_nuts_run.argtypes = [c_p, C.POINTER(NutsArgs), c_p]
     lib.b2m_diag_series.argtypes = [c_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, c_p, c_p, c_p, c_p, c_p]
     lib.b2m_diag_params.argtypes = [c_p, c_p, c_p, c_p, C.c_int64, C.c_int64, C.c_int64, c_p, c_p]
+    lib.b2m_sample.argtypes = [C.c_int32, c_f, c_f, c_p, C.c_int32, C.c_uint64, C.c_int64, c_p, c_p]
     lib.b2m_profile.argtypes = [C.c_int32]
     lib.b2m_profile_read.argtypes = [C.POINTER(C.c_double)]
     lib.b2m_comm_unique_id.argtypes = [c_p]

@@ -23,6 +23,7 @@ int glm_build(GlmModel &g, const float *X, const float *y, int N, int D);
 int debug_tc_gemm(const float *A, const float *Bm, int M, int N, int K, float *Cout, int chunk_kb, int mma_mask,
                   cudaStream_t st);
 
+int sample(int dist, float p0, float p1, const float *cdf, int n_cat, uint64_t seed, int64_t n, float *out, cudaStream_t st);
 int diag_series(const float *draws, int64_t S, int64_t C, int64_t D, int ess_mode, float *mean, float *var, float *ess_ref,
                 float *ess_geyer, cudaStream_t st);
 int diag_params(const float *mean, const float *var, const float *ess_ref, const float *ess_geyer, int64_t S, int64_t C,
@@ -140,6 +141,15 @@ int64_t b2m_launch_count(void) { return b2m::g_launches; }
 int b2m_debug_tc_gemm(const float *A, const float *Bm, int M, int N, int K, float *C, int chunk_kb, int mma_mask,
                       void *stream) {
   return b2m::debug_tc_gemm(A, Bm, M, N, K, C, chunk_kb, mma_mask, static_cast<cudaStream_t>(stream));
+}
+
+int b2m_sample(int32_t dist, float p0, float p1, const float *cdf, int32_t n_cat, uint64_t seed, int64_t n, float *out,
+               void *stream) {
+  B2M_REQUIRE(n >= 0 && (out || n == 0), "b2m_sample: bad output");
+  B2M_REQUIRE((dist >= B2M_NORMAL && dist <= B2M_BETA) || dist == B2M_SAMPLE_CATEGORICAL, "b2m_sample: unknown distribution tag");
+  B2M_REQUIRE(dist != B2M_SAMPLE_CATEGORICAL || (cdf && n_cat > 0), "b2m_sample: categorical needs a cdf");
+  if (dist == B2M_GAMMA || dist == B2M_BETA) B2M_REQUIRE(p0 > 0.f && p1 > 0.f, "b2m_sample: shape / rate parameters must be positive");
+  return b2m::sample(dist, p0, p1, cdf, n_cat, seed, n, out, static_cast<cudaStream_t>(stream));
 }
 
 int b2m_diag_series(const float *draws, int64_t S, int64_t C, int64_t D, int32_t ess_mode, float *mean, float *var,

@@ -28,6 +28,9 @@ class Beta(Distribution):
             inside = (self.alpha - 1) * np.log(x) + (self.beta - 1) * np.log(1 - x) - self._log_beta_const
         return np.where((x > 0) & (x < 1), inside, np.float32(-np.inf)).astype(np.float32)
 
+    def _device_sample_spec(self):
+        return BETA, float(self.alpha), float(self.beta), None
+
     def sample(self, key, shape=()):
         seed = int(mx.random.randint(0, 2 ** 31 - 1, key=key))   # numpy fallback as in beta.py:110-119
         rng = np.random.default_rng(seed)

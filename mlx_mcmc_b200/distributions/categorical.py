@@ -40,6 +40,9 @@ class Categorical(Distribution):
         ok = (k >= 0) & (k < self.num_categories)
         return np.where(ok, self.logits[np.where(ok, k, 0)], np.float32(-np.inf)).astype(np.float32)
 
+    def _device_sample_spec(self):
+        return 6, 0.0, 0.0, np.asarray(self.probs, dtype=np.float64)   # B2M_SAMPLE_CATEGORICAL
+
     def sample(self, key, shape=()):
         u = mx.random.uniform(shape=shape, key=key)
         return np.sum(np.expand_dims(u, -1) > np.cumsum(self.probs), axis=-1).astype(np.int32)

@@ -5,7 +5,7 @@ import numpy as np
 
 from .. import core as mx
 from ..tracer import EXPONENTIAL
-from .base import Distribution, context, f32, traced
+from .base import Distribution, context, f32, require_concrete, traced
 
 
 class Exponential(Distribution):
@@ -21,6 +21,10 @@ class Exponential(Distribution):
         with np.errstate(divide="ignore", invalid="ignore"):
             inside = np.log(self.rate) - self.rate * x
         return np.where(x >= 0, inside, np.float32(-np.inf)).astype(np.float32)
+
+    def _device_sample_spec(self):
+        require_concrete("Exponential rate", self.rate)
+        return EXPONENTIAL, float(self.rate), 0.0, None
 
     def sample(self, key, shape=()):
         u = mx.random.uniform(shape=shape, key=key)

@@ -27,6 +27,10 @@ class Gamma(Distribution):
             inside = (self.alpha * np.log(self.beta) - self._lgamma_alpha) + (self.alpha - 1) * np.log(x) - self.beta * x
         return np.where(x > 0, inside, np.float32(-np.inf)).astype(np.float32)
 
+    def _device_sample_spec(self):
+        require_concrete("Gamma beta", self.beta)
+        return GAMMA, float(self.alpha), float(self.beta), None
+
     def sample(self, key, shape=()):
         # the reference falls back to numpy's sampler seeded from the key (gamma.py:107-117)
         seed = int(mx.random.randint(0, 2 ** 31 - 1, key=key))

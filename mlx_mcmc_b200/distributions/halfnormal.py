@@ -5,7 +5,7 @@ import numpy as np
 
 from .. import core as mx
 from ..tracer import HALFNORMAL
-from .base import Distribution, context, f32, traced
+from .base import Distribution, context, f32, require_concrete, traced
 
 _HALF_LOG_2PI = np.float32(0.5) * np.log(np.float32(2.0 * np.pi), dtype=np.float32)
 _LOG2 = np.log(np.float32(2.0), dtype=np.float32)
@@ -25,6 +25,10 @@ class HalfNormal(Distribution):
         with np.errstate(divide="ignore", invalid="ignore"):
             inside = (_LOG2 - _HALF_LOG_2PI - np.log(self.scale)) - np.float32(0.5) * (x ** 2) / (self.scale ** 2)
         return np.where(x >= 0, inside, np.float32(-np.inf)).astype(np.float32)
+
+    def _device_sample_spec(self):
+        require_concrete("HalfNormal scale", self.scale)
+        return HALFNORMAL, float(self.scale), 0.0, None
 
     def sample(self, key, shape=()):
         return np.abs(mx.random.normal(shape, key=key) * self.scale)

@@ -5,7 +5,7 @@ import numpy as np
 
 from .. import core as mx
 from ..tracer import NORMAL
-from .base import Distribution, context, f32, traced
+from .base import Distribution, context, f32, require_concrete, traced
 
 _HALF_LOG_2PI = np.float32(0.5) * np.log(np.float32(2.0 * np.pi), dtype=np.float32)
 
@@ -24,6 +24,10 @@ class Normal(Distribution):
         x = f32(value)
         with np.errstate(divide="ignore", invalid="ignore"):
             return (-_HALF_LOG_2PI - np.log(self.scale)) - np.float32(0.5) * ((x - self.loc) ** 2) / (self.scale ** 2)
+
+    def _device_sample_spec(self):
+        require_concrete("Normal loc", self.loc), require_concrete("Normal scale", self.scale)
+        return NORMAL, float(self.loc), float(self.scale), None
 
     def sample(self, key, shape=()):
         return mx.random.normal(shape, key=key) * self.scale + self.loc

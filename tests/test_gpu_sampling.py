@@ -315,3 +315,47 @@ def test_device_diagnostics_match_the_oracle(cuda):
           adapt="dual_averaging")
     t = m.diagnostics()["rate"]
     assert abs(t["mean"] - meta.post_shape / meta.post_rate) < 0.05 and 0.99 < t["rhat"] < 1.05 and t["ess_geyer"] > 64 * 50, t
+
+
+def test_device_forward_sampling_moments_and_quantiles(cuda):
+    """SURVEY.md 8(f) row 4.  The reference's own sampling tests are 10k-draw moment checks (tests/test_distributions.py:40-50,
+    87-102; tests/test_new_distributions.py:46-59,107-120,162-175,235-256); here 400k device draws per distribution are held
+    to the exact moments and to the exact quantiles (scipy) much more tightly, plus reproducibility and support."""
+    from scipy import stats
+    n = 400_000
+    cases = [
+        (B.Normal(1.5, 2.0), stats.norm(1.5, 2.0)),
+        (B.HalfNormal(2.0), stats.halfnorm(scale=2.0)),
+        (B.Exponential(3.0), stats.expon(scale=1 / 3.0)),
+        (B.Gamma(2.0, 1.5), stats.gamma(2.0, scale=1 / 1.5)),
+        (B.Gamma(0.4, 2.0), stats.gamma(0.4, scale=1 / 2.0)),            # shape < 1: the boosted branch
+        (B.Gamma(50.0, 5.0), stats.gamma(50.0, scale=1 / 5.0)),
+        (B.Beta(2.0, 5.0), stats.beta(2.0, 5.0)),
+        (B.Beta(0.5, 0.5), stats.beta(0.5, 0.5)),
+        (B.Beta(116.0, 886.0), stats.beta(116.0, 886.0)),                 # the A/B example's posterior
+    ]
+    qs = np.array([0.01, 0.1, 0.25, 0.5, 0.75, 0.9, 0.99])
+    for dist, exact in cases:
+        x = dist.sample_device(mx.random.key(11), (n,))
+        assert x.is_cuda and x.dtype == torch.float32 and x.shape == (n,)
+        h = x.cpu().numpy().astype(np.float64)
+        assert np.isfinite(h).all() and h.min() >= exact.support()[0]
+        se = exact.std() / math.sqrt(n)
+        assert abs(h.mean() - exact.mean()) < 5 * se, (dist, h.mean(), exact.mean())
+        assert abs(h.var() - exact.var()) < 0.02 * exact.var() + 1e-9, (dist, h.var(), exact.var())
+        emp = np.quantile(h, qs)
+        # quantile standard error ~ sqrt(q(1-q)/n) / pdf
+        tol = 6 * np.sqrt(qs * (1 - qs) / n) / np.maximum(exact.pdf(exact.ppf(qs)), 1e-12)
+        assert np.all(np.abs(emp - exact.ppf(qs)) < tol + 1e-6), (dist, emp, exact.ppf(qs))
+        y = dist.sample_device(mx.random.key(11), (n,))
+        z = dist.sample_device(mx.random.key(12), (n,))
+        assert torch.equal(x, y) and not torch.equal(x, z)
+    c = B.Categorical(probs=[0.2, 0.5, 0.3])
+    k = c.sample_device(mx.random.key(5), (200, 1000))
+    assert k.dtype == torch.int64 and k.shape == (200, 1000) and int(k.min()) == 0 and int(k.max()) == 2
+    freq = torch.bincount(k.flatten(), minlength=3).double().cpu().numpy() / k.numel()
+    assert np.allclose(freq, [0.2, 0.5, 0.3], atol=0.005)
+    assert B.Normal(0, 1).sample_device(mx.random.key(1)).shape == ()
+    with pytest.raises(TypeError):                       # a traced parameter cannot be sampled from
+        from mlx_mcmc_b200.tracer import trace
+        trace(lambda p: B.Normal(p["m"], 1.0).sample_device(mx.random.key(0), (3,)), {"m": 0.0})
