@@ -545,10 +545,12 @@ int launch_tc_n(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap 
   using C = Cfg<BLOCK_N, NCTA>;
   auto kernel = tc_gemm_kernel<BLOCK_N, RESID, NCTA, F16>;
   constexpr int SMEM = C::SMEM_BYTES + (RESID ? NUM_EPI_WARPS * 32 * 33 * 4 : 0);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};   // per device: the attribute belongs to the function on the current device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     B2M_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   // `grid` arrives as (128-row tiles, column tiles, K splits); the launch is one persistent CTA group per SM (pair)
   const int Tm = (int)grid.x / NCTA, Tn = (int)grid.y, n_tiles = Tm * Tn * (int)grid.z;

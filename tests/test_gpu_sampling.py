@@ -359,3 +359,19 @@ def test_device_forward_sampling_moments_and_quantiles(cuda):
     with pytest.raises(TypeError):                       # a traced parameter cannot be sampled from
         from mlx_mcmc_b200.tracer import trace
         trace(lambda p: B.Normal(p["m"], 1.0).sample_device(mx.random.key(0), (3,)), {"m": 0.0})
+
+
+def test_summary_on_device_draws_matches_numpy(cuda):
+    """MCMC.summary() (mcmc.py:191-225) on device draws: same keys and numbers as numpy on the host copy."""
+    fn, init, meta = W.c1_normal(B.ns)
+    m = B.MCMC(fn)
+    m.run(init, num_samples=300, num_warmup=300, method="hmc", step_size=0.05, num_chains=50, return_torch=True,
+          verbose=False, adapt="dual_averaging")
+    dev = m.summary(0.9)
+    host = {k: v.cpu().numpy() for k, v in m.samples.items()}
+    for name, x in host.items():
+        want = {'mean': np.mean(x), 'std': np.std(x), 'median': np.median(x), '5.0%': np.percentile(x, 5.0),
+                '95.0%': np.percentile(x, 95.0)}
+        assert list(dev[name].keys()) == list(want.keys())
+        for k, v in want.items():
+            assert abs(dev[name][k] - v) <= 1e-4 * max(1.0, abs(v)), (name, k, dev[name][k], v)
