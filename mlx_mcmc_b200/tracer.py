@@ -472,6 +472,9 @@ class TraceContext:
         for o in (ox, o0, o1):      # a length-1 array argument was folded to a constant above
             if o.kind == OP_PARAMVEC and o.b != length:
                 raise UnsupportedOpError("vector parameter length does not match the other arguments")
+        if OP_MATVEC in (o0.kind, o1.kind) and ox.kind == OP_CONST:
+            # a single observation next to X @ beta: the contraction kernels read y from an observed array
+            ox = Operand(OP_DATA, a=self.add_array(np.full(length, ox.c, dtype=np.float32)))
         t = Term(dist, length, ox, o0, o1, tuple(float(v) for v in k), 1.0, shape)
         return LogProb(self, [Part([t], shape)])
 

@@ -313,3 +313,37 @@ def test_compact_and_general_pointwise_paths_agree_bit_for_bit(cuda, name, monke
     na, _ = B.nuts(fn, init, model=fast, **kw)
     nb, _ = B.nuts(fn, init, model=slow, **kw)
     assert all(np.array_equal(na[k], nb[k], equal_nan=True) for k in na)
+
+
+def test_edge_shapes_empty_single_and_one_by_one(cuda):
+    """Edge inputs: an empty observation array (the likelihood sums to 0), a single observation, a 1 x 1 regression
+    with one chain -- each against the oracle's float64 evaluation."""
+    import mlx_mcmc_b200 as B
+    from oracle.ns import ns as ons, value_and_grad
+
+    def make(ns, y):
+        def fn(p):
+            lik = ns.mx.sum(ns.Exponential(p["rate"]).log_prob(ns.mx.array(y))) if len(y) else 0.0
+            return ns.Gamma(2.0, 1.0).log_prob(p["rate"]) + lik
+        return fn
+    for y in (np.zeros(0, np.float32), np.array([0.7], np.float32), np.array([0.2, 1.1, 0.4], np.float32)):
+        model = compile_model(make(B.ns, y), {"rate": 1.3}, cache=False)
+        lp, g = model.logp_grad(model.pack({"rate": 1.3}, 3))
+        lp64, g64 = value_and_grad(make(ons, y), {"rate": 1.3}, "float64")
+        assert abs(float(lp[0]) - lp64) <= 1e-5 * max(1.0, abs(lp64)) and abs(float(g[0, 0]) - g64["rate"]) <= 1e-5 * max(1.0, abs(g64["rate"]))
+        assert torch.equal(lp, lp[0].expand_as(lp))
+    # 1 x 1 regression, one chain (everything is padding except one element)
+    X = np.array([[2.0]], np.float32)
+    yv = np.array([3.0], np.float32)
+
+    def reg(ns):
+        Xa, ya = ns.mx.array(X), ns.mx.array(yv)
+        return lambda p: ns.mx.sum(ns.Normal(0, 10.0).log_prob(p["beta"])) + ns.mx.sum(ns.Normal(Xa @ p["beta"], 1.0).log_prob(ya))
+    init = {"beta": np.array([0.4], np.float32)}
+    gm = compile_model(reg(B.ns), init, cache=False)
+    assert gm.model_class == 1
+    lp, g = gm.logp_grad(gm.pack(init, 1))
+    lp64, g64 = value_and_grad(reg(ons), init, "float64")
+    assert abs(float(lp[0]) - lp64) <= 1e-5 * abs(lp64) and abs(float(g[0, 0]) - g64["beta"][0]) <= 1e-5 * abs(g64["beta"][0])
+    s, _ = B.nuts(reg(B.ns), init, num_samples=50, num_warmup=50, num_chains=1, compat="correct", model=gm)
+    assert s["beta"].shape == (50, 1) and np.isfinite(s["beta"]).all()

@@ -375,3 +375,26 @@ def test_summary_on_device_draws_matches_numpy(cuda):
         assert list(dev[name].keys()) == list(want.keys())
         for k, v in want.items():
             assert abs(dev[name][k] - v) <= 1e-4 * max(1.0, abs(v)), (name, k, dev[name][k], v)
+
+
+def test_c3_size_nuts_matches_closed_form_posterior(cuda):
+    """parity check 3 at the README 'Medium' size (100 coefficients x 10,000 observations, 1024 lock-step chains):
+    posterior means and variances of every coefficient against the closed-form N(m, V) within 4 MC standard errors."""
+    fn, init, meta = W.regression(B.ns, 10000, 100, seed=0)
+    m, V = W.regression_posterior(meta)
+    s, rate, info = B.nuts(fn, init, num_samples=120, num_warmup=150, step_size=0.005, max_tree_depth=8, num_chains=1024,
+                           compat="correct", step_size_adaptation="pooled", return_info=True, return_torch=True,
+                           key=mx.random.key(12))
+    x = s["beta"].double()                                   # (C, S, D)
+    C, S, D = x.shape
+    sd = np.sqrt(np.diag(V))
+    # chains are independent: the standard error of the grand mean comes from the spread of the chain means
+    cm = x.mean(dim=1)                                       # (C, D)
+    grand = cm.mean(dim=0).cpu().numpy()
+    se = (cm.std(dim=0) / math.sqrt(C)).cpu().numpy()
+    assert np.max(np.abs(grand - m) / se) < 4.5, np.max(np.abs(grand - m) / se)
+    var_c = x.var(dim=1, unbiased=True)                      # per-chain variances, (C, D)
+    v_hat = var_c.mean(dim=0).cpu().numpy() + cm.var(dim=0).cpu().numpy()
+    v_se = (var_c.std(dim=0) / math.sqrt(C)).cpu().numpy() + 1e-12
+    assert np.max(np.abs(v_hat - sd ** 2) / (4.5 * v_se + 0.02 * sd ** 2)) < 1.0
+    assert np.all(info.step_size == info.step_size[0]) and info.grad_evals > 0
