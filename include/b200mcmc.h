@@ -150,7 +150,10 @@ typedef struct {
   int32_t compat;         /* B2M_COMPAT_REFERENCE: float32 slice underflow + NaN => alpha 1 (nuts.py:236-237,173)
                              B2M_COMPAT_CORRECT:   log-space slice, NaN => divergent, alpha 0 */
   int32_t lanes;
-  int32_t _pad;
+  float step_size_jitter; /* 0 = off (the reference).  > 0: every chain and iteration integrates with eps (1 + jitter (2u - 1)),
+                             u from the spare word of Philox slot 0; adaptation keeps tracking the un-jittered eps.  Breaks the
+                             resonance of the position-based U-turn test when a power of two steps is close to a whole
+                             number of oscillation periods. */
   double target_accept;
   uint64_t seed;
   float *theta;        /* [n_chains, D] in/out */

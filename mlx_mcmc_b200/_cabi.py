@@ -50,7 +50,7 @@ class MhArgs(C.Structure):
 class NutsArgs(C.Structure):
     _fields_ = [("n_chains", C.c_int64), ("chain_offset", C.c_int64), ("iter_offset", C.c_int64),
                 ("n_iter", C.c_int32), ("max_tree_depth", C.c_int32), ("adapt", C.c_int32), ("compat", C.c_int32),
-                ("lanes", C.c_int32), ("_pad", C.c_int32), ("target_accept", C.c_double), ("seed", C.c_uint64),
+                ("lanes", C.c_int32), ("step_size_jitter", c_f), ("target_accept", C.c_double), ("seed", C.c_uint64),
                 ("theta", c_p), ("step_size", c_p), ("da_state", c_p), ("n_accept", c_p), ("n_leaves", c_p),
                 ("n_diverge", c_p), ("draws", c_p), ("depths", c_p), ("alphas", c_p),
                 ("inj_normal", c_p), ("inj_slice", c_p), ("inj_dir", c_p), ("inj_take", c_p), ("inj_merge", c_p),

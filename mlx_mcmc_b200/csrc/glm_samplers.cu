@@ -297,6 +297,7 @@ struct NutsBufs {
   int *n_active;    // device: number of chains building in the current doubling
   int *active;      // [C] ordered list of those chains (the compacted lock-step batch)
   float *alpha_it;  // [C] this iteration's mean acceptance statistic (pooled adaptation)
+  double *eps_it;   // [C] step size of this iteration (= step_size, or its jittered value)
 };
 
 // One warp copies a [D] vector.  These kernels are pure HBM streaming with one warp per chain: with a scalar loop each
@@ -371,6 +372,8 @@ __global__ void __launch_bounds__(32 * WPB) nuts_begin_kernel(b2m_nuts_args A, N
     W.log_slice[c] = A.compat == B2M_COMPAT_REFERENCE ? logf(expf((float)log_u64)) : (float)log_u64;
     W.clp[c] = W.lp[c];
     W.n[c] = 1; W.s[c] = 1; W.alpha_sum[c] = 0.0; W.alpha_cnt[c] = 0; W.depth[c] = 0; W.building[c] = 0;
+    const double eps = A.step_size[c];
+    W.eps_it[c] = A.step_size_jitter > 0.f ? eps * (1.0 + (double)A.step_size_jitter * (2.0 * (double)u01(w0.w) - 1.0)) : eps;
     if (A.trace_energy) A.trace_energy[row] = h0;
   }
 }
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(32 * WPB) nuts_doubling_begin_kernel(b2m_nuts_
   if (v == 1) { vcopy(W.fq + o, W.q_hi + o, D, lane); vcopy(W.fp + o, W.p_hi + o, D, lane); vcopy(W.fg + o, W.g_hi + o, D, lane); }
   else        { vcopy(W.fq + o, W.q_lo + o, D, lane); vcopy(W.fp + o, W.p_lo + o, D, lane); vcopy(W.fg + o, W.g_lo + o, D, lane); }
   if (lane == 0) {
-    const double eps = A.step_size[c];
+    const double eps = W.eps_it[c];
     W.v[c] = v;
     W.feps[c] = (float)((double)v * eps);
     W.heps[c] = (float)(0.5 * ((double)v * eps));
@@ -677,6 +680,7 @@ int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     A.take(&W.n_active, 1);
     A.take(&W.active, C);
     A.take(&W.alpha_it, C);
+    A.take(&W.eps_it, C);
   };
   Arena probe;
   layout(probe);

@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(64) nuts_kernel(const __grid_constant__ KModel
     float p0[DMAX];
     draw_normals<DMAX>(p0, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0);
     const float h0 = __fadd_rn(-lp, kinetic<DMAX>(p0, D));
+    // step size of this iteration: jittered when asked for (extension), else exactly eps
+    const double eps_it = A.step_size_jitter > 0.f ? eps * (1.0 + (double)A.step_size_jitter * (2.0 * (double)u01(w0.w) - 1.0)) : eps;
     const float us = A.inj_slice ? A.inj_slice[row] : u01(w0.z);
     const double log_u64 = (double)(-h0) + (double)logf(us);
     // reference: u = exp(float32(log_u)); later float(log(u))
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(64) nuts_kernel(const __grid_constant__ KModel
       if (!A.inj_dir || !A.inj_take) wj = Philox::draw(A.seed, gchain, giter, SLOT_NUTS_DOUBLING + j);
       const float ud = A.inj_dir ? A.inj_dir[row * MD + j] : u01(wj.x);
       const int v = ud < 0.5f ? 1 : -1;
-      const float feps = (float)((double)v * eps), half_eps = (float)(0.5 * ((double)v * eps));
+      const float feps = (float)((double)v * eps_it), half_eps = (float)(0.5 * ((double)v * eps_it));
 
       // frontier = the edge we extend from
       float fq[DMAX], fp[DMAX], fg[DMAX];

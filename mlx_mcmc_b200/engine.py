@@ -181,13 +181,14 @@ def launch_mh(st: ChainState, n_iter: int, proposal_scale: float, seed: int, ite
 
 def launch_nuts(st: ChainState, n_iter: int, max_tree_depth: int, adapt: int, compat: int, target_accept: float,
                 seed: int, iter_offset: int, draws=None, depths=None, alphas=None, lanes: int = 0, inj=None,
-                trace_doubling=None, trace_energy=None):
+                trace_doubling=None, trace_energy=None, step_size_jitter: float = 0.0):
     m = st.model
     inj = inj or {}
     a = _cabi.NutsArgs()
     a.n_chains, a.chain_offset, a.iter_offset = st.n_chains, st.chain_offset, iter_offset
     a.n_iter, a.max_tree_depth, a.adapt, a.compat, a.lanes = n_iter, max_tree_depth, adapt, compat, lanes
     a.target_accept, a.seed = target_accept, seed & 0xFFFFFFFFFFFFFFFF
+    a.step_size_jitter = float(step_size_jitter)
     a.theta, a.step_size, a.da_state = _ptr(st.theta), _ptr(st.step_size), _ptr(st.da_state)
     a.n_accept, a.n_leaves, a.n_diverge = _ptr(st.n_accept), _ptr(st.n_leaves), _ptr(st.n_diverge)
     a.draws, a.depths, a.alphas = _ptr(draws), _ptr(depths), _ptr(alphas)

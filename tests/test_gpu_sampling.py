@@ -398,3 +398,18 @@ def test_c3_size_nuts_matches_closed_form_posterior(cuda):
     v_se = (var_c.std(dim=0) / math.sqrt(C)).cpu().numpy() + 1e-12
     assert np.max(np.abs(v_hat - sd ** 2) / (4.5 * v_se + 0.02 * sd ** 2)) < 1.0
     assert np.all(info.step_size == info.step_size[0]) and info.grad_evals > 0
+
+
+def test_step_size_jitter_keeps_the_posterior_and_is_off_by_default(cuda):
+    """step_size_jitter (extension): 0 reproduces the un-jittered run bit for bit (pointwise class), a positive value
+    changes the trajectories but not the target."""
+    fn, init, meta = W.c2_event_rate(B.ns)
+    kw = dict(num_samples=200, num_warmup=200, num_chains=256, compat="correct", key=mx.random.key(2))
+    a, _ = B.nuts(fn, init, **kw)
+    b, _ = B.nuts(fn, init, step_size_jitter=0.0, **kw)
+    c, _ = B.nuts(fn, init, step_size_jitter=0.3, **kw)
+    assert np.array_equal(a["rate"], b["rate"]) and not np.array_equal(a["rate"], c["rate"])
+    mean, sd = meta.post_shape / meta.post_rate, math.sqrt(meta.post_shape) / meta.post_rate
+    assert mcse_ok(c["rate"], mean, sd)
+    with pytest.raises(ValueError):
+        B.nuts(fn, init, step_size_jitter=1.5, num_chains=2)
