@@ -5,6 +5,9 @@
 // Replaces the same reference code as the pointwise kernels: kernels/hmc.py:113-198, kernels/nuts.py:137-343,
 // kernels/metropolis.py:64-92.  The NUTS tree is the iterative restatement of build_tree: one
 // leaf per lock-step, per-chain masks for chains whose subtree / trajectory has ended.
+#include <stdlib.h>
+
+#include <string>
 #include <vector>
 
 #include "glm.cuh"
@@ -298,6 +301,13 @@ struct NutsBufs {
   int *active;      // [C] ordered list of those chains (the compacted lock-step batch)
   float *alpha_it;  // [C] this iteration's mean acceptance statistic (pooled adaptation)
   double *eps_it;   // [C] step size of this iteration (= step_size, or its jittered value)
+  // iteration-asynchronous schedule (glm_nuts_run_async)
+  int *state;       // [C] 0 = not started, 1 = a leaf is being evaluated, 2 = all iterations done
+  int *iter;        // [C] the chain's own iteration counter
+  int *fin;         // [C] finished an iteration in the current tick (pooled adaptation)
+  int *live;        // [C] state != 2 (input of the compaction)
+  int *n_done;      // device counter of finished chains
+  double *pool;     // [4] pooled adaptation: sum of alpha, count, update index, spare
 };
 
 // One warp copies a [D] vector.  These kernels are pure HBM streaming with one warp per chain: with a scalar loop each
@@ -349,8 +359,7 @@ __device__ __forceinline__ bool straight_w(const float *q_lo, const float *q_hi,
   return a >= 0.f && b >= 0.f;
 }
 
-__global__ void __launch_bounds__(32 * WPB) nuts_begin_kernel(b2m_nuts_args A, NutsBufs W, int D, int it) {
-  CHAIN_PROLOGUE(A.n_chains)
+__device__ __forceinline__ void nuts_begin_dev(const b2m_nuts_args &A, const NutsBufs &W, int D, int64_t c, int lane, int it) {
   const uint64_t gchain = (uint64_t)(A.chain_offset + c);
   const uint32_t giter = (uint32_t)(A.iter_offset + it);
   const size_t row = (size_t)it * A.n_chains + c;
@@ -378,8 +387,12 @@ __global__ void __launch_bounds__(32 * WPB) nuts_begin_kernel(b2m_nuts_args A, N
   }
 }
 
-__global__ void __launch_bounds__(32 * WPB) nuts_doubling_begin_kernel(b2m_nuts_args A, NutsBufs W, int D, int it, int j) {
+__global__ void __launch_bounds__(32 * WPB) nuts_begin_kernel(b2m_nuts_args A, NutsBufs W, int D, int it) {
   CHAIN_PROLOGUE(A.n_chains)
+  nuts_begin_dev(A, W, D, c, lane, it);
+}
+
+__device__ __forceinline__ void nuts_doubling_begin_dev(const b2m_nuts_args &A, const NutsBufs &W, int D, int64_t c, int lane, int it, int j) {
   if (!W.s[c]) { if (lane == 0) W.building[c] = 0; return; }
   const uint64_t gchain = (uint64_t)(A.chain_offset + c);
   const uint32_t giter = (uint32_t)(A.iter_offset + it);
@@ -401,8 +414,12 @@ __global__ void __launch_bounds__(32 * WPB) nuts_doubling_begin_kernel(b2m_nuts_
   }
 }
 
-__global__ void __launch_bounds__(32 * WPB) nuts_leaf_pre_kernel(b2m_nuts_args A, NutsBufs W, int D) {
+__global__ void __launch_bounds__(32 * WPB) nuts_doubling_begin_kernel(b2m_nuts_args A, NutsBufs W, int D, int it, int j) {
   CHAIN_PROLOGUE(A.n_chains)
+  nuts_doubling_begin_dev(A, W, D, c, lane, it, j);
+}
+
+__device__ __forceinline__ void nuts_leaf_pre_dev(const b2m_nuts_args &A, const NutsBufs &W, int D, int64_t c, int lane) {
   if (!W.building[c]) return;
   const size_t o = (size_t)c * D;
   const float he = W.heps[c], fe = W.feps[c];
@@ -416,8 +433,12 @@ __global__ void __launch_bounds__(32 * WPB) nuts_leaf_pre_kernel(b2m_nuts_args A
   }
 }
 
-__global__ void __launch_bounds__(32 * WPB) nuts_leaf_post_kernel(b2m_nuts_args A, NutsBufs W, int D, int it, int j) {
+__global__ void __launch_bounds__(32 * WPB) nuts_leaf_pre_kernel(b2m_nuts_args A, NutsBufs W, int D) {
   CHAIN_PROLOGUE(A.n_chains)
+  nuts_leaf_pre_dev(A, W, D, c, lane);
+}
+
+__device__ __forceinline__ void nuts_leaf_post_dev(const b2m_nuts_args &A, const NutsBufs &W, int D, int64_t c, int lane, int it, int j) {
   if (!W.building[c]) return;
   const int64_t C = A.n_chains;
   const uint64_t gchain = (uint64_t)(A.chain_offset + c);
@@ -519,8 +540,12 @@ __global__ void __launch_bounds__(32 * WPB) nuts_leaf_post_kernel(b2m_nuts_args 
   }
 }
 
-__global__ void __launch_bounds__(32 * WPB) nuts_doubling_end_kernel(b2m_nuts_args A, NutsBufs W, int D, int it, int j) {
+__global__ void __launch_bounds__(32 * WPB) nuts_leaf_post_kernel(b2m_nuts_args A, NutsBufs W, int D, int it, int j) {
   CHAIN_PROLOGUE(A.n_chains)
+  nuts_leaf_post_dev(A, W, D, c, lane, it, j);
+}
+
+__device__ __forceinline__ void nuts_doubling_end_dev(const b2m_nuts_args &A, const NutsBufs &W, int D, int64_t c, int lane, int it, int j) {
   if (!W.s[c]) return;  // chain was not growing in this doubling
   const uint64_t gchain = (uint64_t)(A.chain_offset + c);
   const uint32_t giter = (uint32_t)(A.iter_offset + it);
@@ -559,8 +584,12 @@ __global__ void __launch_bounds__(32 * WPB) nuts_doubling_end_kernel(b2m_nuts_ar
   }
 }
 
-__global__ void __launch_bounds__(32 * WPB) nuts_end_kernel(b2m_nuts_args A, NutsBufs W, int D, int it) {
+__global__ void __launch_bounds__(32 * WPB) nuts_doubling_end_kernel(b2m_nuts_args A, NutsBufs W, int D, int it, int j) {
   CHAIN_PROLOGUE(A.n_chains)
+  nuts_doubling_end_dev(A, W, D, c, lane, it, j);
+}
+
+__device__ __forceinline__ void nuts_end_dev(const b2m_nuts_args &A, const NutsBufs &W, int D, int64_t c, int lane, int it) {
   const uint32_t giter = (uint32_t)(A.iter_offset + it);
   const size_t row = (size_t)it * A.n_chains + c;
   const size_t o = (size_t)c * D;
@@ -589,6 +618,11 @@ __global__ void __launch_bounds__(32 * WPB) nuts_end_kernel(b2m_nuts_args A, Nut
     if (A.depths) A.depths[row] = W.depth[c];
     if (A.alphas) A.alphas[row] = (float)mean_alpha;
   }
+}
+
+__global__ void __launch_bounds__(32 * WPB) nuts_end_kernel(b2m_nuts_args A, NutsBufs W, int D, int it) {
+  CHAIN_PROLOGUE(A.n_chains)
+  nuts_end_dev(A, W, D, c, lane, it);
 }
 
 // Ordered compaction of the chains still building in this doubling: active[0..n) = their ids, ascending.
@@ -659,7 +693,114 @@ __global__ void __launch_bounds__(1024) nuts_pool_adapt_kernel(b2m_nuts_args A, 
   }
 }
 
-int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
+// ================================================================= NUTS, iteration-asynchronous lock-step
+// The synchronous schedule above advances all chains through the same iteration: a chain whose tree stops at depth 4
+// waits for the one that runs to depth 10 (with thousands of chains some always do -- DESIGN.md 4.2), and the host
+// synchronises once per doubling.  Here every chain is a small state machine advanced once per *tick*: consume the
+// leaf that was just evaluated (tree bookkeeping; possibly close the doubling, the iteration, start the next
+// iteration and its first doubling) and put the next leaf position into `fq`.  One tick = this kernel + ONE full-batch
+// value+gradient; every chain has a leaf in every tick, a finished transition is followed immediately by the chain's
+// next one, and the host only looks at a counter every few ticks.  Per chain the algorithm, the Philox slots and the
+// arithmetic are those of the synchronous kernels (the same device functions), so a chain's draws are the same up to
+// the batch-dependent rounding of the GLM contractions.
+__global__ void __launch_bounds__(32 * WPB) nuts_tick_kernel(b2m_nuts_args A, NutsBufs W, int D) {
+  CHAIN_PROLOGUE(A.n_chains)
+  const int st = W.state[c];
+  if (st == 2) return;
+  int it = W.iter[c];
+  if (st == 0) {
+    nuts_begin_dev(A, W, D, c, lane, it);
+    __syncwarp();
+    nuts_doubling_begin_dev(A, W, D, c, lane, it, 0);
+    __syncwarp();
+    if (lane == 0) W.state[c] = 1;
+  } else {
+    const int j = W.depth[c];
+    nuts_leaf_post_dev(A, W, D, c, lane, it, j);
+    __syncwarp();
+    if (!W.building[c]) {                                  // the subtree of doubling j is complete
+      nuts_doubling_end_dev(A, W, D, c, lane, it, j);
+      __syncwarp();
+      if (W.s[c] && W.depth[c] < A.max_tree_depth) {
+        nuts_doubling_begin_dev(A, W, D, c, lane, it, W.depth[c]);
+      } else {                                             // the transition is over
+        nuts_end_dev(A, W, D, c, lane, it);
+        __syncwarp();
+        ++it;
+        if (lane == 0) { W.iter[c] = it; W.fin[c] = 1; }
+        if (it >= A.n_iter) {
+          if (lane == 0) { W.state[c] = 2; W.live[c] = 0; atomicAdd(W.n_done, 1); }
+          return;
+        }
+        nuts_begin_dev(A, W, D, c, lane, it);
+        __syncwarp();
+        nuts_doubling_begin_dev(A, W, D, c, lane, it, 0);
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  nuts_leaf_pre_dev(A, W, D, c, lane);
+}
+
+// Pooled dual averaging under the asynchronous schedule: acceptance statistics of the transitions that finished in
+// this tick are added (fixed order) to a pool; every n_chains completed transitions -- one per chain on average -- the
+// recurrences of nuts.py:298-310 advance once on the pool's mean and every chain gets the new step size for its next
+// transition.  `flush` applies what is left at the end of the call.
+__global__ void __launch_bounds__(1024) nuts_pool_async_kernel(b2m_nuts_args A, NutsBufs W, int flush) {
+  __shared__ double rs[1024];
+  __shared__ int rc[1024];
+  __shared__ double eps_sh, hbar_sh, ebar_sh;
+  __shared__ int updated;
+  const int64_t C = A.n_chains;
+  double s = 0.0;
+  int n = 0;
+  for (int64_t c = threadIdx.x; c < C; c += 1024)
+    if (W.fin[c]) {
+      const float a = W.alpha_it[c];
+      s += (a == a) ? (double)a : 0.0;
+      ++n;
+      W.fin[c] = 0;
+    }
+  rs[threadIdx.x] = s;
+  rc[threadIdx.x] = n;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { rs[threadIdx.x] += rs[threadIdx.x + o]; rc[threadIdx.x] += rc[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    updated = 0;
+    double sum = W.pool[0] + rs[0], cnt = W.pool[1] + (double)rc[0];
+    if (cnt >= (double)C || (flush && cnt > 0.0)) {
+      const double mean_alpha = sum / cnt;
+      double h_bar = A.da_state[0], eps_bar = A.da_state[1];
+      const float mu = (float)A.da_state[2];
+      const double m = (double)(uint32_t)A.iter_offset + W.pool[2], eta = 1.0 / (m + 10.0);
+      h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - mean_alpha);
+      float log_eps = __fsub_rn(mu, (float)((sqrt(m + 1.0) / 0.05) * h_bar));
+      log_eps = fmaxf(fminf(log_eps, 10.0f), -10.0f);
+      const double eps = (double)expf(log_eps);
+      const double wgt = pow(m + 1.0, -0.75);
+      eps_bar = (double)expf((float)(wgt * log(eps) + (1.0 - wgt) * log(eps_bar)));
+      eps_sh = eps; hbar_sh = h_bar; ebar_sh = eps_bar;
+      W.pool[2] += 1.0;
+      sum = 0.0; cnt = 0.0;
+      updated = 1;
+    }
+    W.pool[0] = sum;
+    W.pool[1] = cnt;
+  }
+  __syncthreads();
+  if (updated)
+    for (int64_t c = threadIdx.x; c < C; c += 1024) {
+      A.step_size[c] = eps_sh;
+      A.da_state[c * 3 + 0] = hbar_sh;
+      A.da_state[c * 3 + 1] = ebar_sh;
+    }
+}
+
+int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   const int64_t C = a.n_chains;
   const int D = gm.Dtot, MD = a.max_tree_depth;
   NutsBufs W{};
@@ -681,6 +822,93 @@ int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     A.take(&W.active, C);
     A.take(&W.alpha_it, C);
     A.take(&W.eps_it, C);
+    A.take(&W.state, C); A.take(&W.iter, C); A.take(&W.fin, C); A.take(&W.live, C);
+    A.take(&W.n_done, 1);
+    A.take(&W.pool, 4);
+  };
+  Arena probe;
+  layout(probe);
+  if (int rc0 = arena_reserve(gm, probe.off)) return rc0;
+  Arena real;
+  real.base = gm.ws;
+  layout(real);
+  int *h_flag = gm.h_flag;
+
+  const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
+  const int T = 32 * WPB;
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.state, 0, sizeof(int) * C, st));
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.iter, 0, sizeof(int) * C, st));
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.fin, 0, sizeof(int) * C, st));
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.live, 1, sizeof(int) * C, st));   // any non-zero pattern = live
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.n_done, 0, sizeof(int), st));
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.pool, 0, sizeof(double) * 4, st));
+  int rc = glm_logp_grad(gm, a.theta, C, W.lp, W.g, st, true);
+
+  constexpr int kCheck = 8;                 // ticks between looks at the finished-chain counter / recentring
+  const bool pooled = a.adapt == B2M_ADAPT_POOLED;
+  // worst case: every transition of the slowest chain runs to the depth cap
+  const int64_t max_ticks = (int64_t)a.n_iter * ((int64_t(1) << MD) + 1) + 2 * kCheck;
+  int64_t n_live = C;
+  const int *idx = nullptr;
+  for (int64_t tick = 0; !rc; ++tick) {
+    if (tick > max_ticks) { set_error("NUTS asynchronous schedule: tick budget exceeded"); rc = 2; break; }
+    nuts_tick_kernel<<<grid, T, 0, st>>>(a, W, D);
+    ++g_launches;
+    if (pooled) {
+      nuts_pool_async_kernel<<<1, 1024, 0, st>>>(a, W, 0);
+      ++g_launches;
+    }
+    if (tick % kCheck == kCheck - 1) {
+      cudaMemcpyAsync(h_flag, W.n_done, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) { rc = 2; set_error("NUTS asynchronous schedule: stream error"); break; }
+      const int n_done = *h_flag;
+      if (n_done >= C) break;
+      if ((rc = glm_recenter(gm, a.theta, C, st))) break;      // reference point follows the current states
+      if (n_done > 0) {                                        // the tail: evaluate only the chains still running
+        nuts_compact_kernel<<<1, 1024, 0, st>>>(W.live, C, W.active, W.n_active);
+        ++g_launches;
+        n_live = C - n_done;
+        idx = W.active;
+      }
+    }
+    rc = glm_logp_grad(gm, W.fq, C, W.flp, W.fg, st, false, idx, n_live);
+  }
+  if (!rc && pooled) {
+    nuts_pool_async_kernel<<<1, 1024, 0, st>>>(a, W, 1);
+    ++g_launches;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc) return rc;
+  B2M_CHECK_CUDA(e);
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int glm_nuts_run_sync(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
+  const int64_t C = a.n_chains;
+  const int D = gm.Dtot, MD = a.max_tree_depth;
+  NutsBufs W{};
+  const size_t cd = (size_t)C * D;
+  auto layout = [&](Arena &A) {
+    float **vecs[] = {&W.g, &W.p0, &W.q_lo, &W.p_lo, &W.g_lo, &W.q_hi, &W.p_hi, &W.g_hi, &W.cq, &W.cg,
+                      &W.fq, &W.fp, &W.fg, &W.sfq, &W.sfp, &W.scq, &W.scg};
+    for (auto v : vecs) A.take(v, cd);
+    float **stk[] = {&W.st_fq, &W.st_fp, &W.st_cq, &W.st_cg};
+    for (auto v : stk) A.take(v, cd * MD);
+    float **fs[] = {&W.lp, &W.clp, &W.h0, &W.log_slice, &W.flp, &W.sclp, &W.feps, &W.heps};
+    for (auto v : fs) A.take(v, C);
+    int **is[] = {&W.n, &W.s, &W.v, &W.leaf, &W.building, &W.sub_n, &W.sub_na, &W.sub_s, &W.alpha_cnt, &W.depth};
+    for (auto v : is) A.take(v, C);
+    A.take(&W.alpha_sum, C); A.take(&W.sub_alpha, C);
+    A.take(&W.st_clp, (size_t)C * MD); A.take(&W.st_n, (size_t)C * MD); A.take(&W.st_na, (size_t)C * MD);
+    A.take(&W.st_alpha, (size_t)C * MD);
+    A.take(&W.n_active, 1);
+    A.take(&W.active, C);
+    A.take(&W.alpha_it, C);
+    A.take(&W.eps_it, C);
+    A.take(&W.state, C); A.take(&W.iter, C); A.take(&W.fin, C); A.take(&W.live, C);
+    A.take(&W.n_done, 1);
+    A.take(&W.pool, 4);
   };
   Arena probe;
   layout(probe);
@@ -730,6 +958,13 @@ int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   B2M_CHECK_CUDA(e);
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// B2M_NUTS_SCHED = async (default) | sync
+int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
+  const char *v = getenv("B2M_NUTS_SCHED");
+  if (v && std::string(v) == "sync") return glm_nuts_run_sync(gm, a, st);
+  return glm_nuts_run_async(gm, a, st);
 }
 
 }  // namespace b2m
