@@ -625,9 +625,9 @@ def main():
               "sharding": "chains (no data-path collective; weak scaling: per-GPU chains fixed)",
               "l2": "flushed between timed steps (256 MiB write)"}
     if wl["kind"] == "glm":
-        config.update({"n_obs": wl["n"], "n_params": wl["d"], "sampler": "NUTS (iterative lock-step tree, compat=correct, "
+        config.update({"n_obs": wl["n"], "n_params": wl["d"], "sampler": "NUTS (iterative tree, iteration-asynchronous lock-step schedule, compat=correct, "
                        f"max_tree_depth={wl['max_tree_depth']}, step size from pooled dual averaging over the rank's chains, "
-                       "identity mass matrix; finished chains are compacted out of the lock-step batch)",
+                       "identity mass matrix, no jitter)",
                        "arithmetic": "tcgen05 GEMMs on hi/lo split operands (3xFP16 with power-of-two operand scaling when the data's dynamic "
                                      "range allows, else 3xTF32), fp32 accumulate, centred contraction"})
 

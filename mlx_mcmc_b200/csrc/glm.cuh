@@ -63,7 +63,7 @@ struct GlmModel {
   // sampler workspace (glm_samplers.cu): one arena reused across calls, plus a pinned host flag
   char *ws = nullptr;
   size_t ws_cap = 0;
-  int *h_flag = nullptr;
+  int *h_flag = nullptr, *h_ring = nullptr;   // pinned: one flag + a ring of lagged counters
   // observation sharding (comm.cu): this handle holds rows [r0, r0 + N) of a model with N_total rows
   Comm *comm = nullptr;
   int64_t N_total = 0;

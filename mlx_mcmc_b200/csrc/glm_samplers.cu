@@ -180,7 +180,10 @@ static int arena_reserve(GlmModel &g, size_t bytes) {
     B2M_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(&g.ws), bytes));
     g.ws_cap = bytes;
   }
-  if (!g.h_flag) B2M_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void **>(&g.h_flag), sizeof(int)));
+  if (!g.h_flag) {
+    B2M_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void **>(&g.h_flag), sizeof(int) * 8));
+    g.h_ring = g.h_flag + 4;
+  }
   return 0;
 }
 
@@ -844,24 +847,33 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   B2M_CHECK_CUDA(cudaMemsetAsync(W.pool, 0, sizeof(double) * 4, st));
   int rc = glm_logp_grad(gm, a.theta, C, W.lp, W.g, st, true);
 
-  constexpr int kCheck = 8;                 // ticks between looks at the finished-chain counter / recentring
+  constexpr int kCheck = 8;                 // ticks between recentring / tail compaction (one host sync each)
+  constexpr int kRing = 4, kLag = 2;        // the finished-chain counter is read kLag ticks late, without a sync
   const bool pooled = a.adapt == B2M_ADAPT_POOLED;
   // worst case: every transition of the slowest chain runs to the depth cap
   const int64_t max_ticks = (int64_t)a.n_iter * ((int64_t(1) << MD) + 1) + 2 * kCheck;
+  cudaEvent_t ring[kRing];
+  for (auto &e : ring) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  int *h_ring = gm.h_ring;                  // pinned, kRing ints
   int64_t n_live = C;
   const int *idx = nullptr;
   for (int64_t tick = 0; !rc; ++tick) {
     if (tick > max_ticks) { set_error("NUTS asynchronous schedule: tick budget exceeded"); rc = 2; break; }
+    if (tick >= kLag) {   // the counter as it was kLag ticks ago: the device always has kLag ticks queued, the host
+      cudaEventSynchronize(ring[(tick - kLag) % kRing]);   // never waits on an empty stream
+      if (h_ring[(tick - kLag) % kRing] >= C) break;
+    }
     nuts_tick_kernel<<<grid, T, 0, st>>>(a, W, D);
     ++g_launches;
+    cudaMemcpyAsync(h_ring + tick % kRing, W.n_done, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(ring[tick % kRing], st);
     if (pooled) {
       nuts_pool_async_kernel<<<1, 1024, 0, st>>>(a, W, 0);
       ++g_launches;
     }
     if (tick % kCheck == kCheck - 1) {
-      cudaMemcpyAsync(h_flag, W.n_done, sizeof(int), cudaMemcpyDeviceToHost, st);
-      if (cudaStreamSynchronize(st) != cudaSuccess) { rc = 2; set_error("NUTS asynchronous schedule: stream error"); break; }
-      const int n_done = *h_flag;
+      if (cudaEventSynchronize(ring[tick % kRing]) != cudaSuccess) { rc = 2; set_error("NUTS asynchronous schedule: stream error"); break; }
+      const int n_done = h_ring[tick % kRing];
       if (n_done >= C) break;
       if ((rc = glm_recenter(gm, a.theta, C, st))) break;      // reference point follows the current states
       if (n_done > 0) {                                        // the tail: evaluate only the chains still running
@@ -873,6 +885,7 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     }
     rc = glm_logp_grad(gm, W.fq, C, W.flp, W.fg, st, false, idx, n_live);
   }
+  for (auto &e : ring) cudaEventDestroy(e);
   if (!rc && pooled) {
     nuts_pool_async_kernel<<<1, 1024, 0, st>>>(a, W, 1);
     ++g_launches;
