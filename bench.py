@@ -9,9 +9,9 @@ GPUs the chains shard (weak scaling: 4096 chains per GPU, no data-path collectiv
 (`--workload`, and the `other_workloads` object of the default line) are C3 (100 x 10K regression, NUTS, 1024 chains),
 C2 (examples/04 event-rate model, 65,536 HMC chains), C1 and C5 (examples/03, 1M Metropolis chains).
 
-A *step*:  GLM workloads (c4, c3) -- one NUTS transition of every chain of the rank (momentum draw, iterative tree
-           build with one lock-step value+gradient per leaf = two tcgen05 3xTF32 GEMMs, U-turn / slice bookkeeping,
-           draw written to HBM);
+A *step*:  GLM workloads (c4, c3) -- one b2m_nuts_run call = 4 (c4) / 16 (c3) NUTS transitions of every chain of the rank
+           (momentum draw, iterative tree build with one lock-step value+gradient per leaf = two tcgen05 GEMMs on
+           hi/lo split operands, U-turn / slice bookkeeping, draws written to HBM);
            pointwise workloads (c2, c1, c5) -- one launch of the persistent kernel covering ITERS whole iterations.
 A *grad-eval* = one value-and-gradient of log_prob for one chain (= one leapfrog step / NUTS leaf; masked lanes of
 the lock-step are not counted).  Metropolis counts value evaluations.
@@ -43,9 +43,9 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    "c4": dict(kind="glm", n=100000, d=1000, chains=4096, eps0=8e-4, adapt_iters=40, max_tree_depth=10,
+    "c4": dict(kind="glm", n=100000, d=1000, chains=4096, eps0=8e-4, adapt_iters=40, max_tree_depth=10, iters=4,
                desc="Bayesian linear regression 1000 params x 100K obs (README 'Large'), NUTS, 4096 chains/GPU"),
-    "c3": dict(kind="glm", n=10000, d=100, chains=1024, eps0=5e-3, adapt_iters=60, max_tree_depth=10,
+    "c3": dict(kind="glm", n=10000, d=100, chains=1024, eps0=5e-3, adapt_iters=60, max_tree_depth=10, iters=16,
                desc="Bayesian linear regression 100 params x 10K obs (README 'Medium'), NUTS, 1024 chains/GPU"),
     "c2": dict(kind="pointwise", model="c2_event_rate", method="hmc", chains=65536, step_size=0.1, L=10, iters=100,
                desc="examples/04_event_rates Gamma/Exponential rate model, 65536 chains/GPU, HMC eps0=0.1 L=10"),
@@ -307,12 +307,13 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
     N, D, MD = wl["n"], wl["d"], wl["max_tree_depth"]
     fn, meta, model, st, mode = glm_setup(torch, B, wl, C, chain_offset, seed)
     it0 = [wl["adapt_iters"]]
-    draws = torch.empty((1, C, D), dtype=torch.float32, device="cuda")
-    depths = torch.empty((1, C), dtype=torch.int32, device="cuda")
+    ITERS = wl["iters"]                     # NUTS transitions per step (one b2m_nuts_run call)
+    draws = torch.empty((ITERS, C, D), dtype=torch.float32, device="cuda")
+    depths = torch.empty((ITERS, C), dtype=torch.int32, device="cuda")
 
     def one_step():
-        launch_nuts(st, 1, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, it0[0], draws=draws, depths=depths)
-        it0[0] += 1
+        launch_nuts(st, ITERS, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, it0[0], draws=draws, depths=depths)
+        it0[0] += ITERS
 
     def barrier():
         if world > 1:
@@ -343,7 +344,7 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
     mean_depth = float(depths.float().mean().item())
 
     # ---- e2e: public API, HOST initial values in, draws back to pinned host memory, inside the timed region
-    S_e2e, e2e_steps = 2, max(2, min(args.steps, 3))
+    S_e2e, e2e_steps = ITERS, max(2, min(args.steps, 3))
     host_theta = st.theta.cpu().numpy().copy()                    # [C, D] per-chain starting points (host memory)
     host_init = {"beta": np.zeros(D, dtype=np.float32)}
     eps_host = float(st.step_size.median().item())
@@ -363,7 +364,7 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
     barrier()
     e2e_s = time.perf_counter() - t0
     clock_info = clocks.stop()
-    log(f"timed {args.steps} steps: {total_ms / args.steps:.1f} ms/step, mean depth {mean_depth:.2f}; e2e {e2e_s:.1f}s")
+    log(f"timed {args.steps} steps of {ITERS} transitions: {total_ms / args.steps:.1f} ms/step, mean depth {mean_depth:.2f}; e2e {e2e_s:.1f}s")
 
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([leaves, e2e_evals, launches], dtype=torch.float64, device="cuda")
@@ -377,7 +378,7 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
            "e2e": {"value": e2e_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": C * D * 4, "d2h_bytes_per_step": S_e2e * C * D * 4,
                    "call": f"nuts(num_warmup=1, num_samples={S_e2e}, num_chains={C}, adapt_step_size=False) with [C, D] host "
                            f"initial values; draws returned as host numpy"},
-           "config_extra": {"chains_per_gpu": C, "iters_per_step": 1, "mean_tree_depth": mean_depth,
+           "config_extra": {"chains_per_gpu": C, "iters_per_step": ITERS, "mean_tree_depth": mean_depth,
                             "grad_evals_per_step_per_gpu": leaves / args.steps,
                             "adapted_step_size_median": eps_host}}
     # ---- N > 1: the same 4096 chains in TOTAL with the observations sharded over the ranks (BASELINE configs[3] as
@@ -387,8 +388,8 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
         it_o = [wl["adapt_iters"]]
 
         def obs_step():
-            launch_nuts(st_o, 1, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, it_o[0], draws=draws, depths=depths)
-            it_o[0] += 1
+            launch_nuts(st_o, ITERS, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, it_o[0], draws=draws, depths=depths)
+            it_o[0] += ITERS
 
         timed_o = Timed(torch, args.steps)
         for _ in range(warm):
