@@ -696,8 +696,32 @@ __global__ void __launch_bounds__(1024) nuts_pool_adapt_kernel(b2m_nuts_args A, 
   }
 }
 
+// carve the NUTS workspace (both schedules) out of the model's arena
+static void nuts_layout(Arena &A, NutsBufs &W, int64_t C, int D, int MD) {
+  const size_t cd = (size_t)C * D;
+  float **vecs[] = {&W.g, &W.p0, &W.q_lo, &W.p_lo, &W.g_lo, &W.q_hi, &W.p_hi, &W.g_hi, &W.cq, &W.cg,
+                    &W.fq, &W.fp, &W.fg, &W.sfq, &W.sfp, &W.scq, &W.scg};
+  for (auto v : vecs) A.take(v, cd);
+  float **stk[] = {&W.st_fq, &W.st_fp, &W.st_cq, &W.st_cg};
+  for (auto v : stk) A.take(v, cd * MD);
+  float **fs[] = {&W.lp, &W.clp, &W.h0, &W.log_slice, &W.flp, &W.sclp, &W.feps, &W.heps};
+  for (auto v : fs) A.take(v, C);
+  int **is[] = {&W.n, &W.s, &W.v, &W.leaf, &W.building, &W.sub_n, &W.sub_na, &W.sub_s, &W.alpha_cnt, &W.depth};
+  for (auto v : is) A.take(v, C);
+  A.take(&W.alpha_sum, C); A.take(&W.sub_alpha, C);
+  A.take(&W.st_clp, (size_t)C * MD); A.take(&W.st_n, (size_t)C * MD); A.take(&W.st_na, (size_t)C * MD);
+  A.take(&W.st_alpha, (size_t)C * MD);
+  A.take(&W.n_active, 1);
+  A.take(&W.active, C);
+  A.take(&W.alpha_it, C);
+  A.take(&W.eps_it, C);
+  A.take(&W.state, C); A.take(&W.iter, C); A.take(&W.fin, C); A.take(&W.live, C);
+  A.take(&W.n_done, 1);
+  A.take(&W.pool, 4);
+}
+
 // ================================================================= NUTS, iteration-asynchronous lock-step
-// The synchronous schedule above advances all chains through the same iteration: a chain whose tree stops at depth 4
+// The synchronous schedule (glm_nuts_run_sync, below) advances all chains through the same iteration: a chain whose tree stops at depth 4
 // waits for the one that runs to depth 10 (with thousands of chains some always do -- DESIGN.md 4.2), and the host
 // synchronises once per doubling.  Here every chain is a small state machine advanced once per *tick*: consume the
 // leaf that was just evaluated (tree bookkeeping; possibly close the doubling, the iteration, start the next
@@ -807,34 +831,12 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   const int64_t C = a.n_chains;
   const int D = gm.Dtot, MD = a.max_tree_depth;
   NutsBufs W{};
-  const size_t cd = (size_t)C * D;
-  auto layout = [&](Arena &A) {
-    float **vecs[] = {&W.g, &W.p0, &W.q_lo, &W.p_lo, &W.g_lo, &W.q_hi, &W.p_hi, &W.g_hi, &W.cq, &W.cg,
-                      &W.fq, &W.fp, &W.fg, &W.sfq, &W.sfp, &W.scq, &W.scg};
-    for (auto v : vecs) A.take(v, cd);
-    float **stk[] = {&W.st_fq, &W.st_fp, &W.st_cq, &W.st_cg};
-    for (auto v : stk) A.take(v, cd * MD);
-    float **fs[] = {&W.lp, &W.clp, &W.h0, &W.log_slice, &W.flp, &W.sclp, &W.feps, &W.heps};
-    for (auto v : fs) A.take(v, C);
-    int **is[] = {&W.n, &W.s, &W.v, &W.leaf, &W.building, &W.sub_n, &W.sub_na, &W.sub_s, &W.alpha_cnt, &W.depth};
-    for (auto v : is) A.take(v, C);
-    A.take(&W.alpha_sum, C); A.take(&W.sub_alpha, C);
-    A.take(&W.st_clp, (size_t)C * MD); A.take(&W.st_n, (size_t)C * MD); A.take(&W.st_na, (size_t)C * MD);
-    A.take(&W.st_alpha, (size_t)C * MD);
-    A.take(&W.n_active, 1);
-    A.take(&W.active, C);
-    A.take(&W.alpha_it, C);
-    A.take(&W.eps_it, C);
-    A.take(&W.state, C); A.take(&W.iter, C); A.take(&W.fin, C); A.take(&W.live, C);
-    A.take(&W.n_done, 1);
-    A.take(&W.pool, 4);
-  };
   Arena probe;
-  layout(probe);
+  nuts_layout(probe, W, C, D, MD);
   if (int rc0 = arena_reserve(gm, probe.off)) return rc0;
   Arena real;
   real.base = gm.ws;
-  layout(real);
+  nuts_layout(real, W, C, D, MD);
   int *h_flag = gm.h_flag;
 
   const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
@@ -901,34 +903,12 @@ int glm_nuts_run_sync(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   const int64_t C = a.n_chains;
   const int D = gm.Dtot, MD = a.max_tree_depth;
   NutsBufs W{};
-  const size_t cd = (size_t)C * D;
-  auto layout = [&](Arena &A) {
-    float **vecs[] = {&W.g, &W.p0, &W.q_lo, &W.p_lo, &W.g_lo, &W.q_hi, &W.p_hi, &W.g_hi, &W.cq, &W.cg,
-                      &W.fq, &W.fp, &W.fg, &W.sfq, &W.sfp, &W.scq, &W.scg};
-    for (auto v : vecs) A.take(v, cd);
-    float **stk[] = {&W.st_fq, &W.st_fp, &W.st_cq, &W.st_cg};
-    for (auto v : stk) A.take(v, cd * MD);
-    float **fs[] = {&W.lp, &W.clp, &W.h0, &W.log_slice, &W.flp, &W.sclp, &W.feps, &W.heps};
-    for (auto v : fs) A.take(v, C);
-    int **is[] = {&W.n, &W.s, &W.v, &W.leaf, &W.building, &W.sub_n, &W.sub_na, &W.sub_s, &W.alpha_cnt, &W.depth};
-    for (auto v : is) A.take(v, C);
-    A.take(&W.alpha_sum, C); A.take(&W.sub_alpha, C);
-    A.take(&W.st_clp, (size_t)C * MD); A.take(&W.st_n, (size_t)C * MD); A.take(&W.st_na, (size_t)C * MD);
-    A.take(&W.st_alpha, (size_t)C * MD);
-    A.take(&W.n_active, 1);
-    A.take(&W.active, C);
-    A.take(&W.alpha_it, C);
-    A.take(&W.eps_it, C);
-    A.take(&W.state, C); A.take(&W.iter, C); A.take(&W.fin, C); A.take(&W.live, C);
-    A.take(&W.n_done, 1);
-    A.take(&W.pool, 4);
-  };
   Arena probe;
-  layout(probe);
+  nuts_layout(probe, W, C, D, MD);
   if (int rc0 = arena_reserve(gm, probe.off)) return rc0;
   Arena real;
   real.base = gm.ws;
-  layout(real);
+  nuts_layout(real, W, C, D, MD);
   int *h_flag = gm.h_flag;
   int rc = 0;
 
