@@ -199,6 +199,18 @@ def _dual_averaging_states(tape, nw, step_size, target=0.65):
                                   "nuts_regression", "nuts_regression_sigma"])
 @pytest.mark.parametrize("lanes", [1, 4])
 def test_nuts_tree_decisions_match_reference(cuda, name, lanes):
+    _replay_nuts(name, lanes)
+
+
+@pytest.mark.parametrize("name", ["nuts_regression", "nuts_regression_sigma"])
+def test_nuts_tree_decisions_match_reference_sync_schedule(cuda, name, monkeypatch):
+    """GLM class: the synchronous lock-step schedule (B2M_NUTS_SCHED=sync) against the same reference transitions
+    (the default, iteration-asynchronous schedule is what the test above runs)."""
+    monkeypatch.setenv("B2M_NUTS_SCHED", "sync")
+    _replay_nuts(name, 1)
+
+
+def _replay_nuts(name, lanes):
     """Every NUTS transition of the reference run is replayed on the GPU from the reference's own state
     (position, step size, dual-averaging state) with the reference's draws injected.  Replaying transition by
     transition keeps one-ulp differences of exp/log from being amplified by the step-size feedback loop, so
