@@ -183,6 +183,32 @@ def test_mcmc_errors_before_any_device_work():
         B.nuts(lambda p: B.Normal(0, 1).log_prob(p["x"]), {"x": 0.0}, num_warmup=0)
 
 
+def test_sampler_option_validation_happens_on_the_host():
+    fn, init = (lambda p: B.Normal(0, 1).log_prob(p["x"])), {"x": 0.0}
+    with pytest.raises(ValueError, match="compat"):
+        B.nuts(fn, init, compat="fast")
+    with pytest.raises(ValueError, match="step_size_adaptation"):
+        B.nuts(fn, init, step_size_adaptation="global")
+    with pytest.raises(ValueError, match="step_size_jitter"):
+        B.nuts(fn, init, step_size_jitter=1.0)
+    with pytest.raises(ValueError, match="max_tree_depth"):
+        B.nuts(fn, init, max_tree_depth=0)
+    with pytest.raises(ValueError, match="adapt"):
+        B.hmc(fn, init, adapt="nesterov")
+    with pytest.raises(TypeError):       # kwargs go to the sampler verbatim, as in the reference (mcmc.py:156,177)
+        B.MCMC(fn).run(init, method="metropolis", step_size=0.1, verbose=False)
+
+
+def test_device_only_helpers_refuse_host_input():
+    import torch
+    from mlx_mcmc_b200.diagnostics import device_series_stats
+    with pytest.raises(ValueError, match="CUDA"):
+        device_series_stats(torch.zeros(4, 2, 3))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            B.Normal(0, 1).sample_device(B.core.random.key(0), (4,))
+
+
 def test_product_never_imports_the_oracle():
     import subprocess
     import sys
