@@ -517,7 +517,32 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
   const float iv = 1.0f / (sg * sg);
   float lp = weight * ((float)N * (-kHalfLog2Pi - logf(sg)) - 0.5f * ss * iv);
   float *gr = grad ? grad + src * Dtot : nullptr;
-  if (gr) {
+  // One warp per chain: with a scalar loop over d the warp walks D / 32 dependent iterations (80-120 us at D = 1000
+  // whatever the number of chains: latency bound).  When the layout allows, each lane takes four consecutive
+  // coefficients and all split-K partials of an iteration are independent 16-byte loads.
+  const bool vec4 = gr && sigma_param < 0 && (Dtot & 3) == 0 && (beta_off & 3) == 0 && (D & 3) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(gr) | reinterpret_cast<uintptr_t>(G)) & 15) == 0;
+  if (vec4) {
+    const float ru = r_unscale ? r_unscale[c] : 1.0f;
+    for (int d = 4 * lane; d < Dtot; d += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (d >= beta_off && d < beta_off + D) {
+        const float4 *g4 = reinterpret_cast<const float4 *>(G + (int64_t)c * Dp + (d - beta_off));
+        const int64_t stride4 = (Cp * (int64_t)Dp) >> 2;
+#pragma unroll 8
+        for (int s = 0; s < g_splits; ++s) {   // fixed order, element by element the same sums as the scalar loop
+          const float4 t = g4[(int64_t)s * stride4];
+          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        if (r_unscale) {
+          const float4 ic = *reinterpret_cast<const float4 *>(inv_col_scale + (d - beta_off));
+          v.x *= ru * ic.x; v.y *= ru * ic.y; v.z *= ru * ic.z; v.w *= ru * ic.w;
+        }
+      }
+      *reinterpret_cast<float4 *>(gr + d) = v;
+    }
+    __syncwarp();
+  } else if (gr) {
 #pragma unroll 2
     for (int d = lane; d < Dtot; d += 32) {
       float v = 0.f;
@@ -542,11 +567,27 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
       const float p0 = T.p0.c, p1 = T.p1.c, var = p1 * p1, base = -kHalfLog2Pi - logf(p1), w = T.weight;
       const float *__restrict__ xv = th + T.x.a;
       float *__restrict__ gv = gr ? gr + T.x.a : nullptr;
+      if ((T.length & 3) == 0 && ((reinterpret_cast<uintptr_t>(xv) | reinterpret_cast<uintptr_t>(gv)) & 15) == 0) {
+        for (int n = 4 * lane; n < T.length; n += 128) {   // same per-element expressions, four elements per lane
+          const float4 x4 = *reinterpret_cast<const float4 *>(xv + n);
+          const float z0 = x4.x - p0, z1 = x4.y - p0, z2 = x4.z - p0, z3 = x4.w - p0;
+          acc += base - (0.5f * (z0 * z0)) / var;
+          acc += base - (0.5f * (z1 * z1)) / var;
+          acc += base - (0.5f * (z2 * z2)) / var;
+          acc += base - (0.5f * (z3 * z3)) / var;
+          if (gv) {
+            float4 g4 = *reinterpret_cast<float4 *>(gv + n);
+            g4.x += w * (-(z0 / var)); g4.y += w * (-(z1 / var)); g4.z += w * (-(z2 / var)); g4.w += w * (-(z3 / var));
+            *reinterpret_cast<float4 *>(gv + n) = g4;
+          }
+        }
+      } else {
 #pragma unroll 4
-      for (int n = lane; n < T.length; n += 32) {
-        const float z = xv[n] - p0;
-        acc += base - (0.5f * (z * z)) / var;
-        if (gv) gv[n] += w * (-(z / var));
+        for (int n = lane; n < T.length; n += 32) {
+          const float z = xv[n] - p0;
+          acc += base - (0.5f * (z * z)) / var;
+          if (gv) gv[n] += w * (-(z / var));
+        }
       }
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       pl += w * acc;

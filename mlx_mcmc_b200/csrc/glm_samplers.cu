@@ -428,6 +428,19 @@ __device__ __forceinline__ void nuts_leaf_pre_dev(const b2m_nuts_args &A, const 
   const float he = W.heps[c], fe = W.feps[c];
   float *__restrict__ fq = W.fq + o, *__restrict__ fp = W.fp + o;
   const float *__restrict__ fg = W.fg + o;
+  if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(fq) | reinterpret_cast<uintptr_t>(fp) | reinterpret_cast<uintptr_t>(fg)) & 15) == 0) {
+    for (int d = 4 * lane; d < D; d += 128) {   // four coefficients per lane: same per-element arithmetic
+      const float4 g4 = *reinterpret_cast<const float4 *>(fg + d);
+      float4 p4 = *reinterpret_cast<float4 *>(fp + d), q4 = *reinterpret_cast<float4 *>(fq + d);
+      p4.x = __fadd_rn(p4.x, __fmul_rn(he, g4.x)); p4.y = __fadd_rn(p4.y, __fmul_rn(he, g4.y));
+      p4.z = __fadd_rn(p4.z, __fmul_rn(he, g4.z)); p4.w = __fadd_rn(p4.w, __fmul_rn(he, g4.w));
+      q4.x = __fadd_rn(q4.x, __fmul_rn(fe, p4.x)); q4.y = __fadd_rn(q4.y, __fmul_rn(fe, p4.y));
+      q4.z = __fadd_rn(q4.z, __fmul_rn(fe, p4.z)); q4.w = __fadd_rn(q4.w, __fmul_rn(fe, p4.w));
+      *reinterpret_cast<float4 *>(fp + d) = p4;
+      *reinterpret_cast<float4 *>(fq + d) = q4;
+    }
+    return;
+  }
 #pragma unroll 4
   for (int d = lane; d < D; d += 32) {
     const float pv = __fadd_rn(fp[d], __fmul_rn(he, fg[d]));
@@ -459,6 +472,21 @@ __device__ __forceinline__ void nuts_leaf_post_dev(const b2m_nuts_args &A, const
   {
     float *__restrict__ sfq = W.sfq + o, *__restrict__ sfp = W.sfp + o, *__restrict__ scq = W.scq + o, *__restrict__ scg = W.scg + o;
     int d = lane;
+    if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(fq) | reinterpret_cast<uintptr_t>(fp) | reinterpret_cast<uintptr_t>(fg) |
+                          reinterpret_cast<uintptr_t>(sfq) | reinterpret_cast<uintptr_t>(sfp) | reinterpret_cast<uintptr_t>(scq) |
+                          reinterpret_cast<uintptr_t>(scg)) & 15) == 0) {
+      for (int e = 4 * lane; e < D; e += 128) {   // four coefficients per lane
+        const float4 q4 = *reinterpret_cast<const float4 *>(fq + e), g4 = *reinterpret_cast<const float4 *>(fg + e);
+        float4 p4 = *reinterpret_cast<float4 *>(fp + e);
+        p4.x = __fadd_rn(p4.x, __fmul_rn(he, g4.x)); p4.y = __fadd_rn(p4.y, __fmul_rn(he, g4.y));
+        p4.z = __fadd_rn(p4.z, __fmul_rn(he, g4.z)); p4.w = __fadd_rn(p4.w, __fmul_rn(he, g4.w));
+        k0 = fmaf(p4.x, p4.x, k0); k1 = fmaf(p4.y, p4.y, k1); k0 = fmaf(p4.z, p4.z, k0); k1 = fmaf(p4.w, p4.w, k1);
+        *reinterpret_cast<float4 *>(fp + e) = p4;
+        *reinterpret_cast<float4 *>(sfq + e) = q4; *reinterpret_cast<float4 *>(scq + e) = q4;
+        *reinterpret_cast<float4 *>(sfp + e) = p4; *reinterpret_cast<float4 *>(scg + e) = g4;
+      }
+      d = D;   // nothing left for the scalar loops
+    }
     for (; d + 32 < D; d += 64) {
       const float q0 = fq[d], q1 = fq[d + 32], g0 = fg[d], g1 = fg[d + 32];
       const float p0 = __fadd_rn(fp[d], __fmul_rn(he, g0)), p1 = __fadd_rn(fp[d + 32], __fmul_rn(he, g1));
