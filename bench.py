@@ -57,8 +57,8 @@ WORKLOADS = {
 METRIC = "leapfrog_grad_evals_per_sec"
 UNIT = "grad-evals/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-NCU_TRAFFIC = {"c4": {"bytes": 2.11e9 + 3.34e9, "source": "profiles/r01_tc_gemm_c4_v3_f16_ncu_summary.md (K5 0.49 GB read + 1.61 GB "
-                      "written, K6 3.22 GB read + 0.12 GB written)"}}
+NCU_TRAFFIC = {"c4": {"bytes": 2.25e9 + 4.27e9, "source": "profiles/r01_tc_gemm_c4_v4_f16_ncu_summary.md (K5 0.64 GB read + 1.62 GB "
+                      "written, K6 4.13 GB read + 0.13 GB written)"}}
 
 
 # ----------------------------------------------------------------------------------------- clocks
