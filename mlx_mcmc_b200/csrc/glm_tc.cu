@@ -554,7 +554,11 @@ int launch_tc_n(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap 
   }
   // `grid` arrives as (128-row tiles, column tiles, K splits); the launch is one persistent CTA group per SM (pair)
   const int Tm = (int)grid.x / NCTA, Tn = (int)grid.y, n_tiles = Tm * Tn * (int)grid.z;
-  const int n_groups = n_tiles < 148 / NCTA ? n_tiles : 148 / NCTA;
+  int n_groups = n_tiles < 148 / NCTA ? n_tiles : 148 / NCTA;
+  if (const char *v = getenv(RESID ? "B2M_TC_GROUPS_RESID" : "B2M_TC_GROUPS_GRAD")) {   // experiments: persistent CTA groups
+    const int want = atoi(v);
+    if (want > 0 && want < n_groups) n_groups = want;
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
     cudaEventCreate(&e0);
