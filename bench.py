@@ -413,6 +413,31 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
                                             "on the compute stream between K6 and finish",
                               "note": "every rank holds all chains and takes identical decisions; grad-evals counted once"}
         log(f"obs-sharded: {out['obs_sharded']['ms_per_step']:.1f} ms/step")
+        # the same again with sliced per-chain state (reduce-scatter + all-gather instead of the all-reduce; rank r
+        # finishes / advances C / N chains): per-chain counters are written by the owning rank only -> sum over ranks
+        if C % world == 0 and C % 256 == 0:
+            os.environ["B2M_OBS_SLICE"] = "1"
+            try:
+                for _ in range(warm):
+                    obs_step()
+                barrier()
+                base = st_o.n_leaves.clone()
+                barrier()
+                timed_s = Timed(torch, args.steps)
+                timed_s.run(obs_step)
+                barrier()
+            finally:
+                os.environ.pop("B2M_OBS_SLICE", None)
+            dl = (st_o.n_leaves - base).sum().double().reshape(1)
+            ts = torch.tensor([timed_s.total_ms()], dtype=torch.float64, device="cuda")
+            dist.all_reduce(dl, op=dist.ReduceOp.SUM)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            out["obs_sharded_sliced"] = {"value": float(dl[0]) / (float(ts[0]) * 1e-3), "unit": UNIT, "scaling": "strong",
+                                         "chains_total": C, "chains_advanced_per_gpu": C // world,
+                                         "ms_per_step": float(ts[0]) / args.steps,
+                                         "collective": "ncclReduceScatter of the [C, D] gradient and [C] sum z^2 + ncclAllGather "
+                                                       "of the [C, D] leaf positions per gradient, on the compute stream"}
+            log(f"obs-sharded, sliced state: {out['obs_sharded_sliced']['ms_per_step']:.1f} ms/step")
     if rank != 0:
         return out
 

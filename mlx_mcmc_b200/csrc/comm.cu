@@ -25,6 +25,8 @@ struct NcclApi {
   int (*GetUniqueId)(void *) = nullptr;
   int (*CommInitRank)(void **, int, Id128, int) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*CommDestroy)(void *) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
@@ -46,9 +48,12 @@ int load_nccl() {
   a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
   a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
   a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+  a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
+  a.ReduceScatter = reinterpret_cast<decltype(a.ReduceScatter)>(dlsym(h, "ncclReduceScatter"));
   a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
   a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-  if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy || !a.GetErrorString) {
+  if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.AllGather || !a.ReduceScatter || !a.CommDestroy ||
+      !a.GetErrorString) {
     set_error("NCCL library lacks an expected symbol");
     return 3;
   }
@@ -107,6 +112,23 @@ void comm_destroy(Comm *c) {
 }
 
 int comm_nranks(const Comm *c) { return c ? c->nranks : 1; }
+int comm_rank(const Comm *c) { return c ? c->rank : 0; }
+
+// in place: rank r's `count` elements live at buf + r * count; afterwards every rank holds all nranks * count
+int comm_allgather_inplace(Comm *c, void *buf, int64_t count, int elt_bytes, cudaStream_t st) {
+  B2M_REQUIRE(c && c->nccl, "allgather: communicator is NULL");
+  const int dt = elt_bytes == 8 ? kNcclInt64 : kNcclFloat32;   // 8-byte elements travel as int64, 4-byte as float32
+  char *base = static_cast<char *>(buf);
+  B2M_CHECK_NCCL(g_nccl.AllGather(base + (size_t)c->rank * count * elt_bytes, buf, (size_t)count, dt, c->nccl, st));
+  return 0;
+}
+
+// in place: sums buf[nranks * count] over ranks; rank r ends with its block, at buf + r * count
+int comm_reducescatter_f32_inplace(Comm *c, float *buf, int64_t count, cudaStream_t st) {
+  B2M_REQUIRE(c && c->nccl, "reducescatter: communicator is NULL");
+  B2M_CHECK_NCCL(g_nccl.ReduceScatter(buf, buf + (size_t)c->rank * count, (size_t)count, kNcclFloat32, kNcclSum, c->nccl, st));
+  return 0;
+}
 
 int comm_allreduce_f32(Comm *c, float *buf, int64_t n, cudaStream_t st) {
   B2M_REQUIRE(c && c->nccl, "allreduce: communicator is NULL");

@@ -494,7 +494,7 @@ int glm_set_comm(GlmModel &g, Comm *c, cudaStream_t st) {
 // gradient of beta from G, gradient of sigma analytically, then the prior terms (generic densities)
 // added on top.  n_tiles = number of 64-wide column tiles that wrote ss_part.
 __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_prior, const float *__restrict__ theta,
-                                                          int64_t C, int64_t Cp, int Dtot, int beta_off, int D, int Dp,
+                                                          int64_t row_base, int64_t C, int64_t Cp, int Dtot, int beta_off, int D, int Dp,
                                                           int sigma_param, float sigma_const, float weight, int N,
                                                           int n_tiles, const float *__restrict__ ss_part,
                                                           const float *__restrict__ G, int g_splits, float *__restrict__ logp,
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
   sm.n_terms = 0;
   if (has_prior) model_to_smem(prior, smem, sm);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int64_t c = (int64_t)blockIdx.x * (blockDim.x / 32) + warp;
+  const int64_t c = row_base + (int64_t)blockIdx.x * (blockDim.x / 32) + warp;   // rows [row_base, C)
   if (c >= C) return;
   const int64_t src = idx ? idx[c] : c;       // chain served by row c of a compacted batch
   const float *th = theta + src * Dtot;
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_p
 }
 
 int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st, bool recenter,
-                  const int *idx, int64_t n_rows) {
+                  const int *idx, int64_t n_rows, int64_t own_base, int64_t own_count) {
   if (int rc = glm_reserve(g, C)) return rc;
   if (recenter)
     if (int rc = glm_recenter(g, theta, C, st)) return rc;
@@ -657,13 +657,27 @@ int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float
     const int64_t n_red = Cp * g.Dp + Cp;
     glm_reduce_kernel<<<(unsigned)((n_red + 255) / 256), 256, 0, st>>>(g.G, grad ? splits : 0, g.ss_part, n_tiles, Cp, g.Dp, r_un, ics, g.red);
     ++g_launches;
-    if (int rc = comm_allreduce_f32(g.comm, grad ? g.red : g.red + Cp * g.Dp, grad ? n_red : Cp, st)) return rc;
+    if (own_count > 0) {
+      // sliced state: every rank only needs the sums of its own chains' rows -- two in-place reduce-scatters
+      // (gradient block, sum-of-squares block) instead of the all-reduce
+      const int nr = comm_nranks(g.comm);
+      B2M_REQUIRE(!idx && Cp == C && C % nr == 0 && own_count == C / nr && own_base == own_count * comm_rank(g.comm),
+                  "glm_logp_grad: sliced state needs a full batch whose rows divide evenly over the ranks");
+      if (grad)
+        if (int rc = comm_reducescatter_f32_inplace(g.comm, g.red, own_count * g.Dp, st)) return rc;
+      if (int rc = comm_reducescatter_f32_inplace(g.comm, g.red + Cp * g.Dp, own_count, st)) return rc;
+    } else {
+      if (int rc = comm_allreduce_f32(g.comm, grad ? g.red : g.red + Cp * g.Dp, grad ? n_red : Cp, st)) return rc;
+    }
     Gp = g.red; ssp = g.red + Cp * g.Dp; splits = 1; n_tiles = 1;
     r_un = nullptr; ics = nullptr;   // already unscaled before the sum over ranks
   }
-  glm_finish_kernel<<<(unsigned)((C + 3) / 4), 128, smem, st>>>(g.prior, g.has_prior ? 1 : 0, theta, C, Cp, g.Dtot, g.beta_off,
-                                                                 g.D, g.Dp, g.sigma_param, g.sigma_const, g.weight,
-                                                                 (int)g.N_total, n_tiles, ssp, Gp, splits, logp, grad, idx, r_un, ics);
+  const int64_t row_base = (g.comm && own_count > 0) ? own_base : 0;
+  const int64_t rows = (g.comm && own_count > 0) ? own_count : C;
+  glm_finish_kernel<<<(unsigned)((rows + 3) / 4), 128, smem, st>>>(g.prior, g.has_prior ? 1 : 0, theta, row_base, row_base + rows, Cp,
+                                                                    g.Dtot, g.beta_off, g.D, g.Dp, g.sigma_param, g.sigma_const,
+                                                                    g.weight, (int)g.N_total, n_tiles, ssp, Gp, splits, logp, grad,
+                                                                    idx, r_un, ics);
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -19,6 +19,9 @@ int comm_unique_id(uint8_t *out128);
 int comm_init(const uint8_t *id128, int nranks, int rank, Comm **out);
 void comm_destroy(Comm *c);
 int comm_nranks(const Comm *c);
+int comm_rank(const Comm *c);
+int comm_allgather_inplace(Comm *c, void *buf, int64_t count, int elt_bytes, cudaStream_t st);
+int comm_reducescatter_f32_inplace(Comm *c, float *buf, int64_t count, cudaStream_t st);
 int comm_allreduce_f32(Comm *c, float *buf, int64_t n, cudaStream_t st);
 int comm_allreduce_i64(Comm *c, int64_t *buf, int64_t n, cudaStream_t st);
 
@@ -78,8 +81,11 @@ void glm_free(GlmModel &g);
 // log p and gradient for `theta` [C, Dtot] (device).  grad may be NULL.  recenter: move the reference point of
 // the contraction to the mean of `theta` first (the samplers do it once per iteration, from the current states).
 // idx / n_rows: evaluate only the chains idx[0..n_rows) (a compacted lock-step batch); outputs land at the chains' rows.
+// own_count > 0 (observation sharding with sliced state, full batch only): the partial gradients are reduce-scattered
+// and only the rows [own_base, own_base + own_count) -- this rank's chains -- are finished.
 int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st,
-                  bool recenter = false, const int *idx = nullptr, int64_t n_rows = 0);
+                  bool recenter = false, const int *idx = nullptr, int64_t n_rows = 0, int64_t own_base = 0,
+                  int64_t own_count = 0);
 int glm_recenter(GlmModel &g, const float *theta, int64_t C, cudaStream_t st);
 
 // the two contractions (SIMT implementation)

@@ -181,8 +181,8 @@ static int arena_reserve(GlmModel &g, size_t bytes) {
     g.ws_cap = bytes;
   }
   if (!g.h_flag) {
-    B2M_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void **>(&g.h_flag), sizeof(int) * 8));
-    g.h_ring = g.h_flag + 4;
+    B2M_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void **>(&g.h_flag), sizeof(int) * 16));
+    g.h_ring = g.h_flag + 4;   // 8-byte aligned ring of four 64-bit counters
   }
   return 0;
 }
@@ -758,8 +758,10 @@ static void nuts_layout(Arena &A, NutsBufs &W, int64_t C, int D, int MD) {
 // next one, and the host only looks at a counter every few ticks.  Per chain the algorithm, the Philox slots and the
 // arithmetic are those of the synchronous kernels (the same device functions), so a chain's draws are the same up to
 // the batch-dependent rounding of the GLM contractions.
-__global__ void __launch_bounds__(32 * WPB) nuts_tick_kernel(b2m_nuts_args A, NutsBufs W, int D) {
-  CHAIN_PROLOGUE(A.n_chains)
+__global__ void __launch_bounds__(32 * WPB) nuts_tick_kernel(b2m_nuts_args A, NutsBufs W, int D, int64_t c_base, int64_t c_end) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = c_base + (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5);   // this rank's chains: [c_base, c_end)
+  if (c >= c_end) return;
   const int st = W.state[c];
   if (st == 2) return;
   int it = W.iter[c];
@@ -802,6 +804,8 @@ __global__ void __launch_bounds__(32 * WPB) nuts_tick_kernel(b2m_nuts_args A, Nu
 // this tick are added (fixed order) to a pool; every n_chains completed transitions -- one per chain on average -- the
 // recurrences of nuts.py:298-310 advance once on the pool's mean and every chain gets the new step size for its next
 // transition.  `flush` applies what is left at the end of the call.
+__global__ void set_i64_kernel(long long *dst, const int *src) { *dst = (long long)*src; }
+
 __global__ void __launch_bounds__(1024) nuts_pool_async_kernel(b2m_nuts_args A, NutsBufs W, int flush) {
   __shared__ double rs[1024];
   __shared__ int rc[1024];
@@ -880,11 +884,33 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   constexpr int kCheck = 8;                 // ticks between recentring / tail compaction (one host sync each)
   constexpr int kRing = 4, kLag = 2;        // the finished-chain counter is read kLag ticks late, without a sync
   const bool pooled = a.adapt == B2M_ADAPT_POOLED;
+  // Observation sharding with SLICED state (B2M_OBS_SLICE=1, no adaptation in the call, chains divide evenly over the
+  // ranks): instead of every rank running the per-chain state machine and `finish` for all chains, rank r owns the
+  // chains [r C/G, (r+1) C/G): the gradient partials are reduce-scattered, the rank finishes and advances its slice,
+  // and the new leaf positions of all slices are all-gathered for the next pack / contraction.  Per-chain outputs
+  // (draws, counters, depths) are written for the owned chains only; the final positions are all-gathered.
+  int64_t own_base = 0, own_count = 0;
+  if (gm.comm && a.adapt == B2M_ADAPT_NONE) {
+    const char *v = getenv("B2M_OBS_SLICE");
+    const int nr = comm_nranks(gm.comm);
+    if (v && atoi(v) == 1 && nr > 1) {
+      if (C % nr != 0 || C % 256 != 0) {   // the caller merges per-chain outputs by slice: never fall back silently
+        set_error("B2M_OBS_SLICE=1: n_chains must be a multiple of 256 and of the number of ranks");
+        return 1;
+      }
+      own_count = C / nr;
+      own_base = own_count * comm_rank(gm.comm);
+    }
+  }
+  const bool sliced = own_count > 0;
+  const int64_t c_base = sliced ? own_base : 0, c_end = sliced ? own_base + own_count : C;
+  const unsigned tick_grid = (unsigned)((c_end - c_base + WPB - 1) / WPB);
+  long long *n_done_g = reinterpret_cast<long long *>(W.pool) + 3;   // spare slot of the pool block: global finished count
   // worst case: every transition of the slowest chain runs to the depth cap
   const int64_t max_ticks = (int64_t)a.n_iter * ((int64_t(1) << MD) + 1) + 2 * kCheck;
   cudaEvent_t ring[kRing];
   for (auto &e : ring) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-  int *h_ring = gm.h_ring;                  // pinned, kRing ints
+  long long *h_ring = reinterpret_cast<long long *>(gm.h_ring);   // pinned, kRing 8-byte counters
   int64_t n_live = C;
   const int *idx = nullptr;
   for (int64_t tick = 0; !rc; ++tick) {
@@ -893,9 +919,14 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
       cudaEventSynchronize(ring[(tick - kLag) % kRing]);   // never waits on an empty stream
       if (h_ring[(tick - kLag) % kRing] >= C) break;
     }
-    nuts_tick_kernel<<<grid, T, 0, st>>>(a, W, D);
-    ++g_launches;
-    cudaMemcpyAsync(h_ring + tick % kRing, W.n_done, sizeof(int), cudaMemcpyDeviceToHost, st);
+    nuts_tick_kernel<<<tick_grid, T, 0, st>>>(a, W, D, c_base, c_end);
+    set_i64_kernel<<<1, 1, 0, st>>>(n_done_g, W.n_done);
+    g_launches += 2;
+    if (sliced) {
+      if ((rc = comm_allreduce_i64(gm.comm, reinterpret_cast<int64_t *>(n_done_g), 1, st))) break;
+      if ((rc = comm_allgather_inplace(gm.comm, W.fq, own_count * D, 4, st))) break;      // every rank's new leaf positions
+    }
+    cudaMemcpyAsync(h_ring + tick % kRing, n_done_g, sizeof(long long), cudaMemcpyDeviceToHost, st);
     cudaEventRecord(ring[tick % kRing], st);
     if (pooled) {
       nuts_pool_async_kernel<<<1, 1024, 0, st>>>(a, W, 0);
@@ -903,18 +934,20 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     }
     if (tick % kCheck == kCheck - 1) {
       if (cudaEventSynchronize(ring[tick % kRing]) != cudaSuccess) { rc = 2; set_error("NUTS asynchronous schedule: stream error"); break; }
-      const int n_done = h_ring[tick % kRing];
+      const int64_t n_done = h_ring[tick % kRing];
       if (n_done >= C) break;
+      if (sliced && (rc = comm_allgather_inplace(gm.comm, a.theta, own_count * D, 4, st))) break;
       if ((rc = glm_recenter(gm, a.theta, C, st))) break;      // reference point follows the current states
-      if (n_done > 0) {                                        // the tail: evaluate only the chains still running
+      if (n_done > 0 && !sliced) {                             // the tail: evaluate only the chains still running
         nuts_compact_kernel<<<1, 1024, 0, st>>>(W.live, C, W.active, W.n_active);
         ++g_launches;
         n_live = C - n_done;
         idx = W.active;
       }
     }
-    rc = glm_logp_grad(gm, W.fq, C, W.flp, W.fg, st, false, idx, n_live);
+    rc = glm_logp_grad(gm, W.fq, C, W.flp, W.fg, st, false, idx, n_live, own_base, own_count);
   }
+  if (!rc && sliced) rc = comm_allgather_inplace(gm.comm, a.theta, own_count * D, 4, st);   // final positions everywhere
   for (auto &e : ring) cudaEventDestroy(e);
   if (!rc && pooled) {
     nuts_pool_async_kernel<<<1, 1024, 0, st>>>(a, W, 1);

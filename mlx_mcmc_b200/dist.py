@@ -9,7 +9,10 @@ Two ways to partition a run over the ranks of one box:
 * **observation sharding** (GLM-class models, the 100K-observation regression) -- every rank holds every chain and a
   row shard of (X, y); each value+gradient sums the ``[C, D]`` gradient partial and the ``[C]`` sum of squared
   residuals over ranks with one NCCL all-reduce on the compute stream (`ObsComm`, csrc/comm.cu).  All ranks then
-  hold identical results and take identical accept / U-turn decisions.
+  hold identical results and take identical accept / U-turn decisions.  With ``slice_state=True`` (NUTS sampling
+  phase) the per-chain work is sliced too: rank r finishes and advances chains ``[r C/G, (r+1) C/G)`` only; the
+  all-reduce becomes a reduce-scatter and the new leaf positions are all-gathered (csrc/glm_samplers.cu,
+  `glm_nuts_run_async`), which removes the replicated per-chain kernels from every rank's critical path.
 
 The reference is single device, single chain (README.md:33-36,212-213): nothing here has a counterpart there.
 """
@@ -235,6 +238,8 @@ def run_sharded(log_prob_fn, initial_params, method: str = "nuts", num_chains: i
             tot = reduce_stats({"acc": rate * count, "n": count}, "sum", group, dev)
             rate = tot["acc"] / max(tot["n"], 1.0)
         return samples, rate, info
+    if kwargs.get("slice_state") and method != "nuts":
+        raise ValueError("slice_state is a NUTS option")
     model = compile_obs_sharded(log_prob_fn, initial_params, group)
     samples, rate, info = samplers[method](log_prob_fn, initial_params, num_chains=num_chains, model=model, **kwargs)
     if num_chains == 1:

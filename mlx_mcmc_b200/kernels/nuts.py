@@ -3,12 +3,29 @@ from __future__ import annotations
 
 from typing import Callable, Dict, Tuple
 
+import os
+
 import numpy as np
 import torch
 
 from .. import _cabi
 from ..engine import launch_nuts
 from ._common import SamplerInfo, alloc_draws, philox_seed, prepare
+
+
+def _sliced_world(model, num_chains: int) -> int:
+    """World size when the sliced observation-sharded schedule applies to `model`, else an error (never a silent
+    fall-back: the per-chain outputs of a sliced call must be merged, those of a replicated call must not)."""
+    comm = getattr(model, "_comm", None)
+    if comm is None or comm.world < 2:
+        raise ValueError("slice_state=True needs an observation-sharded model (dist.compile_obs_sharded) on > 1 ranks")
+    if model.model_class != 1:
+        raise ValueError("slice_state=True needs a GLM-class model")
+    if num_chains % comm.world or num_chains % 256:
+        raise ValueError("slice_state=True: num_chains must be a multiple of 256 and of the number of ranks")
+    if os.environ.get("B2M_NUTS_SCHED", "") == "sync":
+        raise ValueError("slice_state=True needs the asynchronous NUTS schedule (unset B2M_NUTS_SCHED)")
+    return comm.world
 
 
 def nuts(
@@ -32,6 +49,7 @@ def nuts(
     return_info: bool = False,
     model=None,
     theta0=None,
+    slice_state: bool = False,
 ) -> Tuple[Dict[str, object], float]:
     """Same arguments and return value as the reference's ``nuts``: ``(samples, rate)`` where rate is the
     fraction of sampling iterations whose mean acceptance statistic exceeded 0.5 (nuts.py:341,353) and
@@ -51,7 +69,11 @@ def nuts(
     ``eps * (1 + j * (2u - 1))``.  The reference's U-turn test looks at positions only (nuts.py:119-135); on a nearly
     isotropic Gaussian posterior it cannot see a turn when 2^k - 1 steps are just over a whole number of oscillation
     periods, and trees then run to ``max_tree_depth`` (measured at the 1000 x 100K regression: mean depth 7.7 instead
-    of 4 at eps = 1.34e-3).  A jitter of 0.1-0.2 removes the resonance."""
+    of 4 at eps = 1.34e-3).  A jitter of 0.1-0.2 removes the resonance.
+
+    ``slice_state=True`` (observation-sharded GLM models only, see dist.py): during the sampling phase rank r advances
+    only the chains of its slice; gradients are reduce-scattered and leaf positions all-gathered inside the library, and
+    draws / counters of the slices are merged over ``torch.distributed`` before returning."""
     if num_warmup == 0:
         raise ZeroDivisionError("division by zero")   # nuts.py:322-323
     if compat not in ("reference", "correct"):
@@ -83,8 +105,27 @@ def nuts(
     st.n_accept.zero_()
     draws = alloc_draws(model, num_samples, num_chains)
     depths = torch.empty((num_samples, num_chains), dtype=torch.int32, device=model.device)
-    launch_nuts(st, num_samples, max_tree_depth, _cabi.ADAPT_NONE, cmode, target_accept, seed, num_warmup,
-                draws=draws, depths=depths, lanes=lanes, step_size_jitter=step_size_jitter)
+    sliced = _sliced_world(model, num_chains) if slice_state else 0
+    if sliced:
+        # rank r writes draws / depths / counters of its slice only: start from zeros and sum the slices afterwards
+        import torch.distributed as td
+        draws.zero_()
+        depths.zero_()
+        base = [t.clone() for t in (st.n_leaves, st.n_diverge)]
+        os.environ["B2M_OBS_SLICE"] = "1"
+    try:
+        launch_nuts(st, num_samples, max_tree_depth, _cabi.ADAPT_NONE, cmode, target_accept, seed, num_warmup,
+                    draws=draws, depths=depths, lanes=lanes, step_size_jitter=step_size_jitter)
+    finally:
+        if sliced:
+            os.environ.pop("B2M_OBS_SLICE", None)
+    if sliced:
+        for t, b in zip((st.n_leaves, st.n_diverge), base):
+            d = t - b
+            td.all_reduce(d)
+            t.copy_(b + d)
+        for t in (st.n_accept, draws, depths):
+            td.all_reduce(t)
     rate = float(st.n_accept.double().sum().item() / max(num_samples * num_chains, 1))
     samples = model.unpack(draws, squeeze_chain=(num_chains == 1), to_numpy=not return_torch)
     if return_info:

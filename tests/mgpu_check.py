@@ -4,7 +4,10 @@
    bit for bit (Philox streams are keyed by global chain id);
 2. observation sharding: log p / gradient of the row-sharded model agree with the unsharded model to float32
    rounding and are bit-identical on every rank;
-3. observation-sharded NUTS: every rank produces bit-identical draws, and they agree with the closed-form posterior.
+3. observation-sharded NUTS: every rank produces bit-identical draws, and they agree with the closed-form posterior;
+4. the same with sliced state (slice_state=True: reduce-scatter / all-gather inside the library): the merged draws are
+   identical on every rank, start out equal to the replicated schedule's (same Philox streams, rounding-level
+   differences only) and agree with the closed-form posterior; counters match the depth record.
 Prints one line `MGPU_CHECK OK ...` from rank 0 on success; any failure raises on the failing rank.
 """
 import os
@@ -72,6 +75,31 @@ def main():
     assert z.max() < 6.0, z.max()
     report["obs_nuts_max_z"] = float(z.max())
     report["obs_nuts_grad_evals"] = info.grad_evals
+
+    # ---- 4. sliced state
+    kw = dict(method="nuts", num_chains=256 * world, shard="obs", num_samples=40, num_warmup=80, step_size=0.05,
+              compat="correct", key=mx.random.key(4), return_torch=True)
+    s_rep, r_rep, i_rep = D.run_sharded(fr, initr, **kw)
+    s_sl, r_sl, i_sl = D.run_sharded(fr, initr, slice_state=True, **kw)
+    d_rep, d_sl = s_rep["beta"].contiguous(), s_sl["beta"].contiguous()
+    assert d_sl.shape == d_rep.shape == (256 * world, 40, 48)
+    allr = [torch.empty_like(d_sl) for _ in range(world)]
+    td.all_gather(allr, d_sl)
+    assert all(torch.equal(allr[0], a) for a in allr), "ranks hold different merged draws after a sliced run"
+    first = float((d_sl[:, 0] - d_rep[:, 0]).abs().max())        # first kept draw: same streams, rounding only
+    assert first < 5e-4, first
+    assert torch.isfinite(d_sl).all()
+    mean = d_sl.double().mean(dim=(0, 1)).cpu().numpy()
+    z = np.abs(mean - m) / np.sqrt(np.diag(V) / (256 * world * 40 / 4))
+    assert z.max() < 6.0, z.max()
+    assert i_sl.depths.shape == i_rep.depths.shape and i_sl.depths.min() >= 1
+    leaves = int((2 ** i_sl.depths.astype(np.int64) - 1).sum())   # leaves of the sampling phase follow from the depths
+    assert i_sl.grad_evals - i_sl.warmup_grad_evals <= leaves + i_sl.depths.size * 2, (i_sl.grad_evals, leaves)
+    assert abs(i_sl.grad_evals - i_rep.grad_evals) < 0.05 * i_rep.grad_evals, (i_sl.grad_evals, i_rep.grad_evals)
+    assert abs(r_sl - r_rep) < 0.05, (r_sl, r_rep)
+    report["sliced_first_draw_maxdiff"] = first
+    report["sliced_max_z"] = float(z.max())
+    report["sliced_grad_evals"] = (i_sl.grad_evals, i_rep.grad_evals)
 
     td.barrier()
     if rank == 0:
