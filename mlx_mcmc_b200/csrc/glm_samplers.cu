@@ -911,6 +911,7 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   cudaEvent_t ring[kRing];
   for (auto &e : ring) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   long long *h_ring = reinterpret_cast<long long *>(gm.h_ring);   // pinned, kRing 8-byte counters
+  for (int i = 0; i < kRing; ++i) h_ring[i] = 0;
   int64_t n_live = C;
   const int *idx = nullptr;
   for (int64_t tick = 0; !rc; ++tick) {
@@ -920,13 +921,16 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
       if (h_ring[(tick - kLag) % kRing] >= C) break;
     }
     nuts_tick_kernel<<<tick_grid, T, 0, st>>>(a, W, D, c_base, c_end);
-    set_i64_kernel<<<1, 1, 0, st>>>(n_done_g, W.n_done);
-    g_launches += 2;
-    if (sliced) {
+    ++g_launches;
+    if (sliced) {   // the counter of this rank's slice, widened and summed over ranks; then every rank's new leaf positions
+      set_i64_kernel<<<1, 1, 0, st>>>(n_done_g, W.n_done);
+      ++g_launches;
       if ((rc = comm_allreduce_i64(gm.comm, reinterpret_cast<int64_t *>(n_done_g), 1, st))) break;
-      if ((rc = comm_allgather_inplace(gm.comm, W.fq, own_count * D, 4, st))) break;      // every rank's new leaf positions
+      if ((rc = comm_allgather_inplace(gm.comm, W.fq, own_count * D, 4, st))) break;
+      cudaMemcpyAsync(h_ring + tick % kRing, n_done_g, sizeof(long long), cudaMemcpyDeviceToHost, st);
+    } else {        // low word of the (zeroed) 64-bit ring slot
+      cudaMemcpyAsync(h_ring + tick % kRing, W.n_done, sizeof(int), cudaMemcpyDeviceToHost, st);
     }
-    cudaMemcpyAsync(h_ring + tick % kRing, n_done_g, sizeof(long long), cudaMemcpyDeviceToHost, st);
     cudaEventRecord(ring[tick % kRing], st);
     if (pooled) {
       nuts_pool_async_kernel<<<1, 1024, 0, st>>>(a, W, 0);
