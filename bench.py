@@ -165,7 +165,7 @@ def cpu_baseline(wl_name: str, cores: int, scale: float = 1.0):
     wl = WORKLOADS[wl_name]
     t0 = time.perf_counter()
     if wl["kind"] == "glm":
-        n_iter = max(1, int(round((2 if wl_name == "c4" else 20) * scale)))
+        n_iter = max(1, int(round((10 if wl_name == "c4" else 60) * scale)))   # ~10-15 s of host work
         evals, busy, grads = _cpu_glm(wl_name, cores, n_iter)
         sample = (f"1 chain x {n_iter} NUTS transition(s) (+1 warm-up transition) from the posterior mode, step size "
                   f"{wl['eps0']}, no adaptation, on the oracle restatement (reference source semantics on a torch-CPU "
