@@ -139,6 +139,22 @@ def reduce_stats(values: Dict[str, float], op: str = "sum", group=None, device: 
     return {k: float(x) for k, x in zip(keys, t.tolist())}
 
 
+def merge_slices(zero_based, accumulators=(), group=None) -> None:
+    """Merge per-chain outputs of a sliced observation-sharded call, in place, on every rank.
+
+    `zero_based`: tensors that were zero before the call and that only the owning rank wrote (draws, depths, accept
+    counts) -- summed over ranks.  `accumulators`: pairs ``(tensor, value_before_the_call)`` of running per-chain counters
+    that every rank held identically before the call and only the owner advanced -- the increments are summed."""
+    if rank_world(group)[1] == 1:
+        return
+    for t, before in accumulators:
+        inc = t - before
+        td.all_reduce(inc, group=group)
+        t.copy_(before + inc)
+    for t in zero_based:
+        td.all_reduce(t, group=group)
+
+
 # ------------------------------------------------------------------------------------------ observation sharding
 class ObsComm:
     """The library-side communicator for observation sharding.  Rank 0 asks the library for a 128-byte NCCL id, the

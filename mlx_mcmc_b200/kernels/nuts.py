@@ -108,7 +108,7 @@ def nuts(
     sliced = _sliced_world(model, num_chains) if slice_state else 0
     if sliced:
         # rank r writes draws / depths / counters of its slice only: start from zeros and sum the slices afterwards
-        import torch.distributed as td
+        from ..dist import merge_slices
         draws.zero_()
         depths.zero_()
         base = [t.clone() for t in (st.n_leaves, st.n_diverge)]
@@ -120,12 +120,7 @@ def nuts(
         if sliced:
             os.environ.pop("B2M_OBS_SLICE", None)
     if sliced:
-        for t, b in zip((st.n_leaves, st.n_diverge), base):
-            d = t - b
-            td.all_reduce(d)
-            t.copy_(b + d)
-        for t in (st.n_accept, draws, depths):
-            td.all_reduce(t)
+        merge_slices((st.n_accept, draws, depths), zip((st.n_leaves, st.n_diverge), base))
     rate = float(st.n_accept.double().sum().item() / max(num_samples * num_chains, 1))
     samples = model.unpack(draws, squeeze_chain=(num_chains == 1), to_numpy=not return_torch)
     if return_info:

@@ -82,6 +82,19 @@ def _worker(rank, world, port, q):
         assert D.reduce_stats({"t": float(rank)}, "max") == {"t": 1.0}
         with pytest.raises(ValueError):
             D.gather_draws({"mu": np.zeros((count + 1, 2), np.float32)}, count)
+        # merge of a sliced call: the owner wrote its slice of zero-initialised outputs and advanced its counters
+        n, per = 6, 3
+        own = slice(rank * per, (rank + 1) * per)
+        draws = torch.zeros(2, n, 3)
+        draws[:, own] = torch.arange(n, dtype=torch.float32)[None, own, None] + 1.0
+        before = torch.full((n,), 7, dtype=torch.int64)
+        leaves = before.clone()
+        leaves[own] += torch.arange(n)[own] + 1
+        D.merge_slices((draws,), [(leaves, before)])
+        assert torch.equal(draws[0, :, 0], torch.arange(n, dtype=torch.float32) + 1.0)
+        assert torch.equal(leaves, 7 + torch.arange(n) + 1)
+        with pytest.raises(ValueError):
+            D.run_sharded(lambda p: 0, {"x": 0.0}, method="hmc", shard="obs", slice_state=True)
         # run_sharded refuses bad modes before touching a device
         with pytest.raises(ValueError):
             D.run_sharded(lambda p: 0, {"x": 0.0}, method="gibbs")
@@ -105,3 +118,17 @@ def test_gather_and_reduce_on_gloo_world_2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, "ok"), (1, "ok")], res
+
+
+def test_sliced_state_preconditions():
+    """nuts(slice_state=True) never falls back silently: it needs an observation-sharded GLM model on > 1 ranks and a
+    chain count the ranks (and the 256-row tiles) divide."""
+    from types import SimpleNamespace as NS
+    from mlx_mcmc_b200.kernels.nuts import _sliced_world
+    comm2 = NS(world=2)
+    assert _sliced_world(NS(_comm=comm2, model_class=1), 512) == 2
+    for model, chains in ((NS(_comm=None, model_class=1), 512), (NS(_comm=NS(world=1), model_class=1), 512),
+                          (NS(_comm=comm2, model_class=0), 512), (NS(_comm=comm2, model_class=1), 384),
+                          (NS(_comm=NS(world=3), model_class=1), 512)):
+        with pytest.raises(ValueError):
+            _sliced_world(model, chains)
