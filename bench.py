@@ -43,7 +43,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    "c4": dict(kind="glm", n=100000, d=1000, chains=4096, eps0=8e-4, adapt_iters=40, max_tree_depth=10, iters=4,
+    "c4": dict(kind="glm", n=100000, d=1000, chains=4096, eps0=8e-4, adapt_iters=40, max_tree_depth=10, iters=8,
                desc="Bayesian linear regression 1000 params x 100K obs (README 'Large'), NUTS, 4096 chains/GPU"),
     "c3": dict(kind="glm", n=10000, d=100, chains=1024, eps0=5e-3, adapt_iters=60, max_tree_depth=10, iters=16,
                desc="Bayesian linear regression 100 params x 10K obs (README 'Medium'), NUTS, 1024 chains/GPU"),

@@ -67,6 +67,8 @@ struct GlmModel {
   char *ws = nullptr;
   size_t ws_cap = 0;
   int *h_flag = nullptr, *h_ring = nullptr;   // pinned: one flag + a ring of lagged counters
+  const int *skip_flag = nullptr;             // device counter; the tensor-core contractions return at once when it has
+  int skip_target = 0;                        // reached skip_target (set by the asynchronous NUTS loop only)
   // observation sharding (comm.cu): this handle holds rows [r0, r0 + N) of a model with N_total rows
   Comm *comm = nullptr;
   int64_t N_total = 0;

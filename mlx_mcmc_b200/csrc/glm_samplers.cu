@@ -914,6 +914,8 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   for (int i = 0; i < kRing; ++i) h_ring[i] = 0;
   int64_t n_live = C;
   const int *idx = nullptr;
+  // the host sees the counter kLag ticks late: the contractions of those surplus ticks return immediately
+  if (!gm.comm) { gm.skip_flag = W.n_done; gm.skip_target = (int)C; }
   for (int64_t tick = 0; !rc; ++tick) {
     if (tick > max_ticks) { set_error("NUTS asynchronous schedule: tick budget exceeded"); rc = 2; break; }
     if (tick >= kLag) {   // the counter as it was kLag ticks ago: the device always has kLag ticks queued, the host
@@ -951,6 +953,7 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     }
     rc = glm_logp_grad(gm, W.fq, C, W.flp, W.fg, st, false, idx, n_live, own_base, own_count);
   }
+  gm.skip_flag = nullptr;
   if (!rc && sliced) rc = comm_allgather_inplace(gm.comm, a.theta, own_count * D, 4, st);   // final positions everywhere
   for (auto &e : ring) cudaEventDestroy(e);
   if (!rc && pooled) {

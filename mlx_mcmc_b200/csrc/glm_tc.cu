@@ -212,6 +212,10 @@ struct EpiParams {
   // PLAIN
   float *Gpart;  // [splits, Cp, Dp]
   int Dp;
+  // both: the launch is a no-op once *skip_flag >= skip_target (every chain of the call has finished; the host learns
+  // it a few launches late because it reads the counter without draining the stream)
+  const int *skip_flag;
+  int skip_target;
 };
 
 template <int BLOCK_N, int NCTA>
@@ -231,6 +235,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int k_blocks_total,
                int k_blocks_per_split, int CHUNK_KB, int mma_mask, int Tm, int Tn, int n_tiles, EpiParams E) {
   using C = Cfg<BLOCK_N, NCTA>;
+  if (E.skip_flag && *reinterpret_cast<const volatile int *>(E.skip_flag) >= E.skip_target) return;   // uniform over the grid
   constexpr int BLOCK_K = Enc<F16>::BLOCK_K;   // K elements per k-block (shadows the tf32 constant)
   constexpr int SCRATCH_BYTES = RESID ? NUM_EPI_WARPS * 32 * 33 * 4 : 0;   // per-warp transpose scratch of the K5 epilogue
   extern __shared__ unsigned char smem_raw[];
@@ -674,6 +679,7 @@ int tc_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st) {
     return 2;
   EpiParams E{};
   E.y = g.y0; E.inv_var = g.inv_var; E.ss_part = g.ss_part; E.Cp = Cp; E.Np = g.Np;
+  E.skip_flag = g.skip_flag; E.skip_target = g.skip_target;
   E.Rh = f16 ? (void *)g.R16h : (void *)g.Rh;
   E.Rl = f16 ? (void *)g.R16l : (void *)g.Rl;
   E.a_unscale = g.a_unscale; E.r_scale = g.r_scale;
@@ -702,6 +708,7 @@ int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
     return 2;
   EpiParams E{};
   E.Gpart = g.G; E.Cp = Cp; E.Dp = g.Dp;
+  E.skip_flag = g.skip_flag; E.skip_target = g.skip_target;
   dim3 grid((unsigned)(Cp / BLOCK_M), g.Dp / bn, (unsigned)((kb_total + kb_per - 1) / kb_per));
   g.g_splits = (int)grid.z;
   const int ck = chunk_kb("B2M_TC_CHUNK_GRAD", f16 ? DEFAULT_CHUNK_KB / 2 : DEFAULT_CHUNK_KB);
