@@ -224,3 +224,78 @@ def test_no_cuda_fails_loudly():
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError, match="no CUDA device"):
         B.MCMC(lambda p: B.Normal(0, 1).log_prob(p["x"])).run({"x": 0.0}, num_samples=5, num_warmup=5, verbose=False)
+
+
+@pytest.mark.parametrize("name", sorted(W.ALL_SMALL))
+def test_traced_table_means_what_the_model_says(name):
+    """Tracing preserves the model: a plain float64 evaluation of the term table (tests/table_eval.py) gives the
+    oracle's log p and gradient at the initial point and at perturbed points inside the support."""
+    from oracle.ns import ns as ons, value_and_grad
+    from table_eval import table_grad, table_logp
+    fn, init, _ = W.ALL_SMALL[name](B.ns)
+    fo, _, _ = W.ALL_SMALL[name](ons)
+    model = trace(fn, init)
+    rng = np.random.default_rng(7)
+    for trial in range(3):
+        params = {k: (np.asarray(v, dtype=np.float64) * (1.0 + 0.1 * trial * rng.uniform(-1, 1, np.shape(v)))
+                      + 0.01 * trial * rng.uniform(0, 1, np.shape(v))) for k, v in init.items()}
+        params = {k: (float(v) if np.ndim(v) == 0 else v) for k, v in params.items()}
+        lp64, g64 = value_and_grad(fo, params, "float64")
+        theta = np.concatenate([np.atleast_1d(np.asarray(params[k], dtype=np.float64)).ravel() for k in model.layout])
+        want = np.concatenate([np.atleast_1d(g64[k]).ravel() for k in model.layout])
+        # the table holds observations and normalising constants in float32 (the reference's device dtype), the
+        # oracle call keeps float64: the bound is float32 rounding of the largest addend
+        scale = max([1.0, abs(lp64)] + [abs(k) for t in model.terms for k in t.k])
+        assert abs(table_logp(model, theta) - lp64) <= 2e-7 * scale, (name, trial)
+        got = table_grad(model, theta)
+        assert np.max(np.abs(got - want)) <= 1e-5 * max(1.0, np.max(np.abs(want))), (name, trial, got, want)
+
+
+def _idiom_models():
+    """namespace-generic models exercising the tracer's operand forms beyond the benchmark workloads"""
+    x = np.linspace(-1, 1, 7).astype(np.float32)
+    y = (2 * x + 1 + 0.1 * np.cos(5 * x)).astype(np.float32)
+    t = np.array([0.3, 1.1, 0.2, 0.7], dtype=np.float32)
+
+    def affine(ns):       # OP_LIN location, fractional / negative weights, additive constant
+        def f(p):
+            mean = p["a"] + p["b"] * ns.mx.array(x) - 0.25
+            return (0.5 * ns.mx.sum(ns.Normal(mean, 2.0).log_prob(ns.mx.array(y)))
+                    - ns.Normal(0, 1).log_prob(p["a"]) * 2 + 3.0 + ns.Normal(1.0, 3.0).log_prob(p["b"]) / 4)
+        return f, {"a": 0.3, "b": -0.2}
+
+    def unrolled(ns):     # python loop over observations + parameter in the scale slot (examples/01:46-48)
+        def f(p):
+            lp = ns.HalfNormal(5.0).log_prob(p["s"]) + ns.Gamma(2.0, 1.5).log_prob(p["r"])
+            for ti in t:
+                lp = lp + ns.Exponential(p["r"]).log_prob(ns.mx.array(ti))
+            for yi in y[:3]:
+                lp += ns.Normal(0.5, p["s"]).log_prob(ns.mx.array(yi))
+            return lp
+        return f, {"s": 1.2, "r": 0.8}
+
+    def stacked(ns):      # mx.array([...traced scalars...]) summed (tests/test_nuts.py:205-207)
+        def f(p):
+            return (ns.mx.sum(ns.mx.array([ns.Normal(p["m"] * float(xi), 0.7).log_prob(ns.mx.array(yi)) for xi, yi in zip(x, y)]))
+                    + ns.Beta(2.0, 3.0).log_prob(p["q"]) + ns.Normal(p["m"], 2.0).log_prob(0.1))
+        return f, {"m": 0.4, "q": 0.35}
+
+    return {"affine": affine, "unrolled": unrolled, "stacked": stacked}
+
+
+@pytest.mark.parametrize("name", ["affine", "unrolled", "stacked"])
+def test_traced_idioms_keep_value_and_gradient(name):
+    from oracle.ns import ns as ons, value_and_grad
+    from table_eval import table_grad, table_logp
+    fn, init = _idiom_models()[name](B.ns)
+    fo, _ = _idiom_models()[name](ons)
+    model = trace(fn, init)
+    rng = np.random.default_rng(11)
+    for trial in range(3):
+        params = {k: float(v * (1.0 + 0.2 * trial * rng.uniform(-1, 1))) for k, v in init.items()}
+        lp64, g64 = value_and_grad(fo, params, "float64")
+        theta = np.array([params[k] for k in model.layout], dtype=np.float64)
+        want = np.array([float(g64[k]) for k in model.layout])
+        scale = max([1.0, abs(lp64)] + [abs(k) for t in model.terms for k in t.k])
+        assert abs(table_logp(model, theta) - lp64) <= 5e-7 * scale, (name, trial, table_logp(model, theta), lp64)
+        assert np.max(np.abs(table_grad(model, theta) - want)) <= 1e-5 * max(1.0, np.max(np.abs(want))), (name, trial)
