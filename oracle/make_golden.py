@@ -1,6 +1,7 @@
 """ORACLE / TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.json (run in the build container).
 
     python oracle/make_golden.py            # needs /root/reference (read-only) -- not available on the GPU box
+    python oracle/make_golden.py --check hmc_c2 nuts_c2 ...   # re-run the reference and compare with the committed files
 
 What it does
   1. imports the UNMODIFIED reference package from /root/reference on the mlx.core stand-in
@@ -144,7 +145,23 @@ def golden_run(model, method, kw):
             "draws": {k: tolist(v) for k, v in s_ref.items()}, "tape": tape_json(tape)}
 
 
+def check(names):
+    """Re-run the unmodified reference (and the restatement next to it) for the named run fixtures and compare with
+    the committed JSON: draws, acceptance rate and the recorded random draws must be identical."""
+    runs = {n: (m, meth, kw) for n, m, meth, kw in RUNS}
+    for name in names:
+        g = json.loads(json.dumps(golden_run(*runs[name])))
+        with open(os.path.join(OUT, f"{name}.json")) as f:
+            have = json.load(f)
+        for key in ("draws", "accept_rate", "final_step_size", "kwargs", "seed"):
+            assert g[key] == have[key], f"{name}: committed fixture differs from the reference in {key!r}"
+        assert g["tape"]["normals"] == have["tape"]["normals"] and g["tape"]["uniforms"] == have["tape"]["uniforms"], name
+        print(f"{name}: committed fixture reproduces")
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--check":
+        return check(sys.argv[2:])
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "logp_grad.json"), "w") as f:
         json.dump(golden_points(), f)
