@@ -32,7 +32,7 @@ extern "C" {
 
 /* ---- model description (produced by the Python tracer from the user's log_prob) ---- */
 
-/* distribution tags: the reference's six classes (mlx_mcmc/distributions/*.py) */
+/* distribution tags: the reference's six classes (mlx_mcmc/distributions/<name>.py) */
 enum {
   B2M_NORMAL = 0,      /* normal.py:49-56      p0=loc  p1=scale               */
   B2M_HALFNORMAL = 1,  /* halfnormal.py:55-63  p0=scale           mask x>=0   */
@@ -183,7 +183,7 @@ int b2m_abi_version(void);
 int b2m_struct_sizes(int32_t *out6); /* term, operand, lin_entry, hmc_args, mh_args, nuts_args */
 
 /* Build a model from the traced term table.  Replaces the user log_prob + Distribution.log_prob
- * bodies (distributions/*.py) as differentiated by grad_log_prob, kernels/hmc.py:53-67.
+ * bodies (distributions/<name>.py) as differentiated by grad_log_prob, kernels/hmc.py:53-67.
  * `arrays[i].data` must stay valid for the life of the model. */
 int b2m_model_create(const b2m_term *terms, int32_t n_terms, const b2m_lin_entry *lin, int32_t n_lin,
                      const b2m_array *arrays, int32_t n_arrays, int32_t D, b2m_model **out);
@@ -218,7 +218,7 @@ int b2m_model_set_comm(b2m_model *m, b2m_comm *c, void *stream); /* collective (
 int b2m_comm_allreduce_f32(b2m_comm *c, float *buf, int64_t n, void *stream);   /* in place, sum */
 
 /* ---- forward sampling on the device ----
- * n draws from one library distribution into out[n] (device).  Replaces Distribution.sample (distributions/*.py; the
+ * n draws from one library distribution into out[n] (device).  Replaces Distribution.sample (distributions/<name>.py; the
  * reference's Gamma / Beta fall back to numpy, gamma.py:107-117, beta.py:110-119).  dist = B2M_NORMAL (p0 loc, p1 scale),
  * B2M_HALFNORMAL (p0 scale), B2M_EXPONENTIAL (p0 rate), B2M_GAMMA (p0 alpha, p1 rate), B2M_BETA (p0 a, p1 b) or
  * B2M_SAMPLE_CATEGORICAL (cdf = device array of n_cat cumulative probabilities, last = 1; draws are indices as floats).

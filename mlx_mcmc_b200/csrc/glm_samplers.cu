@@ -869,9 +869,7 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   Arena real;
   real.base = gm.ws;
   nuts_layout(real, W, C, D, MD);
-  int *h_flag = gm.h_flag;
 
-  const unsigned grid = (unsigned)((C + WPB - 1) / WPB);
   const int T = 32 * WPB;
   B2M_CHECK_CUDA(cudaMemsetAsync(W.state, 0, sizeof(int) * C, st));
   B2M_CHECK_CUDA(cudaMemsetAsync(W.iter, 0, sizeof(int) * C, st));

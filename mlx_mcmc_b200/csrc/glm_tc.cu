@@ -42,7 +42,7 @@ constexpr int ROW_BYTES = 128;                        // one SWIZZLE_128B row of
 constexpr int MMA_K_BYTES = 32;                       // one MMA k-step: 8 tf32 or 16 fp16 values
 constexpr int A_TILE_BYTES = BLOCK_M * ROW_BYTES;     // 16 KB
 // elements of K per k-block (one swizzle row) for the two operand encodings
-template <bool F16> struct Enc { static constexpr int BLOCK_K = F16 ? 64 : 32; static constexpr int ELT = F16 ? 2 : 4; };
+template <bool F16> struct Enc { static constexpr int BLOCK_K = F16 ? 64 : 32; };
 constexpr int BLOCK_K = 32;                           // tf32 k-block (host-side helpers of the tf32 path)
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp, MMA warp, 8 promotion/epilogue warps
