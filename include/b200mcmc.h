@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B2M_ABI_VERSION 1
+#define B2M_ABI_VERSION 2
 #define B2M_MAX_TREE_DEPTH 12
 
 /* ---- model description (produced by the Python tracer from the user's log_prob) ---- */
@@ -83,6 +83,26 @@ typedef struct {
 
 typedef struct b2m_model b2m_model;
 
+/* Constraint transforms (the reference has none -- README.md:165,220, PROGRESS.md:119 list them as
+ * planned).  With transforms set, the samplers move in the UNCONSTRAINED coordinate u_d and the model sees
+ * theta_d = T_d(u_d); the log-Jacobian is added to log p and chained into the gradient.
+ *   B2M_TF_LOG    theta = exp(u)        (support x > 0: HalfNormal / Exponential / Gamma values)   log|J| = u
+ *   B2M_TF_LOGIT  theta = 1/(1+exp(-u)) (support 0 < x < 1: Beta values)                          log|J| = log theta + log(1-theta)
+ * `theta` / `step_size` state of the sampler calls is then unconstrained; `draws` are written constrained unless
+ * draws_unconstrained is set. */
+enum { B2M_TF_NONE = 0, B2M_TF_LOG = 1, B2M_TF_LOGIT = 2 };
+
+/* arithmetic of the two GLM contractions / evaluation path of pointwise models (were environment variables in ABI 1) */
+enum { B2M_GLM_AUTO = 0, B2M_GLM_SIMT = 1, B2M_GLM_TC = 2, B2M_GLM_TC16 = 3 };
+enum { B2M_POINTWISE_AUTO = 0, B2M_POINTWISE_GENERAL = 1 };
+
+typedef struct {
+  int32_t glm_path;          /* B2M_GLM_*: AUTO = tcgen05 3xFP16 when the data's dynamic range allows, else 3xTF32 */
+  int32_t pointwise_path;    /* B2M_POINTWISE_*: AUTO = compact (registers + constant bank) when the model allows */
+  const int32_t *transforms; /* HOST array [D] of B2M_TF_*, or NULL (= the reference: no transforms) */
+  int32_t reserved[4];       /* must be zero */
+} b2m_model_options;
+
 /* ---- sampler arguments ---- */
 
 enum {
@@ -94,6 +114,10 @@ enum {
                                    batch at one tree depth).  An extension: the reference has a single chain. */
 };
 enum { B2M_COMPAT_REFERENCE = 0, B2M_COMPAT_CORRECT = 1 };
+enum { B2M_SCHED_ASYNC = 0, B2M_SCHED_SYNC = 1 };
+/* B2M_SLICE_PEER: gradients travel through the peer window (b2m_model_peer_attach): K6's epilogue stores each finished
+ * tile into its owner's slot over NVLink, no collective on the critical path.  B2M_SLICE_NCCL: reduce-scatter + all-gather. */
+enum { B2M_SLICE_OFF = 0, B2M_SLICE_NCCL = 1, B2M_SLICE_PEER = 2 };
 
 /* Replaces hmc()'s warm-up and sampling loops, kernels/hmc.py:155-198, with hmc_step :113-153,
  * leapfrog_step :69-100, hamiltonian :102-111 and the +-5 % rule :164-170 inside one launch. */
@@ -117,6 +141,13 @@ typedef struct {
   const float *inj_uniform; /* [n_iter, n_chains]    accept uniforms, or NULL                 */
   float *trace_energy;      /* [n_iter, n_chains, 2] (H_init, H_prop) or NULL                 */
   uint8_t *trace_accept;    /* [n_iter, n_chains] or NULL                                     */
+  /* ABI 2 */
+  const float *inv_mass;    /* [D] diagonal of M^-1 shared by all chains (p ~ N(0, M), K = p'M^-1 p / 2, dq = eps M^-1 p),
+                               or NULL = identity (the reference, hmc.py:102-111) */
+  int32_t draws_unconstrained; /* models with transforms: write u instead of theta into `draws` (warm-up windows) */
+  int32_t _pad2;
+  int64_t adapt_origin;     /* dual averaging counts iterations from this global iteration (restart after a mass-matrix
+                               update); 0 = the reference's single run */
 } b2m_hmc_args;
 
 /* Replaces metropolis_hastings(), kernels/metropolis.py:6-101 (proposal :66-74, accept :77-88). */
@@ -173,6 +204,15 @@ typedef struct {
   const float *inj_merge;  /* [n_iter, n_chains, max_tree_depth, 2^max_tree_depth - 1] post-order merge slots */
   int32_t *trace_doubling; /* [n_iter, n_chains, max_tree_depth, 6] (v, n_sub, s_sub, took, s, n) or NULL */
   float *trace_energy;     /* [n_iter, n_chains] H0 or NULL */
+  /* ABI 2 (the first three were environment variables in ABI 1) */
+  const float *inv_mass;   /* [D] diagonal of M^-1 shared by all chains, or NULL = identity (the reference, nuts.py:113-117) */
+  int32_t schedule;        /* GLM class: B2M_SCHED_ASYNC (iteration-asynchronous lock-step) or B2M_SCHED_SYNC */
+  int32_t slice_state;     /* observation-sharded GLM models, adapt == NONE: rank r advances chains [r C/G, (r+1) C/G) only;
+                              per-chain outputs are written by the owner (callers merge them).  B2M_SLICE_* */
+  int32_t draws_unconstrained;
+  int32_t _pad2;
+  int64_t adapt_origin;    /* dual averaging (per chain or pooled) counts iterations from this global iteration: the
+                              recurrences of nuts.py:298-310 see m = iteration - adapt_origin.  0 = the reference */
 } b2m_nuts_args;
 
 /* ---- entry points ---- */
@@ -181,19 +221,21 @@ const char *b2m_last_error(void);
 int b2m_abi_version(void);
 /* sizeof of the structs above as compiled, so a binding can verify its mirror */
 int b2m_struct_sizes(int32_t *out6); /* term, operand, lin_entry, hmc_args, mh_args, nuts_args */
+int b2m_options_size(void);          /* sizeof(b2m_model_options) */
 
 /* Build a model from the traced term table.  Replaces the user log_prob + Distribution.log_prob
  * bodies (distributions/<name>.py) as differentiated by grad_log_prob, kernels/hmc.py:53-67.
  * `arrays[i].data` must stay valid for the life of the model. */
 int b2m_model_create(const b2m_term *terms, int32_t n_terms, const b2m_lin_entry *lin, int32_t n_lin,
-                     const b2m_array *arrays, int32_t n_arrays, int32_t D, b2m_model **out);
+                     const b2m_array *arrays, int32_t n_arrays, int32_t D, const b2m_model_options *opt /* or NULL */,
+                     b2m_model **out);
 void b2m_model_destroy(b2m_model *m);
 int b2m_model_dim(const b2m_model *m);
 /* 0 = pointwise class (persistent register-resident kernels), 1 = GLM class (X @ beta, GEMM kernels) */
 int b2m_model_class(const b2m_model *m);
 /* GLM class: arithmetic of the two contractions -- 0 fp32 FMA tiles, 1 tcgen05 3xTF32, 2 tcgen05 3xFP16 (operands scaled
  * by powers of two into fp16's range, chosen automatically unless the data's dynamic range is too wide); -1 otherwise.
- * The environment variable B2M_GLM_PATH = simt | tc | tc16 forces one. */
+ * b2m_model_options.glm_path forces one. */
 int b2m_model_glm_path(const b2m_model *m);
 
 /* log p(theta_c) and d/dtheta for C chains.  Replaces mx.grad(log_prob_flat)(*params) plus the
@@ -216,6 +258,33 @@ int b2m_comm_init(const uint8_t *id128, int32_t n_ranks, int32_t rank, b2m_comm 
 void b2m_comm_destroy(b2m_comm *c);
 int b2m_model_set_comm(b2m_model *m, b2m_comm *c, void *stream); /* collective (sums the shard row counts); c may be NULL */
 int b2m_comm_allreduce_f32(b2m_comm *c, float *buf, int64_t n, void *stream);   /* in place, sum */
+
+/* ---- peer window: the fused gradient exchange of observation sharding (B2M_SLICE_PEER) ----
+ * Every rank allocates one window of b2m_model_peer_bytes() bytes (b2m_peer_alloc: cudaMalloc + a 64-byte CUDA IPC
+ * handle), the handles travel over torch.distributed, every rank maps its peers' windows (b2m_peer_open) and hands the
+ * G device pointers -- its own included, indexed by rank -- to b2m_model_peer_attach.  From then on a NUTS call with
+ * slice_state = B2M_SLICE_PEER exchanges, per gradient, through plain NVLink stores:
+ *   owner  -> all : the packed fp16 hi/lo position rows of its chains + row scales  (state kernel)
+ *   all -> owner  : the [256, D] gradient tiles of the owner's chains, straight from K6's epilogue, and the sum z^2
+ * with per-source slots summed in rank order by the owner (deterministic) and release/acquire flags at system scope. */
+int b2m_peer_alloc(int64_t bytes, void **ptr, uint8_t *handle64);
+int b2m_peer_open(const uint8_t *handle64, void **ptr);
+int b2m_peer_close(void *ptr);
+int b2m_peer_free(void *ptr);
+int b2m_model_peer_bytes(b2m_model *m, int64_t n_chains, int32_t n_ranks, int64_t *bytes);
+int b2m_model_peer_attach(b2m_model *m, void *const *windows, int32_t n_ranks, int32_t rank, int64_t n_chains, int64_t bytes);
+
+/* ---- diagonal mass matrix from warm-up draws (reference roadmap README.md:165,220) ----
+ * draws [S, C, D] (unconstrained coordinates) -> inv_mass[d] = regularised pooled variance over all S x C draws of
+ * coordinate d around their grand mean:  v (n / (n + 5)) + 1e-3 (5 / (n + 5)), n = S x C  (Stan's shrinkage).
+ * Two kernels: per-(slice, d) float64 partial moments in fixed order, then a fixed-order fold: deterministic. */
+int b2m_mass_from_draws(const float *draws, int64_t S, int64_t C, int64_t D, float *inv_mass, void *stream);
+
+/* ---- order statistics on the device (MCMC.summary: np.median / np.percentile, inference/mcmc.py:221-224) ----
+ * x[n] float32 (device, not modified), q[n_q] in [0, 1] (host) -> out[n_q] (host) with numpy's default linear
+ * interpolation between the two neighbouring order statistics.  Three 11/11/10-bit radix-histogram passes over x select
+ * every requested order statistic at once (all n_q ranks share each pass). */
+int b2m_quantiles(const float *x, int64_t n, const double *q, int32_t n_q, double *out, void *stream);
 
 /* ---- forward sampling on the device ----
  * n draws from one library distribution into out[n] (device).  Replaces Distribution.sample (distributions/<name>.py; the

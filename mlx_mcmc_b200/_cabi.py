@@ -31,12 +31,18 @@ class Array(C.Structure):
     _fields_ = [("data", c_p), ("rows", C.c_int64), ("cols", C.c_int64)]
 
 
+class ModelOptions(C.Structure):
+    _fields_ = [("glm_path", C.c_int32), ("pointwise_path", C.c_int32), ("transforms", C.POINTER(C.c_int32)),
+                ("reserved", C.c_int32 * 4)]
+
+
 class HmcArgs(C.Structure):
     _fields_ = [("n_chains", C.c_int64), ("chain_offset", C.c_int64), ("iter_offset", C.c_int64),
                 ("n_iter", C.c_int32), ("n_leapfrog", C.c_int32), ("adapt", C.c_int32), ("lanes", C.c_int32),
                 ("target_accept", C.c_double), ("seed", C.c_uint64),
                 ("theta", c_p), ("step_size", c_p), ("n_accept", c_p), ("n_total", c_p), ("da_state", c_p),
-                ("draws", c_p), ("inj_normal", c_p), ("inj_uniform", c_p), ("trace_energy", c_p), ("trace_accept", c_p)]
+                ("draws", c_p), ("inj_normal", c_p), ("inj_uniform", c_p), ("trace_energy", c_p), ("trace_accept", c_p),
+                ("inv_mass", c_p), ("draws_unconstrained", C.c_int32), ("_pad2", C.c_int32), ("adapt_origin", C.c_int64)]
 
 
 class MhArgs(C.Structure):
@@ -54,18 +60,28 @@ class NutsArgs(C.Structure):
                 ("theta", c_p), ("step_size", c_p), ("da_state", c_p), ("n_accept", c_p), ("n_leaves", c_p),
                 ("n_diverge", c_p), ("draws", c_p), ("depths", c_p), ("alphas", c_p),
                 ("inj_normal", c_p), ("inj_slice", c_p), ("inj_dir", c_p), ("inj_take", c_p), ("inj_merge", c_p),
-                ("trace_doubling", c_p), ("trace_energy", c_p)]
+                ("trace_doubling", c_p), ("trace_energy", c_p),
+                ("inv_mass", c_p), ("schedule", C.c_int32), ("slice_state", C.c_int32),
+                ("draws_unconstrained", C.c_int32), ("_pad2", C.c_int32), ("adapt_origin", C.c_int64)]
 
 
 ADAPT_NONE, ADAPT_REFERENCE, ADAPT_DUAL_AVERAGING, ADAPT_POOLED = 0, 1, 2, 3
 COMPAT_REFERENCE, COMPAT_CORRECT = 0, 1
+SCHED_ASYNC, SCHED_SYNC = 0, 1
+SLICE_OFF, SLICE_NCCL, SLICE_PEER = 0, 1, 2
+TF_NONE, TF_LOG, TF_LOGIT = 0, 1, 2
+GLM_AUTO, GLM_SIMT, GLM_TC, GLM_TC16 = 0, 1, 2, 3
+GLM_PATHS = {"auto": GLM_AUTO, "simt": GLM_SIMT, "tc": GLM_TC, "tc16": GLM_TC16}
+POINTWISE_AUTO, POINTWISE_GENERAL = 0, 1
 MAX_TREE_DEPTH = 12
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = ["b2m_last_error", "b2m_abi_version", "b2m_struct_sizes", "b2m_model_create", "b2m_model_destroy",
            "b2m_model_dim", "b2m_model_class", "b2m_model_glm_path", "b2m_logp_grad", "b2m_hmc_run", "b2m_mh_run", "b2m_nuts_run",
            "b2m_launch_count", "b2m_comm_unique_id", "b2m_comm_init", "b2m_comm_destroy", "b2m_model_set_comm",
-           "b2m_comm_allreduce_f32", "b2m_profile", "b2m_profile_read", "b2m_diag_series", "b2m_diag_params", "b2m_sample"]
+           "b2m_comm_allreduce_f32", "b2m_profile", "b2m_profile_read", "b2m_diag_series", "b2m_diag_params", "b2m_sample",
+           "b2m_options_size", "b2m_peer_alloc", "b2m_peer_open", "b2m_peer_close", "b2m_peer_free", "b2m_model_peer_bytes",
+           "b2m_model_peer_attach", "b2m_mass_from_draws", "b2m_quantiles"]
 
 _lib = None
 
@@ -88,9 +104,10 @@ def load(build_if_missing: bool = True):
     if build_if_missing and not _build.is_current():
         try:
             _build.build()
-        except Exception as e:  # no nvcc on this box: fall through to whatever was shipped
-            if not os.path.exists(path):
-                raise ImportError(f"libb200mcmc.so is not built and could not be built here: {e}") from e
+        except Exception as e:
+            # A library that does not match the checked-in sources must never run silently: parity claims refer to the
+            # sources.  (A box without nvcc gets the library from the snapshot, built and stamped where the sources were.)
+            raise ImportError(f"libb200mcmc.so is missing or older than its sources and could not be rebuilt here: {e}") from e
     if not os.path.exists(path):
         raise ImportError(f"{path} not found; run `python -m mlx_mcmc_b200.build` (needs nvcc)")
     lib = C.CDLL(path)
@@ -99,7 +116,15 @@ def load(build_if_missing: bool = True):
     lib.b2m_launch_count.restype = C.c_int64
     lib.b2m_struct_sizes.argtypes = [C.POINTER(C.c_int32)]
     lib.b2m_model_create.argtypes = [C.POINTER(Term), C.c_int32, C.POINTER(LinEntry), C.c_int32,
-                                     C.POINTER(Array), C.c_int32, C.c_int32, C.POINTER(c_p)]
+                                     C.POINTER(Array), C.c_int32, C.c_int32, C.POINTER(ModelOptions), C.POINTER(c_p)]
+    lib.b2m_peer_alloc.argtypes = [C.c_int64, C.POINTER(c_p), c_p]
+    lib.b2m_peer_open.argtypes = [c_p, C.POINTER(c_p)]
+    lib.b2m_peer_close.argtypes = [c_p]
+    lib.b2m_peer_free.argtypes = [c_p]
+    lib.b2m_model_peer_bytes.argtypes = [c_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]
+    lib.b2m_model_peer_attach.argtypes = [c_p, C.POINTER(c_p), C.c_int32, C.c_int32, C.c_int64, C.c_int64]
+    lib.b2m_mass_from_draws.argtypes = [c_p, C.c_int64, C.c_int64, C.c_int64, c_p, c_p]
+    lib.b2m_quantiles.argtypes = [c_p, C.c_int64, C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double), c_p]
     lib.b2m_model_destroy.argtypes = [c_p]
     lib.b2m_model_destroy.restype = None
     lib.b2m_model_dim.argtypes = [c_p]
@@ -127,6 +152,8 @@ def load(build_if_missing: bool = True):
     mine = [C.sizeof(Term), C.sizeof(Operand), C.sizeof(LinEntry), C.sizeof(HmcArgs), C.sizeof(MhArgs), C.sizeof(NutsArgs)]
     if list(sizes) != mine:
         raise ImportError(f"struct layout mismatch: library {list(sizes)} vs ctypes mirror {mine}")
+    if lib.b2m_options_size() != C.sizeof(ModelOptions):
+        raise ImportError(f"b2m_model_options layout mismatch: library {lib.b2m_options_size()} vs {C.sizeof(ModelOptions)}")
     _lib = lib
     return lib
 

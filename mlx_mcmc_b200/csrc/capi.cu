@@ -19,7 +19,14 @@ int launch_logp_grad(const KModel &km, const float *theta, int64_t C, float *log
 int launch_hmc(const KModel &km, b2m_hmc_args a, cudaStream_t st);
 int launch_mh(const KModel &km, b2m_mh_args a, cudaStream_t st);
 int launch_nuts(const KModel &km, b2m_nuts_args a, cudaStream_t st);
-int glm_build(GlmModel &g, const float *X, const float *y, int N, int D);
+int glm_build(GlmModel &g, const float *X, const float *y, int N, int D, bool force_tc16);
+int mass_from_draws(const float *draws, int64_t S, int64_t C, int64_t D, float *inv_mass, cudaStream_t st);
+int quantiles(const float *x, int64_t n, const double *q, int n_q, double *out, cudaStream_t st);
+int peer_alloc(int64_t bytes, void **ptr, uint8_t *handle64);
+int peer_open(const uint8_t *handle64, void **ptr);
+int peer_close(void *ptr);
+int peer_free(void *ptr);
+int glm_peer_attach(GlmModel &g, void *const *windows, int n_ranks, int rank, int64_t n_chains, int64_t bytes);
 int debug_tc_gemm(const float *A, const float *Bm, int M, int N, int K, float *Cout, int chunk_kb, int mma_mask,
                   cudaStream_t st);
 
@@ -78,7 +85,7 @@ static int check_operand(const b2m_operand &o, int length, int D, int n_lin, con
 
 // GLM class: exactly one Normal likelihood whose location is X @ beta (+ const), observed y, scale constant or
 // a scalar parameter; every other term is a pointwise prior.
-static int setup_glm(b2m_model *m, int D) {
+static int setup_glm(b2m_model *m, int D, int glm_path, const int32_t *tf) {
   int lik = -1;
   for (size_t t = 0; t < m->terms.size(); ++t) {
     const b2m_term &T = m->terms[t];
@@ -103,12 +110,18 @@ static int setup_glm(b2m_model *m, int D) {
   g.weight = L.weight;
   g.sigma_param = L.p1.kind == B2M_OP_PARAM ? L.p1.a : -1;
   g.sigma_const = L.p1.kind == B2M_OP_CONST ? L.p1.c : 1.f;
-  // B2M_GLM_PATH: simt (fp32 FMA tiles) | tc (tcgen05 3xTF32) | tc16 (tcgen05 3xFP16 with scaled operands);
-  // default: the fp16 encoding when the data's dynamic range allows it (checked in glm_build), else tf32
-  const char *path = getenv("B2M_GLM_PATH");
-  const std::string want = path ? path : "auto";
-  g.use_tc = (!b2m::tc_available() || want == "simt") ? 0 : (want == "tc" ? 1 : 2);
-  if (int rc = b2m::glm_build(g, X.data, Y.data, (int)L.length, (int)X.cols)) return rc;
+  // b2m_model_options.glm_path: SIMT (fp32 FMA tiles) | TC (tcgen05 3xTF32) | TC16 (tcgen05 3xFP16 with scaled operands);
+  // AUTO: the fp16 encoding when the data's dynamic range allows it (checked in glm_build), else tf32
+  g.use_tc = (!b2m::tc_available() || glm_path == B2M_GLM_SIMT) ? 0 : (glm_path == B2M_GLM_TC ? 1 : 2);
+  if (tf) {   // constraint transforms: device copy of the per-parameter codes (before any workspace is reserved)
+    bool any = false;
+    for (int d = 0; d < D; ++d) any = any || tf[d] != B2M_TF_NONE;
+    if (any) {
+      B2M_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(&g.tf), sizeof(int) * D));
+      B2M_CHECK_CUDA(cudaMemcpy(g.tf, tf, sizeof(int) * D, cudaMemcpyHostToDevice));
+    }
+  }
+  if (int rc = b2m::glm_build(g, X.data, Y.data, (int)L.length, (int)X.cols, glm_path == B2M_GLM_TC16)) return rc;
   // prior = all other terms
   std::vector<b2m_term> prior;
   for (size_t t = 0; t < m->terms.size(); ++t)
@@ -187,10 +200,21 @@ int b2m_struct_sizes(int32_t *out6) {
   return 0;
 }
 
+int b2m_options_size(void) { return (int)sizeof(b2m_model_options); }
+
 int b2m_model_create(const b2m_term *terms, int32_t n_terms, const b2m_lin_entry *lin, int32_t n_lin,
-                     const b2m_array *arrays, int32_t n_arrays, int32_t D, b2m_model **out) {
+                     const b2m_array *arrays, int32_t n_arrays, int32_t D, const b2m_model_options *opt, b2m_model **out) {
   B2M_REQUIRE(out != nullptr, "b2m_model_create: out is NULL");
   *out = nullptr;
+  b2m_model_options o{};
+  if (opt) o = *opt;
+  B2M_REQUIRE(o.glm_path >= B2M_GLM_AUTO && o.glm_path <= B2M_GLM_TC16, "b2m_model_create: unknown glm_path");
+  B2M_REQUIRE(o.pointwise_path == B2M_POINTWISE_AUTO || o.pointwise_path == B2M_POINTWISE_GENERAL,
+              "b2m_model_create: unknown pointwise_path");
+  for (int i = 0; i < 4; ++i) B2M_REQUIRE(o.reserved[i] == 0, "b2m_model_create: reserved option fields must be zero");
+  if (o.transforms)
+    for (int d = 0; d < D; ++d)
+      B2M_REQUIRE(o.transforms[d] >= B2M_TF_NONE && o.transforms[d] <= B2M_TF_LOGIT, "b2m_model_create: unknown transform code");
   B2M_REQUIRE(n_terms > 0 && n_terms <= 256, "b2m_model_create: need 1..256 terms");
   B2M_REQUIRE(D > 0, "b2m_model_create: D must be positive");
   B2M_REQUIRE(n_lin >= 0 && n_arrays >= 0, "b2m_model_create: negative table size");
@@ -250,15 +274,28 @@ int b2m_model_create(const b2m_term *terms, int32_t n_terms, const b2m_lin_entry
   bool compact = n_terms <= b2m::kCompactTerms && D <= b2m::kCompactDim && n_matvec == 0;
   for (int t = 0; t < n_terms && compact; ++t)
     compact = terms[t].x.kind != B2M_OP_LIN && terms[t].p0.kind != B2M_OP_LIN && terms[t].p1.kind != B2M_OP_LIN;
-  const char *force = getenv("B2M_POINTWISE_PATH");
-  if (force && std::string(force) == "general") compact = false;
+  if (o.pointwise_path == B2M_POINTWISE_GENERAL) compact = false;
   m->km.compact = compact ? 1 : 0;
+  m->km.has_tf = 0;
+  memset(m->km.tf, 0, sizeof(m->km.tf));
+  if (o.transforms && n_matvec == 0) {
+    for (int d = 0; d < D; ++d)
+      if (o.transforms[d] != B2M_TF_NONE) {
+        if (d >= 16) {
+          set_error("constraint transforms: pointwise models support at most 16 scalar parameters");
+          b2m_model_destroy(m);
+          return 1;
+        }
+        m->km.tf[d] = (uint8_t)o.transforms[d];
+        m->km.has_tf = 1;
+      }
+  }
   memset(m->km.cterms, 0, sizeof(m->km.cterms));
   if (compact) memcpy(m->km.cterms, terms, sizeof(b2m_term) * n_terms);
   // observation vectors are staged in shared memory when they fit beside the mailboxes
   m->km.stage_floats = (stage * 4 <= 96 * 1024) ? (int32_t)stage : 0;
   if (m->model_class == 1) {
-    if (int rc = setup_glm(m, D)) {
+    if (int rc = setup_glm(m, D, o.glm_path, o.transforms)) {
       b2m_model_destroy(m);
       return rc;
     }
@@ -327,6 +364,53 @@ int b2m_comm_allreduce_f32(b2m_comm *c, float *buf, int64_t n, void *stream) {
   return b2m::comm_allreduce_f32(c->c, buf, n, static_cast<cudaStream_t>(stream));
 }
 
+int b2m_peer_alloc(int64_t bytes, void **ptr, uint8_t *handle64) {
+  B2M_REQUIRE(bytes > 0 && ptr && handle64, "b2m_peer_alloc: bad argument");
+  return b2m::peer_alloc(bytes, ptr, handle64);
+}
+int b2m_peer_open(const uint8_t *handle64, void **ptr) {
+  B2M_REQUIRE(handle64 && ptr, "b2m_peer_open: NULL argument");
+  return b2m::peer_open(handle64, ptr);
+}
+int b2m_peer_close(void *ptr) { return ptr ? b2m::peer_close(ptr) : 0; }
+int b2m_peer_free(void *ptr) { return ptr ? b2m::peer_free(ptr) : 0; }
+
+int b2m_model_peer_bytes(b2m_model *m, int64_t n_chains, int32_t n_ranks, int64_t *bytes) {
+  B2M_REQUIRE(m && bytes, "b2m_model_peer_bytes: NULL argument");
+  B2M_REQUIRE(m->model_class == 1, "b2m_model_peer_bytes: the peer window is defined for GLM-class models only");
+  B2M_REQUIRE(n_ranks >= 2 && n_ranks <= b2m::kMaxPeers, "b2m_model_peer_bytes: 2..8 ranks");
+  B2M_REQUIRE(n_chains > 0 && n_chains % (128 * (int64_t)n_ranks) == 0 && n_chains % 256 == 0,
+              "b2m_model_peer_bytes: n_chains must be a multiple of 256 and of 128 x the number of ranks");
+  b2m::PeerWindow w;
+  *bytes = (int64_t)b2m::peer_layout(w, n_chains, n_ranks, m->glm.Dp);
+  return 0;
+}
+
+int b2m_model_peer_attach(b2m_model *m, void *const *windows, int32_t n_ranks, int32_t rank, int64_t n_chains, int64_t bytes) {
+  B2M_REQUIRE(m && windows, "b2m_model_peer_attach: NULL argument");
+  B2M_REQUIRE(m->model_class == 1, "b2m_model_peer_attach: the peer window is defined for GLM-class models only");
+  B2M_REQUIRE(m->glm.use_tc == 2, "b2m_model_peer_attach: the peer exchange is built on the fp16-encoded tcgen05 path");
+  B2M_REQUIRE(m->glm.tf == nullptr, "b2m_model_peer_attach: constraint transforms are not supported with the peer exchange");
+  B2M_REQUIRE(n_ranks >= 2 && n_ranks <= b2m::kMaxPeers && rank >= 0 && rank < n_ranks, "b2m_model_peer_attach: 2..8 ranks");
+  B2M_REQUIRE(n_chains > 0 && n_chains % (128 * (int64_t)n_ranks) == 0 && n_chains % 256 == 0,
+              "b2m_model_peer_attach: n_chains must be a multiple of 256 and of 128 x the number of ranks");
+  for (int s = 0; s < n_ranks; ++s) B2M_REQUIRE(windows[s] != nullptr, "b2m_model_peer_attach: NULL window");
+  return b2m::glm_peer_attach(m->glm, windows, n_ranks, rank, n_chains, bytes);
+}
+
+int b2m_mass_from_draws(const float *draws, int64_t S, int64_t C, int64_t D, float *inv_mass, void *stream) {
+  B2M_REQUIRE(draws && inv_mass, "b2m_mass_from_draws: NULL argument");
+  B2M_REQUIRE(S > 0 && C > 0 && D > 0, "b2m_mass_from_draws: sizes must be positive");
+  return b2m::mass_from_draws(draws, S, C, D, inv_mass, static_cast<cudaStream_t>(stream));
+}
+
+int b2m_quantiles(const float *x, int64_t n, const double *q, int32_t n_q, double *out, void *stream) {
+  B2M_REQUIRE(x && q && out, "b2m_quantiles: NULL argument");
+  B2M_REQUIRE(n > 0 && n_q > 0 && n_q <= 8, "b2m_quantiles: need n > 0 and 1..8 quantiles");
+  for (int i = 0; i < n_q; ++i) B2M_REQUIRE(q[i] >= 0.0 && q[i] <= 1.0, "b2m_quantiles: quantiles must lie in [0, 1]");
+  return b2m::quantiles(x, n, q, n_q, out, static_cast<cudaStream_t>(stream));
+}
+
 int b2m_hmc_run(b2m_model *m, const b2m_hmc_args *a, void *stream) {
   B2M_REQUIRE(m && a, "b2m_hmc_run: NULL argument");
   B2M_REQUIRE(a->n_chains > 0 && a->n_iter >= 0 && a->n_leapfrog > 0, "b2m_hmc_run: bad sizes");
@@ -360,6 +444,11 @@ int b2m_nuts_run(b2m_model *m, const b2m_nuts_args *a, void *stream) {
               "b2m_nuts_run: bad adapt mode");
   B2M_REQUIRE(a->adapt != B2M_ADAPT_POOLED || m->model_class == 1,
               "b2m_nuts_run: pooled step-size adaptation needs a GLM-class model (lock-step kernels)");
+  B2M_REQUIRE(a->schedule == B2M_SCHED_ASYNC || a->schedule == B2M_SCHED_SYNC, "b2m_nuts_run: unknown schedule");
+  B2M_REQUIRE(a->slice_state >= B2M_SLICE_OFF && a->slice_state <= B2M_SLICE_PEER, "b2m_nuts_run: unknown slice_state");
+  B2M_REQUIRE(a->slice_state == B2M_SLICE_OFF || (m->model_class == 1 && m->glm.comm && a->adapt == B2M_ADAPT_NONE &&
+                                                   a->schedule == B2M_SCHED_ASYNC),
+              "b2m_nuts_run: slice_state needs an observation-sharded GLM-class model, the asynchronous schedule and no adaptation");
   if (a->n_iter == 0) return 0;
   if (m->model_class == 1) return b2m::glm_nuts_run(m->glm, *a, static_cast<cudaStream_t>(stream));
   return b2m::launch_nuts(m->km, *a, static_cast<cudaStream_t>(stream));

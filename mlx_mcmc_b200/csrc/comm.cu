@@ -142,4 +142,77 @@ int comm_allreduce_i64(Comm *c, int64_t *buf, int64_t n, cudaStream_t st) {
   return 0;
 }
 
+// ---------------------------------------------------------------- peer window (B2M_SLICE_PEER)
+// One cudaMalloc'd window per rank, shared with the other ranks of the box through CUDA IPC handles (the handles
+// travel over torch.distributed; include/b200mcmc.h).  All traffic through it is plain NVLink stores from the state
+// kernel (packed rows) and from K6's epilogue (gradient tiles), ordered by release / acquire flags at system scope.
+size_t peer_layout(PeerWindow &w, int64_t C, int nranks, int Dp) {
+  auto up = [](size_t x) { return (x + 1023) & ~size_t(1023); };
+  w.C = C; w.nranks = nranks; w.own = C / nranks; w.Dp = Dp;
+  size_t o = 0;
+  w.off_g = o;     o = up(o + sizeof(float) * (size_t)C * Dp);
+  w.off_ss = o;    o = up(o + sizeof(float) * (size_t)C);
+  w.off_bh = o;    o = up(o + sizeof(__half) * (size_t)C * Dp);
+  w.off_bl = o;    o = up(o + sizeof(__half) * (size_t)C * Dp);
+  w.off_meta = o;  o = up(o + sizeof(float4) * (size_t)C);
+  w.off_bflag = o; o = up(o + sizeof(uint64_t) * kMaxPeers);
+  w.off_gflag = o; o = up(o + sizeof(uint64_t) * kMaxPeers);
+  w.off_done = o;  o = up(o + sizeof(int64_t) * kMaxPeers);
+  w.off_err = o;   o = up(o + sizeof(int) * 4);
+  w.bytes = o;
+  return o;
+}
+
+int peer_alloc(int64_t bytes, void **ptr, uint8_t *handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  void *p = nullptr;
+  B2M_CHECK_CUDA(cudaMalloc(&p, (size_t)bytes));
+  B2M_CHECK_CUDA(cudaMemset(p, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    return 2;
+  }
+  memcpy(handle64, &h, 64);
+  B2M_CHECK_CUDA(cudaDeviceSynchronize());
+  *ptr = p;
+  return 0;
+}
+
+int peer_open(const uint8_t *handle64, void **ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  B2M_CHECK_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int peer_close(void *ptr) {
+  B2M_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+int peer_free(void *ptr) {
+  B2M_CHECK_CUDA(cudaFree(ptr));
+  return 0;
+}
+
+int glm_peer_attach(GlmModel &g, void *const *windows, int n_ranks, int rank, int64_t n_chains, int64_t bytes) {
+  B2M_REQUIRE(g.comm && comm_nranks(g.comm) == n_ranks && comm_rank(g.comm) == rank,
+              "peer window: attach the NCCL communicator (b2m_model_set_comm) first; ranks must agree");
+  PeerWindow w;
+  const size_t need = peer_layout(w, n_chains, n_ranks, g.Dp);
+  B2M_REQUIRE((size_t)bytes >= need, "peer window: the window is smaller than b2m_model_peer_bytes()");
+  w.rank = rank;
+  for (int s = 0; s < n_ranks; ++s) w.base[s] = static_cast<char *>(windows[s]);
+  w.seq = 0;
+  g.pw = w;
+  if (!g.blk_counter) {
+    B2M_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(&g.blk_counter), sizeof(unsigned) * 8));
+    B2M_CHECK_CUDA(cudaMemset(g.blk_counter, 0, sizeof(unsigned) * 8));
+  }
+  return 0;
+}
+
 }  // namespace b2m

@@ -1,5 +1,5 @@
 // GLM-class evaluation pipeline: pack -> GEMM (B X^T) with residual epilogue -> GEMM (R X) -> finish.
-#include "glm.cuh"
+#include "glm_rows.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -21,6 +21,7 @@ static int dev_alloc(T **p, size_t n) {
 static void free_workspace(GlmModel &g) {
   FREE(g.B); FREE(g.Bh); FREE(g.Bl); FREE(g.R); FREE(g.Rh); FREE(g.Rl); FREE(g.G); FREE(g.ss_part); FREE(g.inv_var);
   FREE(g.red); FREE(g.B16h); FREE(g.B16l); FREE(g.R16h); FREE(g.R16l); FREE(g.a_unscale); FREE(g.r_scale); FREE(g.r_unscale);
+  FREE(g.thc);
   g.cap = 0;
 }
 
@@ -30,9 +31,12 @@ void glm_free(GlmModel &g) {
   FREE(g.y0); FREE(g.beta0); FREE(g.center_part);
   FREE(g.X16h); FREE(g.X16l); FREE(g.XT16h); FREE(g.XT16l); FREE(g.col_scale); FREE(g.inv_col_scale); FREE(g.y0max_bits);
   FREE(g.ws);
+  FREE(g.tf); FREE(g.blk_counter);
   g.ws_cap = 0;
   if (g.h_flag) cudaFreeHost(g.h_flag);
   g.h_flag = nullptr;
+  if (g.h_prog) cudaFreeHost(const_cast<long long *>(g.h_prog));
+  g.h_prog = nullptr;
 }
 
 int glm_reserve(GlmModel &g, int64_t n_chains) {
@@ -50,6 +54,7 @@ int glm_reserve(GlmModel &g, int64_t n_chains) {
   if (dev_alloc(&g.B, cp * g.Dp) || dev_alloc(&g.G, g_rows * g.Dp) || dev_alloc(&g.ss_part, (size_t)(g.Np / 64) * cp) ||
       dev_alloc(&g.inv_var, cp) || dev_alloc(&g.red, (size_t)cp * g.Dp + cp))
     return 2;
+  if (g.tf && dev_alloc(&g.thc, (size_t)cp * g.Dtot)) return 2;
   if (g.use_tc == 0 && dev_alloc(&g.R, cp * (size_t)g.Np)) return 2;
   if (g.use_tc == 1) {
     if (dev_alloc(&g.Bh, cp * g.Dp) || dev_alloc(&g.Bl, cp * g.Dp) || dev_alloc(&g.Rh, cp * (size_t)g.Np) ||
@@ -123,28 +128,12 @@ __global__ void __launch_bounds__(256) x_small_count_kernel(const float *__restr
   if (cnt) atomicAdd(small + d, cnt);
 }
 
-// power-of-two scale that puts a maximum of `m` just below 2^14 (fp16 overflows at 65504 = 2^16 - 32)
-__host__ __device__ inline float pow2_scale(float m) {
-  if (!(m > 0.f) || !(m < 3.0e38f)) return 1.0f;
-  int e;
-  frexpf(m, &e);                 // m = f * 2^e, f in [0.5, 1)  =>  m < 2^e
-  int k = 14 - e;
-  if (k > 100) k = 100;
-  if (k < -100) k = -100;
-  return ldexpf(1.0f, k);
-}
-
 __global__ void col_scale_kernel(const unsigned *__restrict__ colmax_bits, int Dp, float *col_scale, float *inv_col_scale) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= Dp) return;
   const float s = pow2_scale(__uint_as_float(colmax_bits[d]));
   col_scale[d] = s;
   inv_col_scale[d] = 1.0f / s;
-}
-
-__device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo) {
-  hi = __float2half_rn(v);
-  lo = __float2half_rn(v - __half2float(hi));
 }
 
 __global__ void split_f16_kernel(const float *__restrict__ Xp, int Np, int Dp, const float *__restrict__ col_scale,
@@ -158,7 +147,7 @@ __global__ void split_f16_kernel(const float *__restrict__ Xp, int Np, int Dp, c
   XTh[(int64_t)d * Np + n] = hi; XTl[(int64_t)d * Np + n] = lo;
 }
 
-int glm_build(GlmModel &g, const float *X, const float *y, int N, int D) {
+int glm_build(GlmModel &g, const float *X, const float *y, int N, int D, bool force_tc16) {
   g.N = N; g.D = D;
   g.N_total = N;
   g.Np = (N + 255) / 256 * 256;
@@ -191,8 +180,7 @@ int glm_build(GlmModel &g, const float *X, const float *y, int N, int D) {
       if (!(m < 3.0e38f)) ok = false;                                  // inf / NaN in the data
       if ((double)hmax[g.Dp + 1 + d] > 1e-3 * (double)(N > 0 ? N : 1)) ok = false;
     }
-    const char *force = getenv("B2M_GLM_PATH");
-    if (!ok && !(force && std::string(force) == "tc16")) g.use_tc = 1;   // wide-range data: tf32 encoding
+    if (!ok && !force_tc16) g.use_tc = 1;   // wide-range data: tf32 encoding
     if (g.use_tc == 2) {
       if (dev_alloc(&g.X16h, nd) || dev_alloc(&g.X16l, nd) || dev_alloc(&g.XT16h, nd) || dev_alloc(&g.XT16l, nd) ||
           dev_alloc(&g.col_scale, g.Dp) || dev_alloc(&g.inv_col_scale, g.Dp))
@@ -318,53 +306,37 @@ __global__ void glm_pack_kernel(const float *__restrict__ theta, const float *__
   }
 }
 
-// fp16 encoding of the A operand of K5, one warp per chain row:
-//   delta'_d = (beta_d - beta0_d) / col_scale_d          (X' = X col_scale, so delta' . X' = delta . X exactly)
-//   row scale s_a = 2^k putting max_d |delta'_d| just below 2^14; hi / lo halves of delta' s_a
-// and the row scale of the residual operand of K6 from a bound that is known before K5 runs:
-//   |z_n| = |y0_n - (X delta)_n| <= max|y0| + ||delta||_2 max_n ||X_n||_2      (Cauchy-Schwarz)
-__global__ void __launch_bounds__(128) glm_pack16_kernel(const float *__restrict__ theta, const float *__restrict__ beta0,
-                                                         const int *__restrict__ idx, int64_t C, int64_t Cp, int Dtot,
-                                                         int beta_off, int D, int Dp, int sigma_param, float sigma_const,
-                                                         float weight, const float *__restrict__ inv_col_scale,
-                                                         const unsigned *__restrict__ y0max_bits, float x_rownorm_max,
-                                                         __half *Bh, __half *Bl, float *inv_var, float *a_unscale,
-                                                         float *r_scale, float *r_unscale) {
+// fp16 encoding of the A operand of K5, one warp per batch row (body: pack16_row, glm_rows.cuh)
+__global__ void __launch_bounds__(128) glm_pack16_kernel(PackP P, const float *__restrict__ theta,
+                                                         const int *__restrict__ idx, int64_t C, int64_t Cp) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= Cp) return;
-  const bool live = row < C;
-  const int64_t c = (live && idx) ? idx[row] : row;
-  float amax = 0.f, n2 = 0.f;
-  if (live)
-    for (int d = lane; d < D; d += 32) {
-      const float dl = __fsub_rn(theta[c * Dtot + beta_off + d], beta0[d]);
-      amax = fmaxf(amax, fabsf(dl * inv_col_scale[d]));
-      n2 = fmaf(dl, dl, n2);
-    }
-  for (int o = 16; o > 0; o >>= 1) {
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-  }
-  const float sa = pow2_scale(amax);
-  for (int d = lane; d < Dp; d += 32) {
-    float v = 0.f;
-    if (live && d < D) v = __fsub_rn(theta[c * Dtot + beta_off + d], beta0[d]) * inv_col_scale[d] * sa;
-    __half hi, lo;
-    split_f16(v, hi, lo);
-    Bh[row * Dp + d] = hi;
-    Bl[row * Dp + d] = lo;
-  }
-  if (lane == 0) {
-    const float sg = (live && sigma_param >= 0) ? theta[c * Dtot + sigma_param] : sigma_const;
-    const float iv = 1.0f / (sg * sg);
-    inv_var[row] = iv;
-    const float bound = (__uint_as_float(*y0max_bits) + sqrtf(n2) * x_rownorm_max) * fabsf(iv * weight);
-    const float sr = pow2_scale(bound);
-    a_unscale[row] = 1.0f / sa;
-    r_scale[row] = sr;
-    r_unscale[row] = 1.0f / sr;
-  }
+  const int64_t c = (row < C && idx) ? idx[row] : row;
+  pack16_row(P, row < C ? theta + c * P.Dtot : nullptr, row, lane);
+}
+
+// models with constraint transforms on the fp32 / tf32 paths: thc[row] = T(theta[chain of row])
+__global__ void glm_constrain_kernel(const float *__restrict__ theta, const int *__restrict__ idx, const int *__restrict__ tf,
+                                     int64_t C, int Dtot, float *__restrict__ thc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * Dtot) return;
+  const int64_t row = i / Dtot;
+  const int d = int(i % Dtot);
+  const int64_t c = idx ? idx[row] : row;
+  thc[i] = tf_constrain(tf[d], theta[c * Dtot + d]);
+}
+
+PackP make_pack(const GlmModel &g) {
+  PackP P{};
+  P.beta0 = g.beta0; P.tf = g.tf; P.thc = g.thc;
+  P.Dtot = g.Dtot; P.beta_off = g.beta_off; P.D = g.D; P.Dp = g.Dp; P.sigma_param = g.sigma_param;
+  P.sigma_const = g.sigma_const; P.weight = g.weight;
+  P.inv_col_scale = g.inv_col_scale; P.y0max_bits = g.y0max_bits; P.x_rownorm_max = g.x_rownorm_max;
+  P.Bh = g.B16h; P.Bl = g.B16l;
+  P.inv_var = g.inv_var; P.a_unscale = g.a_unscale; P.r_scale = g.r_scale; P.r_unscale = g.r_unscale;
+  P.n_peers = 0;
+  return P;
 }
 
 // ---------------------------------------------------------------- SIMT contractions (fp32, 64x64x16 tiles)
@@ -490,135 +462,47 @@ int glm_set_comm(GlmModel &g, Comm *c, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------- finish: assemble log p and the full gradient
-// One warp per chain.  Likelihood value from the partial sums (fixed summation order => deterministic),
-// gradient of beta from G, gradient of sigma analytically, then the prior terms (generic densities)
-// added on top.  n_tiles = number of 64-wide column tiles that wrote ss_part.
-__global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, int has_prior, const float *__restrict__ theta,
-                                                          int64_t row_base, int64_t C, int64_t Cp, int Dtot, int beta_off, int D, int Dp,
-                                                          int sigma_param, float sigma_const, float weight, int N,
-                                                          int n_tiles, const float *__restrict__ ss_part,
-                                                          const float *__restrict__ G, int g_splits, float *__restrict__ logp,
-                                                          float *__restrict__ grad, const int *__restrict__ idx,
-                                                          const float *__restrict__ r_unscale,
-                                                          const float *__restrict__ inv_col_scale) {
+// One warp per chain (body: finish_row, glm_rows.cuh).  Rows [row_base, row_end) of the batch.
+__global__ void __launch_bounds__(128) glm_finish_kernel(KModel prior, FinishP F, const float *__restrict__ theta,
+                                                          int64_t row_base, int64_t row_end, float *__restrict__ logp,
+                                                          float *__restrict__ grad, const int *__restrict__ idx) {
   extern __shared__ __align__(16) unsigned char smem[];
   SModel sm;
   sm.n_terms = 0;
-  if (has_prior) model_to_smem(prior, smem, sm);
+  if (F.has_prior) model_to_smem(prior, smem, sm);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int64_t c = row_base + (int64_t)blockIdx.x * (blockDim.x / 32) + warp;   // rows [row_base, C)
-  if (c >= C) return;
+  const int64_t c = row_base + (int64_t)blockIdx.x * (blockDim.x / 32) + warp;
+  if (c >= row_end) return;
   const int64_t src = idx ? idx[c] : c;       // chain served by row c of a compacted batch
-  const float *th = theta + src * Dtot;
-  float ss = 0.f;
-  for (int t = lane; t < n_tiles; t += 32) ss += ss_part[(int64_t)t * Cp + c];
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float sg = sigma_param >= 0 ? th[sigma_param] : sigma_const;
-  const float iv = 1.0f / (sg * sg);
-  float lp = weight * ((float)N * (-kHalfLog2Pi - logf(sg)) - 0.5f * ss * iv);
-  float *gr = grad ? grad + src * Dtot : nullptr;
-  // One warp per chain: with a scalar loop over d the warp walks D / 32 dependent iterations (80-120 us at D = 1000
-  // whatever the number of chains: latency bound).  When the layout allows, each lane takes four consecutive
-  // coefficients and all split-K partials of an iteration are independent 16-byte loads.
-  const bool vec4 = gr && sigma_param < 0 && (Dtot & 3) == 0 && (beta_off & 3) == 0 && (D & 3) == 0 &&
-                    ((reinterpret_cast<uintptr_t>(gr) | reinterpret_cast<uintptr_t>(G)) & 15) == 0;
-  if (vec4) {
-    const float ru = r_unscale ? r_unscale[c] : 1.0f;
-    for (int d = 4 * lane; d < Dtot; d += 128) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (d >= beta_off && d < beta_off + D) {
-        const float4 *g4 = reinterpret_cast<const float4 *>(G + (int64_t)c * Dp + (d - beta_off));
-        const int64_t stride4 = (Cp * (int64_t)Dp) >> 2;
-#pragma unroll 8
-        for (int s = 0; s < g_splits; ++s) {   // fixed order, element by element the same sums as the scalar loop
-          const float4 t = g4[(int64_t)s * stride4];
-          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-        }
-        if (r_unscale) {
-          const float4 ic = *reinterpret_cast<const float4 *>(inv_col_scale + (d - beta_off));
-          v.x *= ru * ic.x; v.y *= ru * ic.y; v.z *= ru * ic.z; v.w *= ru * ic.w;
-        }
-      }
-      *reinterpret_cast<float4 *>(gr + d) = v;
-    }
-    __syncwarp();
-  } else if (gr) {
-#pragma unroll 2
-    for (int d = lane; d < Dtot; d += 32) {
-      float v = 0.f;
-      if (d >= beta_off && d < beta_off + D) {
-#pragma unroll 8
-        for (int s = 0; s < g_splits; ++s) v += G[((int64_t)s * Cp + c) * Dp + (d - beta_off)];  // fixed order
-        if (r_unscale) v *= r_unscale[c] * inv_col_scale[d - beta_off];   // fp16 encoding: undo the operand scales
-      }
-      if (d == sigma_param) v = weight * (ss * iv - (float)N) / sg;
-      gr[d] = v;
-    }
-    __syncwarp();
-  }
-  // priors: lanes stride the elements of each term; each element touches its own theta entries
-  float pl = 0.f;
-  for (int t = 0; t < sm.n_terms; ++t) {
-    const b2m_term &T = sm.terms[t];
-    float acc = 0.f, ax = 0.f, a0 = 0.f, a1 = 0.f;
-    if (T.dist == B2M_NORMAL && T.x.kind == B2M_OP_PARAMVEC && T.p0.kind == B2M_OP_CONST && T.p1.kind == B2M_OP_CONST) {
-      // the usual coefficient prior, sum Normal(loc, scale).log_prob(beta): constants hoisted out of the element loop
-      // (same expressions as dist_eval, evaluated once)
-      const float p0 = T.p0.c, p1 = T.p1.c, var = p1 * p1, base = -kHalfLog2Pi - logf(p1), w = T.weight;
-      const float *__restrict__ xv = th + T.x.a;
-      float *__restrict__ gv = gr ? gr + T.x.a : nullptr;
-      if ((T.length & 3) == 0 && ((reinterpret_cast<uintptr_t>(xv) | reinterpret_cast<uintptr_t>(gv)) & 15) == 0) {
-        for (int n = 4 * lane; n < T.length; n += 128) {   // same per-element expressions, four elements per lane
-          const float4 x4 = *reinterpret_cast<const float4 *>(xv + n);
-          const float z0 = x4.x - p0, z1 = x4.y - p0, z2 = x4.z - p0, z3 = x4.w - p0;
-          acc += base - (0.5f * (z0 * z0)) / var;
-          acc += base - (0.5f * (z1 * z1)) / var;
-          acc += base - (0.5f * (z2 * z2)) / var;
-          acc += base - (0.5f * (z3 * z3)) / var;
-          if (gv) {
-            float4 g4 = *reinterpret_cast<float4 *>(gv + n);
-            g4.x += w * (-(z0 / var)); g4.y += w * (-(z1 / var)); g4.z += w * (-(z2 / var)); g4.w += w * (-(z3 / var));
-            *reinterpret_cast<float4 *>(gv + n) = g4;
-          }
-        }
-      } else {
-#pragma unroll 4
-        for (int n = lane; n < T.length; n += 32) {
-          const float z = xv[n] - p0;
-          acc += base - (0.5f * (z * z)) / var;
-          if (gv) gv[n] += w * (-(z / var));
-        }
-      }
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      pl += w * acc;
-      __syncwarp();
-      continue;
-    }
-    for (int n = lane; n < T.length; n += 32) {
-      const float x = op_fetch(T.x, n, th, 1, sm), p0 = op_fetch(T.p0, n, th, 1, sm), p1 = op_fetch(T.p1, n, th, 1, sm);
-      Elem e = dist_eval<true>(T.dist, x, p0, p1, T.k0, T.k1, T.k2);
-      acc += e.lp;
-      if (gr) {
-        if (T.x.kind == B2M_OP_PARAM) ax += e.dx; else if (T.x.kind == B2M_OP_PARAMVEC) gr[T.x.a + n] += T.weight * e.dx;
-        if (T.p0.kind == B2M_OP_PARAM) a0 += e.d0; else if (T.p0.kind == B2M_OP_PARAMVEC) gr[T.p0.a + n] += T.weight * e.d0;
-        if (T.p1.kind == B2M_OP_PARAM) a1 += e.d1; else if (T.p1.kind == B2M_OP_PARAMVEC) gr[T.p1.a + n] += T.weight * e.d1;
-      }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      ax += __shfl_xor_sync(0xffffffffu, ax, o);
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    }
-    pl += T.weight * acc;
-    if (gr && lane == 0) {
-      if (T.x.kind == B2M_OP_PARAM) gr[T.x.a] += T.weight * ax;
-      if (T.p0.kind == B2M_OP_PARAM) gr[T.p0.a] += T.weight * a0;
-      if (T.p1.kind == B2M_OP_PARAM) gr[T.p1.a] += T.weight * a1;
-    }
-    __syncwarp();
-  }
-  if (lane == 0) logp[src] = lp + pl;
+  finish_row(F, sm, theta + src * F.Dtot, c, c, logp + src, grad ? grad + src * F.Dtot : nullptr, lane);
+}
+
+FinishP make_finish(const GlmModel &g, int64_t Cp, bool with_grad) {
+  FinishP F{};
+  F.has_prior = g.has_prior ? 1 : 0;
+  F.Dtot = g.Dtot; F.beta_off = g.beta_off; F.D = g.D; F.Dp = g.Dp; F.sigma_param = g.sigma_param;
+  F.sigma_const = g.sigma_const; F.weight = g.weight; F.N = (int)g.N_total;
+  F.n_tiles = g.use_tc ? g.Np / 128 : g.Np / TN;   // tcgen05: 256-wide tiles, two column halves each
+  F.ss_part = g.ss_part; F.G = g.G; F.g_splits = with_grad ? (g.use_tc ? g.g_splits : 1) : 0; F.Cp = Cp;
+  F.r_unscale = g.use_tc == 2 ? g.r_unscale : nullptr;
+  F.inv_col_scale = g.use_tc == 2 ? g.inv_col_scale : nullptr;
+  F.tf = g.tf; F.thc = g.thc;
+  return F;
+}
+
+size_t finish_smem(const GlmModel &g) { return g.has_prior ? model_smem_bytes(g.prior) : 16; }
+
+// the finish step of the most recent contraction pair, on its own (the fused NUTS loop needs it before a recentring /
+// compaction changes the row <-> chain mapping)
+int glm_finish_launch(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st,
+                      const int *idx, int64_t n_rows) {
+  if (idx) C = n_rows;
+  const int64_t Cp = C <= 128 ? 128 : (C + 255) / 256 * 256;
+  const FinishP F = make_finish(g, Cp, grad != nullptr);
+  glm_finish_kernel<<<(unsigned)((C + 3) / 4), 128, finish_smem(g), st>>>(g.prior, F, theta, 0, C, logp, grad, idx);
+  ++g_launches;
+  B2M_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st, bool recenter,
@@ -629,33 +513,35 @@ int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float
   if (idx) C = n_rows;   // compacted batch: rows 0..n_rows-1 are the chains idx[0..n_rows-1]
   const int64_t Cp = C <= 128 ? 128 : (C + 255) / 256 * 256;   // one 128-row tile, or whole 256-row CTA-pair tiles
   const int64_t tot = Cp * g.Dp;
-  if (g.use_tc == 2)
-    glm_pack16_kernel<<<(unsigned)((Cp + 3) / 4), 128, 0, st>>>(theta, g.beta0, idx, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
-                                                                g.sigma_param, g.sigma_const, g.weight, g.inv_col_scale,
-                                                                g.y0max_bits, g.x_rownorm_max, g.B16h, g.B16l, g.inv_var,
-                                                                g.a_unscale, g.r_scale, g.r_unscale);
-  else
-    glm_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(theta, g.beta0, idx, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
+  if (g.use_tc == 2) {
+    const PackP P = make_pack(g);
+    glm_pack16_kernel<<<(unsigned)((Cp + 3) / 4), 128, 0, st>>>(P, theta, idx, C, Cp);
+  } else {
+    const float *src = theta;
+    const int *sidx = idx;
+    if (g.tf) {   // the contraction sees T(theta)
+      glm_constrain_kernel<<<(unsigned)((C * g.Dtot + 255) / 256), 256, 0, st>>>(theta, idx, g.tf, C, g.Dtot, g.thc);
+      ++g_launches;
+      src = g.thc;
+      sidx = nullptr;
+    }
+    glm_pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, g.beta0, sidx, C, Cp, g.Dtot, g.beta_off, g.D, g.Dp,
                                                                     g.sigma_param, g.sigma_const, g.B, g.Bh, g.Bl, g.inv_var);
+  }
   ++g_launches;
-  int n_tiles;
   if (g.use_tc) {
     if (int rc = tc_gemm_resid(g, Cp, st)) return rc;
     if (grad) if (int rc = tc_gemm_grad(g, Cp, st)) return rc;
-    n_tiles = g.Np / 128;   // 256-wide tiles, two column halves each
   } else {
     if (int rc = simt_gemm_resid(g, Cp, st)) return rc;
     if (grad) if (int rc = simt_gemm_grad(g, Cp, st)) return rc;
-    n_tiles = g.Np / TN;
   }
-  const size_t smem = g.has_prior ? model_smem_bytes(g.prior) : 16;
-  const float *ssp = g.ss_part, *Gp = g.G;
-  int splits = g.use_tc ? g.g_splits : 1;
-  const float *r_un = g.use_tc == 2 ? g.r_unscale : nullptr, *ics = g.use_tc == 2 ? g.inv_col_scale : nullptr;
+  FinishP F = make_finish(g, Cp, grad != nullptr);
   if (g.comm) {
     // observation shard: contiguous [Cp, Dp] gradient partial || [Cp] sum z^2, summed over ranks on this stream
     const int64_t n_red = Cp * g.Dp + Cp;
-    glm_reduce_kernel<<<(unsigned)((n_red + 255) / 256), 256, 0, st>>>(g.G, grad ? splits : 0, g.ss_part, n_tiles, Cp, g.Dp, r_un, ics, g.red);
+    glm_reduce_kernel<<<(unsigned)((n_red + 255) / 256), 256, 0, st>>>(g.G, F.g_splits, g.ss_part, F.n_tiles, Cp, g.Dp,
+                                                                        F.r_unscale, F.inv_col_scale, g.red);
     ++g_launches;
     if (own_count > 0) {
       // sliced state: every rank only needs the sums of its own chains' rows -- two in-place reduce-scatters
@@ -669,15 +555,13 @@ int glm_logp_grad(GlmModel &g, const float *theta, int64_t C, float *logp, float
     } else {
       if (int rc = comm_allreduce_f32(g.comm, grad ? g.red : g.red + Cp * g.Dp, grad ? n_red : Cp, st)) return rc;
     }
-    Gp = g.red; ssp = g.red + Cp * g.Dp; splits = 1; n_tiles = 1;
-    r_un = nullptr; ics = nullptr;   // already unscaled before the sum over ranks
+    F.G = g.red; F.ss_part = g.red + Cp * g.Dp; F.g_splits = grad ? 1 : 0; F.n_tiles = 1;
+    F.r_unscale = nullptr; F.inv_col_scale = nullptr;   // already unscaled before the sum over ranks
   }
   const int64_t row_base = (g.comm && own_count > 0) ? own_base : 0;
   const int64_t rows = (g.comm && own_count > 0) ? own_count : C;
-  glm_finish_kernel<<<(unsigned)((rows + 3) / 4), 128, smem, st>>>(g.prior, g.has_prior ? 1 : 0, theta, row_base, row_base + rows, Cp,
-                                                                    g.Dtot, g.beta_off, g.D, g.Dp, g.sigma_param, g.sigma_const,
-                                                                    g.weight, (int)g.N_total, n_tiles, ssp, Gp, splits, logp, grad,
-                                                                    idx, r_un, ics);
+  glm_finish_kernel<<<(unsigned)((rows + 3) / 4), 128, finish_smem(g), st>>>(g.prior, F, theta, row_base, row_base + rows,
+                                                                            logp, grad, idx);
   ++g_launches;
   B2M_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -26,6 +26,28 @@ int comm_allreduce_f32(Comm *c, float *buf, int64_t n, cudaStream_t st);
 int comm_allreduce_i64(Comm *c, int64_t *buf, int64_t n, cudaStream_t st);
 
 constexpr int kCenterSlices = 32;  // chain slices of the deterministic two-stage mean (glm.cu, centring)
+constexpr int kMaxPeers = 8;       // ranks of one NVSwitch box
+
+// The peer window of observation sharding with sliced state (include/b200mcmc.h, B2M_SLICE_PEER).  Every rank owns one
+// window with this layout; `base[s]` is rank s's window as mapped into this process (CUDA IPC), base[rank] is local.
+struct PeerWindow {
+  int nranks = 0, rank = 0;
+  int64_t C = 0, own = 0;          // chains of the call, chains per owner (C / nranks)
+  int Dp = 0;
+  char *base[kMaxPeers] = {};
+  // byte offsets inside a window
+  size_t off_g = 0;      // float  [nranks][own][Dp]  gradient partial of MY chains from each source rank (unscaled)
+  size_t off_ss = 0;     // float  [nranks][own]      sum z^2 partial of my chains from each source rank
+  size_t off_bh = 0, off_bl = 0;   // __half [C][Dp]  packed position rows of ALL chains (each owner writes its rows everywhere)
+  size_t off_meta = 0;   // float4 [C]                (1/sigma^2, 1 / row scale of delta', ||delta||^2, spare) per row
+  size_t off_bflag = 0;  // u64 [nranks]  "rank s has published the rows of its chains for sequence number n"
+  size_t off_gflag = 0;  // u64 [nranks]  "rank s has stored its gradient / sum z^2 partials of sequence number n"
+  size_t off_done = 0;   // i64 [nranks]  finished chains of rank s's slice
+  size_t off_err = 0;    // int           a spin-wait timed out (the call then fails instead of hanging the GPU)
+  size_t bytes = 0;
+  uint64_t seq = 0;      // sequence number of the last exchange (identical on every rank: the calls are collective)
+};
+size_t peer_layout(PeerWindow &w, int64_t C, int nranks, int Dp);
 
 struct GlmModel {
   // problem
@@ -73,7 +95,24 @@ struct GlmModel {
   Comm *comm = nullptr;
   int64_t N_total = 0;
   float *red = nullptr;                                      // [cap * Dp + cap] gradient partial || sum z^2, all-reduced
+  PeerWindow pw;                                             // attached by b2m_model_peer_attach (nranks == 0: none)
+  // constraint transforms (include/b200mcmc.h): per-parameter B2M_TF_* codes, device [Dtot], or nullptr; the samplers'
+  // theta is then the unconstrained coordinate and `thc` [cap, Dtot] holds T(theta) of the batch being evaluated
+  int *tf = nullptr;
+  float *thc = nullptr;
+  // K6 push epilogue (peer window): set only while a peer-sliced NUTS call is running
+  bool push_on = false;
+  unsigned *blk_counter = nullptr;                           // device: "last block" counters of the signalling kernels
+  volatile long long *h_prog = nullptr;                      // pinned + mapped: {ticks completed, finished chains} written by the device
 };
+
+// knobs for experiments, read ONCE per process from the environment (never on the launch path):
+//   B2M_TC_GROUPS_RESID / B2M_TC_GROUPS_GRAD  persistent CTA groups, B2M_TC_CHUNK_RESID / B2M_TC_CHUNK_GRAD promotion
+//   interval in k-blocks, B2M_TC_PAIR=0 single-CTA kernels
+struct Tuning {
+  int groups_resid = 0, groups_grad = 0, chunk_resid = 0, chunk_grad = 0, pair = 1;
+};
+const Tuning &tuning();
 
 int glm_set_comm(GlmModel &g, Comm *c, cudaStream_t st);
 
@@ -101,6 +140,9 @@ void tc_profile(bool enable);
 int tc_profile_read(double *out4);
 int grad_splits(const GlmModel &g, int64_t Cp);
 
+int tc_gemm_grad_push(GlmModel &g, int64_t Cp, cudaStream_t st);   // K6 whose epilogue stores into the owners' windows
+int glm_finish_launch(GlmModel &g, const float *theta, int64_t C, float *logp, float *grad, cudaStream_t st,
+                      const int *idx, int64_t n_rows);
 int glm_hmc_run(GlmModel &g, const b2m_hmc_args &a, cudaStream_t st);
 int glm_nuts_run(GlmModel &g, const b2m_nuts_args &a, cudaStream_t st);
 int glm_mh_run(GlmModel &g, const b2m_mh_args &a, cudaStream_t st);

@@ -7,10 +7,11 @@
 // leaf per lock-step, per-chain masks for chains whose subtree / trajectory has ended.
 #include <stdlib.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
-#include "glm.cuh"
+#include "glm_rows.cuh"
 
 namespace b2m {
 
@@ -29,10 +30,11 @@ __device__ __forceinline__ void normals4(uint64_t seed, uint64_t gchain, uint32_
   box_muller(w.z, w.w, out[2], out[3]);
 }
 
+// im = diag(M^-1) shared by all chains or nullptr (identity, the reference): p = z sqrt(m_d) ~ N(0, M)
 __device__ inline void fill_momentum(float *p, int D, const float *inj, uint64_t seed, uint64_t gchain, uint32_t giter,
-                                     uint4 w0, int lane) {
+                                     uint4 w0, int lane, const float *__restrict__ im = nullptr) {
   if (inj) {
-    for (int d = lane; d < D; d += 32) p[d] = inj[d];
+    for (int d = lane; d < D; d += 32) p[d] = im ? inj[d] / sqrtf(im[d]) : inj[d];
     return;
   }
   if (lane == 0) {
@@ -47,11 +49,19 @@ __device__ inline void fill_momentum(float *p, int D, const float *inj, uint64_t
     for (int i = 0; i < 4; ++i)
       if (2 + 4 * grp + i < D) p[2 + 4 * grp + i] = z[i];
   }
+  if (im) {
+    __syncwarp();
+    for (int d = lane; d < D; d += 32) p[d] = p[d] / sqrtf(im[d]);
+  }
 }
 
-__device__ __forceinline__ float kinetic_w(const float *__restrict__ p, int D, int lane) {
+__device__ __forceinline__ float kinetic_w(const float *__restrict__ p, int D, int lane, const float *__restrict__ im = nullptr) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   int d = lane;
+  if (im) {   // 0.5 sum p_d^2 / m_d
+    for (; d < D; d += 32) s0 = fmaf(p[d] * p[d], im[d], s0);
+    return 0.5f * warp_sum(s0);
+  }
   for (; d + 96 < D; d += 128) {
     const float a = p[d], b = p[d + 32], c = p[d + 64], e = p[d + 96];
     s0 = fmaf(a, a, s0); s1 = fmaf(b, b, s1); s2 = fmaf(c, c, s2); s3 = fmaf(e, e, s3);
@@ -68,7 +78,14 @@ __device__ __forceinline__ float kinetic_w(const float *__restrict__ p, int D, i
 // ================================================================= HMC
 struct HmcBufs {
   float *p, *g, *qn, *gn, *lp, *lpn, *h0;
+  const int *tf;   // constraint transforms of the model (draws are written constrained) or nullptr
 };
+
+// one warp writes a draw: the constrained value unless the call asks for the sampler's own coordinates
+__device__ __forceinline__ void write_draw(float *__restrict__ dst, const float *__restrict__ q, int D, int lane,
+                                           const int *__restrict__ tf) {
+  for (int d = lane; d < D; d += 32) dst[d] = tf_constrain(tf[d], q[d]);
+}
 
 __global__ void __launch_bounds__(32 * WPB) hmc_begin_kernel(b2m_hmc_args A, HmcBufs W, int D, int it) {
   CHAIN_PROLOGUE(A.n_chains)
@@ -78,16 +95,17 @@ __global__ void __launch_bounds__(32 * WPB) hmc_begin_kernel(b2m_hmc_args A, Hmc
   float *p = W.p + c * D, *qn = W.qn + c * D;
   const float *q = A.theta + c * D, *g = W.g + c * D;
   const uint4 w0 = Philox::draw(A.seed, gchain, giter, 0u);
-  fill_momentum(p, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0, lane);
+  const float *__restrict__ im = A.inv_mass;
+  fill_momentum(p, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0, lane, im);
   __syncwarp();
-  const float kin = kinetic_w(p, D, lane);
+  const float kin = kinetic_w(p, D, lane, im);
   if (lane == 0) W.h0[c] = -W.lp[c] + kin;
   const double eps = A.step_size[c];
   const float he = (float)(0.5 * eps), fe = (float)eps;
   for (int d = lane; d < D; d += 32) {
     const float pv = __fadd_rn(p[d], __fmul_rn(he, g[d]));
     p[d] = pv;
-    qn[d] = __fadd_rn(q[d], __fmul_rn(fe, pv));
+    qn[d] = __fadd_rn(q[d], __fmul_rn(fe, im ? im[d] * pv : pv));
   }
 }
 
@@ -98,11 +116,12 @@ __global__ void __launch_bounds__(32 * WPB) hmc_mid_kernel(b2m_hmc_args A, HmcBu
   const float *gn = W.gn + c * D;
   const double eps = A.step_size[c];
   const float he = (float)(0.5 * eps), fe = (float)eps;
+  const float *__restrict__ im = A.inv_mass;
   for (int d = lane; d < D; d += 32) {
     float pv = __fadd_rn(p[d], __fmul_rn(he, gn[d]));
     pv = __fadd_rn(pv, __fmul_rn(he, gn[d]));
     p[d] = pv;
-    qn[d] = __fadd_rn(qn[d], __fmul_rn(fe, pv));
+    qn[d] = __fadd_rn(qn[d], __fmul_rn(fe, im ? im[d] * pv : pv));
   }
 }
 
@@ -117,7 +136,7 @@ __global__ void __launch_bounds__(32 * WPB) hmc_end_kernel(b2m_hmc_args A, HmcBu
   const float he = (float)(0.5 * eps);
   for (int d = lane; d < D; d += 32) p[d] = __fadd_rn(p[d], __fmul_rn(he, gn[d]));
   __syncwarp();
-  const float kin = kinetic_w(p, D, lane);
+  const float kin = kinetic_w(p, D, lane, A.inv_mass);
   const float h0 = W.h0[c], h1 = -W.lpn[c] + kin;
   float u;
   if (A.inj_uniform) u = A.inj_uniform[row];
@@ -139,7 +158,7 @@ __global__ void __launch_bounds__(32 * WPB) hmc_end_kernel(b2m_hmc_args A, HmcBu
       double h_bar = A.da_state[c * 3 + 0], log_eps_bar = A.da_state[c * 3 + 1];
       const double mu = A.da_state[c * 3 + 2];
       const float a = (log_ratio == log_ratio) ? expf(fminf(log_ratio, 0.f)) : 0.f;
-      const double m = (double)giter + 1.0, eta = 1.0 / (m + 10.0);
+      const double m = (double)((int64_t)giter - A.adapt_origin) + 1.0, eta = 1.0 / (m + 10.0);
       h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - (double)a);
       double log_eps = mu - sqrt(m) / 0.05 * h_bar;
       log_eps = fmin(fmax(log_eps, -10.0), 10.0);
@@ -154,7 +173,8 @@ __global__ void __launch_bounds__(32 * WPB) hmc_end_kernel(b2m_hmc_args A, HmcBu
   }
   if (A.draws) {
     __syncwarp();
-    for (int d = lane; d < D; d += 32) A.draws[row * D + d] = q[d];
+    if (W.tf && !A.draws_unconstrained) write_draw(A.draws + row * D, q, D, lane, W.tf);
+    else for (int d = lane; d < D; d += 32) A.draws[row * D + d] = q[d];
   }
 }
 
@@ -191,6 +211,7 @@ int glm_hmc_run(GlmModel &gm, const b2m_hmc_args &a, cudaStream_t st) {
   const int64_t C = a.n_chains;
   const int D = gm.Dtot;
   HmcBufs W{};
+  W.tf = gm.tf;
   auto layout = [&](Arena &A) {
     A.take(&W.p, C * D); A.take(&W.g, C * D); A.take(&W.qn, C * D); A.take(&W.gn, C * D);
     A.take(&W.lp, C); A.take(&W.lpn, C); A.take(&W.h0, C);
@@ -238,7 +259,8 @@ __global__ void __launch_bounds__(32 * WPB) mh_propose_kernel(b2m_mh_args A, flo
   for (int d = lane; d < D; d += 32) z[d] = __fadd_rn(q[d], __fmul_rn(z[d], A.proposal_scale));
 }
 
-__global__ void __launch_bounds__(32 * WPB) mh_accept_kernel(b2m_mh_args A, const float *qn, const float *lpn, int D, int it) {
+__global__ void __launch_bounds__(32 * WPB) mh_accept_kernel(b2m_mh_args A, const float *qn, const float *lpn, int D, int it,
+                                                             const int *__restrict__ tf) {
   CHAIN_PROLOGUE(A.n_chains)
   const uint64_t gchain = (uint64_t)(A.chain_offset + c);
   const uint32_t giter = (uint32_t)(A.iter_offset + it);
@@ -255,8 +277,10 @@ __global__ void __launch_bounds__(32 * WPB) mh_accept_kernel(b2m_mh_args A, cons
     if (accept) { A.logp[c] = lpn[c]; A.n_accept[c] += 1; }
     if (A.trace_accept) A.trace_accept[row] = accept ? 1 : 0;
   }
-  if (A.draws)
-    for (int d = lane; d < D; d += 32) A.draws[row * D + d] = q[d];
+  if (A.draws) {
+    if (tf) write_draw(A.draws + row * D, q, D, lane, tf);
+    else for (int d = lane; d < D; d += 32) A.draws[row * D + d] = q[d];
+  }
 }
 
 int glm_mh_run(GlmModel &gm, const b2m_mh_args &a, cudaStream_t st) {
@@ -277,7 +301,7 @@ int glm_mh_run(GlmModel &gm, const b2m_mh_args &a, cudaStream_t st) {
     if (it > 0 && (it & 15) == 0) rc = glm_recenter(gm, a.theta, C, st);
     mh_propose_kernel<<<grid, 32 * WPB, 0, st>>>(a, qn, D, it);
     rc = glm_logp_grad(gm, qn, C, lpn, nullptr, st);
-    mh_accept_kernel<<<grid, 32 * WPB, 0, st>>>(a, qn, lpn, D, it);
+    mh_accept_kernel<<<grid, 32 * WPB, 0, st>>>(a, qn, lpn, D, it, gm.tf);
     g_launches += 2;
   }
   cudaError_t e = cudaStreamSynchronize(st);
@@ -311,6 +335,7 @@ struct NutsBufs {
   int *live;        // [C] state != 2 (input of the compaction)
   int *n_done;      // device counter of finished chains
   double *pool;     // [4] pooled adaptation: sum of alpha, count, update index, spare
+  const int *tf;    // constraint transforms of the model (draws are written constrained) or nullptr
 };
 
 // One warp copies a [D] vector.  These kernels are pure HBM streaming with one warp per chain: with a scalar loop each
@@ -368,9 +393,9 @@ __device__ __forceinline__ void nuts_begin_dev(const b2m_nuts_args &A, const Nut
   const size_t row = (size_t)it * A.n_chains + c;
   const size_t o = (size_t)c * D;
   const uint4 w0 = Philox::draw(A.seed, gchain, giter, 0u);
-  fill_momentum(W.p0 + o, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0, lane);
+  fill_momentum(W.p0 + o, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0, lane, A.inv_mass);
   __syncwarp();
-  const float kin = kinetic_w(W.p0 + o, D, lane);
+  const float kin = kinetic_w(W.p0 + o, D, lane, A.inv_mass);
   const float *q = A.theta + o;
   vcopy(W.q_lo + o, q, D, lane); vcopy(W.q_hi + o, q, D, lane);
   vcopy(W.p_lo + o, W.p0 + o, D, lane); vcopy(W.p_hi + o, W.p0 + o, D, lane);
@@ -428,6 +453,15 @@ __device__ __forceinline__ void nuts_leaf_pre_dev(const b2m_nuts_args &A, const 
   const float he = W.heps[c], fe = W.feps[c];
   float *__restrict__ fq = W.fq + o, *__restrict__ fp = W.fp + o;
   const float *__restrict__ fg = W.fg + o;
+  if (const float *__restrict__ im = A.inv_mass) {   // diagonal mass matrix: drift by eps M^-1 p
+#pragma unroll 4
+    for (int d = lane; d < D; d += 32) {
+      const float pv = __fadd_rn(fp[d], __fmul_rn(he, fg[d]));
+      fp[d] = pv;
+      fq[d] = __fadd_rn(fq[d], __fmul_rn(fe, im[d] * pv));
+    }
+    return;
+  }
   if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(fq) | reinterpret_cast<uintptr_t>(fp) | reinterpret_cast<uintptr_t>(fg)) & 15) == 0) {
     for (int d = 4 * lane; d < D; d += 128) {   // four coefficients per lane: same per-element arithmetic
       const float4 g4 = *reinterpret_cast<const float4 *>(fg + d);
@@ -502,8 +536,9 @@ __device__ __forceinline__ void nuts_leaf_post_dev(const b2m_nuts_args &A, const
       fp[d] = p0; sfq[d] = q0; scq[d] = q0; sfp[d] = p0; scg[d] = g0;
     }
   }
-  const float kin = 0.5f * warp_sum(k0 + k1);
+  float kin = 0.5f * warp_sum(k0 + k1);
   __syncwarp();
+  if (A.inv_mass) kin = kinetic_w(fp, D, lane, A.inv_mass);   // 0.5 sum p^2 / m (fp holds the completed step's momentum)
   const float flp = W.flp[c], h0 = W.h0[c], log_slice = W.log_slice[c];
   const float h1 = -flp + kin;
   const int n1 = (log_slice <= -h1) ? 1 : 0;
@@ -626,7 +661,10 @@ __device__ __forceinline__ void nuts_end_dev(const b2m_nuts_args &A, const NutsB
   const size_t o = (size_t)c * D;
   vcopy(A.theta + o, W.cq + o, D, lane);
   vcopy(W.g + o, W.cg + o, D, lane);
-  if (A.draws) vcopy(A.draws + row * D, W.cq + o, D, lane);
+  if (A.draws) {
+    if (W.tf && !A.draws_unconstrained) write_draw(A.draws + row * D, W.cq + o, D, lane, W.tf);
+    else vcopy(A.draws + row * D, W.cq + o, D, lane);
+  }
   if (lane == 0) {
     W.lp[c] = W.clp[c];
     const double mean_alpha = W.alpha_sum[c] / fmax((double)W.alpha_cnt[c], 1.0);
@@ -635,7 +673,7 @@ __device__ __forceinline__ void nuts_end_dev(const b2m_nuts_args &A, const NutsB
     if (A.adapt == B2M_ADAPT_DUAL_AVERAGING) {
       double h_bar = A.da_state[c * 3 + 0], eps_bar = A.da_state[c * 3 + 1];
       const float mu = (float)A.da_state[c * 3 + 2];
-      const double m = (double)giter, eta = 1.0 / (m + 10.0);
+      const double m = (double)((int64_t)giter - A.adapt_origin), eta = 1.0 / (m + 10.0);
       h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - mean_alpha);
       float log_eps = __fsub_rn(mu, (float)((sqrt(m + 1.0) / 0.05) * h_bar));
       log_eps = fmaxf(fminf(log_eps, 10.0f), -10.0f);
@@ -707,7 +745,7 @@ __global__ void __launch_bounds__(1024) nuts_pool_adapt_kernel(b2m_nuts_args A, 
     const double mean_alpha = red[0] / (double)C;
     double h_bar = A.da_state[0], eps_bar = A.da_state[1];
     const float mu = (float)A.da_state[2];
-    const double m = (double)(uint32_t)(A.iter_offset + it), eta = 1.0 / (m + 10.0);
+    const double m = (double)((int64_t)(uint32_t)(A.iter_offset + it) - A.adapt_origin), eta = 1.0 / (m + 10.0);
     h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - mean_alpha);
     float log_eps = __fsub_rn(mu, (float)((sqrt(m + 1.0) / 0.05) * h_bar));
     log_eps = fmaxf(fminf(log_eps, 10.0f), -10.0f);
@@ -758,10 +796,7 @@ static void nuts_layout(Arena &A, NutsBufs &W, int64_t C, int D, int MD) {
 // next one, and the host only looks at a counter every few ticks.  Per chain the algorithm, the Philox slots and the
 // arithmetic are those of the synchronous kernels (the same device functions), so a chain's draws are the same up to
 // the batch-dependent rounding of the GLM contractions.
-__global__ void __launch_bounds__(32 * WPB) nuts_tick_kernel(b2m_nuts_args A, NutsBufs W, int D, int64_t c_base, int64_t c_end) {
-  const int lane = threadIdx.x & 31;
-  const int64_t c = c_base + (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5);   // this rank's chains: [c_base, c_end)
-  if (c >= c_end) return;
+__device__ __forceinline__ void nuts_tick_dev(const b2m_nuts_args &A, const NutsBufs &W, int D, int64_t c, int lane) {
   const int st = W.state[c];
   if (st == 2) return;
   int it = W.iter[c];
@@ -800,6 +835,185 @@ __global__ void __launch_bounds__(32 * WPB) nuts_tick_kernel(b2m_nuts_args A, Nu
   nuts_leaf_pre_dev(A, W, D, c, lane);
 }
 
+__global__ void __launch_bounds__(32 * WPB) nuts_tick_kernel(b2m_nuts_args A, NutsBufs W, int D, int64_t c_base, int64_t c_end) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = c_base + (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5);   // this rank's chains: [c_base, c_end)
+  if (c >= c_end) return;
+  nuts_tick_dev(A, W, D, c, lane);
+}
+
+// ================================================================= NUTS, fused tick (fp16-encoded tcgen05 path)
+// One tick of the asynchronous schedule used to be tick -> pack -> K5 -> K6 -> finish (+ a counter copy and an event):
+// at the small configuration (100 x 10K, 1024 chains) launch latency was half of the tick.  The per-chain work of a
+// tick now lives in ONE kernel, one warp per batch row:
+//     finish (log p / gradient of the leaf evaluated by the previous tick, from K6's output)
+//  -> tree bookkeeping (nuts_tick_dev: the same device functions as every other schedule)
+//  -> pack (fp16 hi/lo operand rows of the next leaf position for K5)
+// so a tick is state kernel -> K5 -> K6.  The last block to finish publishes {tick, finished chains} to mapped pinned
+// host memory: the host throttles on it and never touches the stream inside the loop.
+//
+// Peer mode (observation sharding, B2M_SLICE_PEER): the rank runs this kernel for the chains it owns only.  `finish`
+// first waits for the flags that say every rank has stored its gradient partial for these chains into this rank's
+// window (K6's epilogue does those stores), sums the per-source slots in rank order, and `pack` writes the new rows
+// into EVERY rank's window; the last block then raises this rank's "rows published" flag on every peer.
+struct StateP {
+  FinishP F;
+  PackP P;
+  const int *idx;            // batch row -> chain of a compacted batch, or nullptr
+  int64_t n_rows;            // live rows [row_base, row_base + n_rows); rows up to row_base + n_pad are zero padding
+  int64_t n_pad;
+  int64_t row_base;          // peer mode: first chain of this rank's slice
+  int do_finish, do_tick_pack;
+  unsigned *blk_counter;
+  volatile long long *h_prog;   // ring of {tick + 1, finished chains} pairs (non-peer mode), or nullptr
+  long long tick;
+  // peer mode
+  int peer, nranks, rank;
+  unsigned long long wait_seq, seq;
+  const unsigned long long *gflag;            // [nranks] in MY window
+  unsigned long long *bflag_peer[kMaxPeers];  // &bflag[rank] in every rank's window
+  long long *done_peer[kMaxPeers];            // &done[rank] in every rank's window
+  int *err;                                   // in my window
+};
+
+constexpr int kProgRing = 8;
+constexpr long long kSpinTimeout = 20000000000ll;   // cycles (~10 s): a lost peer fails the call instead of hanging the GPU
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// thread-level wait for *flag >= want; gives up (and records it) after kSpinTimeout cycles or when a peer already has
+__device__ __forceinline__ void spin_until(const unsigned long long *flag, unsigned long long want, int *err) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < want) {
+    if (*reinterpret_cast<volatile int *>(err)) return;
+    if (clock64() - t0 > kSpinTimeout) { *reinterpret_cast<volatile int *>(err) = 1; __threadfence_system(); return; }
+    __nanosleep(64);
+  }
+}
+
+__global__ void __launch_bounds__(32 * WPB) nuts_state_kernel(b2m_nuts_args A, NutsBufs W, int D, KModel prior, StateP S) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int last_block;
+  SModel sm;
+  sm.n_terms = 0;
+  if (S.do_finish && S.F.has_prior) model_to_smem(prior, smem, sm);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (S.peer && S.do_finish) {   // gradient partials of the previous evaluation: one flag per source rank
+    if ((int)threadIdx.x < S.nranks) spin_until(S.gflag + threadIdx.x, S.wait_seq, S.err);
+    __syncthreads();
+  }
+  const int64_t r = (int64_t)blockIdx.x * WPB + warp;
+  if (r < S.n_rows) {
+    const int64_t row = S.row_base + r;
+    const int64_t c = S.idx ? S.idx[row] : row;
+    if (S.do_finish) {
+      finish_row(S.F, sm, W.fq + c * D, S.peer ? r : row, row, W.flp + c, W.fg + c * D, lane);
+      __syncwarp();
+    }
+    if (S.do_tick_pack) {
+      nuts_tick_dev(A, W, D, c, lane);
+      __syncwarp();
+      pack16_row(S.P, W.fq + c * D, row, lane);
+    }
+  } else if (r < S.n_pad && S.do_tick_pack) {
+    pack16_row(S.P, nullptr, S.row_base + r, lane);
+  }
+  if (!S.do_tick_pack) return;
+  // the last block to get here publishes the tick
+  if (S.peer) __threadfence_system(); else __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(S.blk_counter, 1u);
+    last_block = prev == gridDim.x - 1;
+    if (last_block) *S.blk_counter = 0;
+  }
+  __syncthreads();
+  if (!last_block) return;
+  __threadfence();
+  const long long n_done = *reinterpret_cast<volatile int *>(W.n_done);
+  if (S.peer) {
+    if ((int)threadIdx.x < S.nranks) {
+      *reinterpret_cast<volatile long long *>(S.done_peer[threadIdx.x]) = n_done;
+      __threadfence_system();
+      st_release_sys(S.bflag_peer[threadIdx.x], S.seq);
+    }
+  } else if (threadIdx.x == 0 && S.h_prog) {
+    volatile long long *slot = S.h_prog + 2 * (S.tick % kProgRing);
+    slot[1] = n_done;
+    __threadfence_system();
+    slot[0] = S.tick + 1;
+  }
+}
+
+// Peer mode, after the state kernel: wait until every rank has published its rows for this evaluation, expand the row
+// scalars (the residual's row scale depends on THIS rank's max |y0|), add up the finished-chain counts of the slices
+// and publish {tick, finished chains of all slices} to the host.
+__global__ void __launch_bounds__(256) obs_wait_kernel(const unsigned long long *bflag, int nranks, unsigned long long seq, int *err,
+                                                       const float4 *__restrict__ meta, int64_t C,
+                                                       const unsigned *__restrict__ y0max_bits, float x_rownorm_max, float weight,
+                                                       float *__restrict__ inv_var, float *__restrict__ a_unscale,
+                                                       float *__restrict__ r_scale, float *__restrict__ r_unscale,
+                                                       const long long *done, volatile long long *h_prog, long long tick) {
+  if ((int)threadIdx.x < nranks) spin_until(bflag + threadIdx.x, seq, err);
+  __syncthreads();
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float4 m = meta[c];
+    inv_var[c] = m.x;
+    a_unscale[c] = m.y;
+    const float bound = (__uint_as_float(*y0max_bits) + sqrtf(m.z) * x_rownorm_max) * fabsf(m.x * weight);
+    const float sr = pow2_scale(bound);
+    r_scale[c] = sr;
+    r_unscale[c] = 1.0f / sr;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    long long tot = 0;
+    for (int s = 0; s < nranks; ++s) tot += reinterpret_cast<const volatile long long *>(done)[s];
+    volatile long long *slot = h_prog + 2 * (tick % kProgRing);
+    slot[1] = *reinterpret_cast<volatile int *>(err) ? -1 : tot;
+    __threadfence_system();
+    slot[0] = tick + 1;
+  }
+}
+
+// Peer mode, after K6 (whose epilogue has stored the gradient tiles into the owners' windows): push the sum z^2
+// partial of every chain into its owner's slot, then -- last block -- raise "partials stored" on every rank.
+struct PeerP {
+  int nranks, rank;
+  int64_t own;
+  float *ss_slot[kMaxPeers];                   // sum z^2 block [nranks][own] of every rank's window
+  unsigned long long *gflag_peer[kMaxPeers];   // &gflag[rank] in every rank's window
+};
+
+__global__ void __launch_bounds__(128) obs_signal_kernel(const float *__restrict__ ss_part, int n_tiles, int64_t Cp, PeerP Q,
+                                                         unsigned long long seq, unsigned *blk_counter) {
+  __shared__ int last_block;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < Cp) {
+    float v = 0.f;
+    for (int t = 0; t < n_tiles; ++t) v += ss_part[(int64_t)t * Cp + c];   // fixed order
+    const int owner = (int)(c / Q.own);
+    Q.ss_slot[owner][(int64_t)Q.rank * Q.own + (c - (int64_t)owner * Q.own)] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(blk_counter, 1u);
+    last_block = prev == gridDim.x - 1;
+    if (last_block) *blk_counter = 0;
+  }
+  __syncthreads();
+  if (!last_block) return;
+  __threadfence();
+  if ((int)threadIdx.x < Q.nranks) st_release_sys(Q.gflag_peer[threadIdx.x], seq);
+}
+
 // Pooled dual averaging under the asynchronous schedule: acceptance statistics of the transitions that finished in
 // this tick are added (fixed order) to a pool; every n_chains completed transitions -- one per chain on average -- the
 // recurrences of nuts.py:298-310 advance once on the pool's mean and every chain gets the new step size for its next
@@ -835,7 +1049,7 @@ __global__ void __launch_bounds__(1024) nuts_pool_async_kernel(b2m_nuts_args A, 
       const double mean_alpha = sum / cnt;
       double h_bar = A.da_state[0], eps_bar = A.da_state[1];
       const float mu = (float)A.da_state[2];
-      const double m = (double)(uint32_t)A.iter_offset + W.pool[2], eta = 1.0 / (m + 10.0);
+      const double m = (double)((int64_t)(uint32_t)A.iter_offset - A.adapt_origin) + W.pool[2], eta = 1.0 / (m + 10.0);
       h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - mean_alpha);
       float log_eps = __fsub_rn(mu, (float)((sqrt(m + 1.0) / 0.05) * h_bar));
       log_eps = fmaxf(fminf(log_eps, 10.0f), -10.0f);
@@ -869,6 +1083,7 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   Arena real;
   real.base = gm.ws;
   nuts_layout(real, W, C, D, MD);
+  W.tf = gm.tf;
 
   const int T = 32 * WPB;
   B2M_CHECK_CUDA(cudaMemsetAsync(W.state, 0, sizeof(int) * C, st));
@@ -888,12 +1103,11 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   // and the new leaf positions of all slices are all-gathered for the next pack / contraction.  Per-chain outputs
   // (draws, counters, depths) are written for the owned chains only; the final positions are all-gathered.
   int64_t own_base = 0, own_count = 0;
-  if (gm.comm && a.adapt == B2M_ADAPT_NONE) {
-    const char *v = getenv("B2M_OBS_SLICE");
+  if (gm.comm && a.adapt == B2M_ADAPT_NONE && a.slice_state == B2M_SLICE_NCCL) {
     const int nr = comm_nranks(gm.comm);
-    if (v && atoi(v) == 1 && nr > 1) {
+    if (nr > 1) {
       if (C % nr != 0 || C % 256 != 0) {   // the caller merges per-chain outputs by slice: never fall back silently
-        set_error("B2M_OBS_SLICE=1: n_chains must be a multiple of 256 and of the number of ranks");
+        set_error("slice_state: n_chains must be a multiple of 256 and of the number of ranks");
         return 1;
       }
       own_count = C / nr;
@@ -927,11 +1141,12 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
       ++g_launches;
       if ((rc = comm_allreduce_i64(gm.comm, reinterpret_cast<int64_t *>(n_done_g), 1, st))) break;
       if ((rc = comm_allgather_inplace(gm.comm, W.fq, own_count * D, 4, st))) break;
-      cudaMemcpyAsync(h_ring + tick % kRing, n_done_g, sizeof(long long), cudaMemcpyDeviceToHost, st);
+      if (cudaMemcpyAsync(h_ring + tick % kRing, n_done_g, sizeof(long long), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 2;
     } else {        // low word of the (zeroed) 64-bit ring slot
-      cudaMemcpyAsync(h_ring + tick % kRing, W.n_done, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (cudaMemcpyAsync(h_ring + tick % kRing, W.n_done, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 2;
     }
-    cudaEventRecord(ring[tick % kRing], st);
+    if (cudaEventRecord(ring[tick % kRing], st) != cudaSuccess) rc = 2;
+    if (rc) { set_error("NUTS asynchronous schedule: counter copy / event record failed"); break; }
     if (pooled) {
       nuts_pool_async_kernel<<<1, 1024, 0, st>>>(a, W, 0);
       ++g_launches;
@@ -975,6 +1190,7 @@ int glm_nuts_run_sync(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   Arena real;
   real.base = gm.ws;
   nuts_layout(real, W, C, D, MD);
+  W.tf = gm.tf;
   int *h_flag = gm.h_flag;
   int rc = 0;
 
@@ -1019,10 +1235,214 @@ int glm_nuts_run_sync(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   return 0;
 }
 
-// B2M_NUTS_SCHED = async (default) | sync
+// ================================================================= NUTS, fused-tick host loop
+int glm_nuts_run_fused(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
+  const int64_t C = a.n_chains;
+  const int D = gm.Dtot, MD = a.max_tree_depth;
+  const bool peer = a.slice_state == B2M_SLICE_PEER;
+  PeerWindow &pw = gm.pw;
+  if (peer) {
+    B2M_REQUIRE(pw.nranks >= 2 && pw.C == C, "slice_state = PEER: attach a peer window for this number of chains first "
+                                               "(b2m_model_peer_attach)");
+    B2M_REQUIRE(a.inj_normal == nullptr && a.trace_doubling == nullptr, "slice_state = PEER: draw injection is not supported");
+  }
+  NutsBufs W{};
+  Arena probe;
+  nuts_layout(probe, W, C, D, MD);
+  if (int rc0 = arena_reserve(gm, probe.off)) return rc0;
+  Arena real;
+  real.base = gm.ws;
+  nuts_layout(real, W, C, D, MD);
+  W.tf = gm.tf;
+  if (!gm.blk_counter) {
+    B2M_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(&gm.blk_counter), sizeof(unsigned) * 8));
+    B2M_CHECK_CUDA(cudaMemset(gm.blk_counter, 0, sizeof(unsigned) * 8));
+  }
+  if (!gm.h_prog) {
+    long long *hp = nullptr;
+    B2M_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&hp), sizeof(long long) * 2 * kProgRing, cudaHostAllocMapped | cudaHostAllocPortable));
+    gm.h_prog = hp;
+  }
+  volatile long long *h_prog = gm.h_prog;
+  for (int i = 0; i < 2 * kProgRing; ++i) h_prog[i] = 0;
+
+  const int T = 32 * WPB;
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.state, 0, sizeof(int) * C, st));
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.iter, 0, sizeof(int) * C, st));
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.fin, 0, sizeof(int) * C, st));
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.live, 1, sizeof(int) * C, st));   // any non-zero pattern = live
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.n_done, 0, sizeof(int), st));
+  B2M_CHECK_CUDA(cudaMemsetAsync(W.pool, 0, sizeof(double) * 4, st));
+  // log p / gradient of the starting points (observation shards: summed over ranks by NCCL, once)
+  int rc = glm_logp_grad(gm, a.theta, C, W.lp, W.g, st, true);
+  if (rc) return rc;
+
+  constexpr int kCheck = 8, kLag = 2;
+  const bool pooled = a.adapt == B2M_ADAPT_POOLED;
+  const int64_t own = peer ? pw.own : C, own_base = peer ? pw.own * pw.rank : 0;
+  const int64_t max_ticks = (int64_t)a.n_iter * ((int64_t(1) << MD) + 1) + 2 * kCheck;
+  int64_t n_live = C;
+  const int *idx = nullptr;
+  // peer mode: K5 reads the packed rows from the window (every owner writes its rows there); restored on exit
+  __half *const saved_bh = gm.B16h, *const saved_bl = gm.B16l;
+  PeerP Q{};
+  if (peer) {
+    gm.B16h = reinterpret_cast<__half *>(pw.base[pw.rank] + pw.off_bh);
+    gm.B16l = reinterpret_cast<__half *>(pw.base[pw.rank] + pw.off_bl);
+    Q.nranks = pw.nranks; Q.rank = pw.rank; Q.own = pw.own;
+    for (int s = 0; s < pw.nranks; ++s) {
+      Q.ss_slot[s] = reinterpret_cast<float *>(pw.base[s] + pw.off_ss);
+      Q.gflag_peer[s] = reinterpret_cast<unsigned long long *>(pw.base[s] + pw.off_gflag) + pw.rank;
+    }
+  } else if (!gm.comm) {
+    gm.skip_flag = W.n_done;   // the contractions of the ticks the host launches after the last chain finished return at once
+    gm.skip_target = (int)C;
+  }
+  auto cleanup = [&]() { gm.B16h = saved_bh; gm.B16l = saved_bl; gm.skip_flag = nullptr; };
+
+  auto state_params = [&](bool do_finish, bool do_tick_pack, int64_t tick, unsigned long long wait_seq, unsigned long long seq) {
+    StateP S{};
+    const int64_t rows = idx ? n_live : C;
+    const int64_t Cp = rows <= 128 ? 128 : (rows + 255) / 256 * 256;
+    S.F = make_finish(gm, peer ? own : Cp, true);
+    S.P = make_pack(gm);
+    S.idx = idx;
+    S.n_rows = peer ? own : rows;
+    S.n_pad = peer ? own : Cp;
+    S.row_base = own_base;
+    S.do_finish = do_finish ? 1 : 0;
+    S.do_tick_pack = do_tick_pack ? 1 : 0;
+    S.blk_counter = gm.blk_counter;
+    S.h_prog = peer ? nullptr : h_prog;
+    S.tick = tick;
+    S.peer = peer ? 1 : 0;
+    if (peer) {
+      S.nranks = pw.nranks; S.rank = pw.rank;
+      S.wait_seq = wait_seq; S.seq = seq;
+      char *mine = pw.base[pw.rank];
+      S.gflag = reinterpret_cast<const unsigned long long *>(mine + pw.off_gflag);
+      S.err = reinterpret_cast<int *>(mine + pw.off_err);
+      // finish: per-source slots of my window, summed in rank order; already unscaled by the senders
+      S.F.G = reinterpret_cast<const float *>(mine + pw.off_g);
+      S.F.ss_part = reinterpret_cast<const float *>(mine + pw.off_ss);
+      S.F.g_splits = pw.nranks; S.F.n_tiles = pw.nranks; S.F.Cp = own;
+      S.F.r_unscale = nullptr; S.F.inv_col_scale = nullptr;
+      S.P.n_peers = pw.nranks;
+      for (int s = 0; s < pw.nranks; ++s) {
+        S.P.peer_Bh[s] = reinterpret_cast<__half *>(pw.base[s] + pw.off_bh);
+        S.P.peer_Bl[s] = reinterpret_cast<__half *>(pw.base[s] + pw.off_bl);
+        S.P.peer_meta[s] = reinterpret_cast<float4 *>(pw.base[s] + pw.off_meta);
+        S.bflag_peer[s] = reinterpret_cast<unsigned long long *>(pw.base[s] + pw.off_bflag) + pw.rank;
+        S.done_peer[s] = reinterpret_cast<long long *>(pw.base[s] + pw.off_done) + pw.rank;
+      }
+    }
+    return S;
+  };
+  auto launch_state = [&](const StateP &S) {
+    const unsigned grid = (unsigned)((S.n_pad + WPB - 1) / WPB);
+    nuts_state_kernel<<<grid, T, finish_smem(gm), st>>>(a, W, D, gm.prior, S);
+    ++g_launches;
+  };
+  // host side of the progress ring: {tick + 1, finished chains} of tick t lives in slot t % kProgRing
+  auto wait_tick = [&](int64_t t, long long &n_done) -> int {
+    volatile long long *slot = h_prog + 2 * (t % kProgRing);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spins = 0; slot[0] != t + 1; ++spins) {
+      if ((spins & 0xfff) == 0xfff) {
+        if (cudaStreamQuery(st) != cudaErrorNotReady && slot[0] != t + 1) {   // the stream drained (or failed) without the tick
+          set_error("NUTS fused schedule: the device stopped before publishing a tick");
+          return 2;
+        }
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+          set_error("NUTS fused schedule: timed out waiting for the device");
+          return 2;
+        }
+      }
+    }
+    n_done = slot[1];
+    if (n_done < 0) { set_error("NUTS peer exchange: a rank stopped answering (flag wait timed out)"); return 2; }
+    return 0;
+  };
+
+  unsigned long long prev_seq = 0;
+  for (int64_t tick = 0; !rc; ++tick) {
+    if (tick > max_ticks) { set_error("NUTS fused schedule: tick budget exceeded"); rc = 2; break; }
+    const bool check = tick > 0 && tick % kCheck == 0;
+    long long n_done = 0;
+    if (check) {
+      // finish the leaf of tick - 1 with the row mapping it was evaluated under, then drain: recentre / compact
+      launch_state(state_params(true, false, tick, prev_seq, 0));
+      if ((rc = wait_tick(tick - 1, n_done))) break;
+      if (n_done >= C) break;
+      if (peer && (rc = comm_allgather_inplace(gm.comm, a.theta, own * D, 4, st))) break;
+      if ((rc = glm_recenter(gm, a.theta, C, st))) break;      // reference point follows the current states
+      if (n_done > 0 && !peer) {                               // the tail: evaluate only the chains still running
+        nuts_compact_kernel<<<1, 1024, 0, st>>>(W.live, C, W.active, W.n_active);
+        ++g_launches;
+        n_live = C - n_done;
+        idx = W.active;
+      }
+    } else if (tick >= kLag) {   // the device always has kLag ticks queued; the host never drains the stream
+      if ((rc = wait_tick(tick - kLag, n_done))) break;
+      if (n_done >= C) break;
+    }
+    const unsigned long long seq = peer ? ++pw.seq : 0;
+    launch_state(state_params(tick > 0 && !check, true, tick, prev_seq, seq));
+    prev_seq = seq;
+    if (pooled) {
+      nuts_pool_async_kernel<<<1, 1024, 0, st>>>(a, W, 0);
+      ++g_launches;
+    }
+    const int64_t rows = idx ? n_live : C;
+    const int64_t Cp = rows <= 128 ? 128 : (rows + 255) / 256 * 256;
+    if (peer) {
+      char *mine = pw.base[pw.rank];
+      obs_wait_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const unsigned long long *>(mine + pw.off_bflag), pw.nranks, seq,
+          reinterpret_cast<int *>(mine + pw.off_err), reinterpret_cast<const float4 *>(mine + pw.off_meta), C, gm.y0max_bits,
+          gm.x_rownorm_max, gm.weight, gm.inv_var, gm.a_unscale, gm.r_scale, gm.r_unscale,
+          reinterpret_cast<const long long *>(mine + pw.off_done), h_prog, tick);
+      ++g_launches;
+    }
+    if ((rc = tc_gemm_resid(gm, Cp, st))) break;
+    if (peer) {
+      if ((rc = tc_gemm_grad_push(gm, Cp, st))) break;
+      obs_signal_kernel<<<(unsigned)((Cp + 127) / 128), 128, 0, st>>>(gm.ss_part, gm.Np / 128, Cp, Q, seq, gm.blk_counter + 1);
+      ++g_launches;
+    } else {
+      if ((rc = tc_gemm_grad(gm, Cp, st))) break;
+    }
+    if (cudaGetLastError() != cudaSuccess) { set_error("NUTS fused schedule: launch failed"); rc = 2; }
+  }
+  cleanup();
+  if (!rc && peer) rc = comm_allgather_inplace(gm.comm, a.theta, own * D, 4, st);   // final positions everywhere
+  if (!rc && pooled) {
+    nuts_pool_async_kernel<<<1, 1024, 0, st>>>(a, W, 1);
+    ++g_launches;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc) return rc;
+  B2M_CHECK_CUDA(e);
+  B2M_CHECK_CUDA(cudaGetLastError());
+  if (peer) {
+    int herr = 0;
+    B2M_CHECK_CUDA(cudaMemcpy(&herr, pw.base[pw.rank] + pw.off_err, sizeof(int), cudaMemcpyDeviceToHost));
+    B2M_REQUIRE(herr == 0, "NUTS peer exchange: a flag wait timed out");
+  }
+  return 0;
+}
+
+// schedule / slicing come with the call (b2m_nuts_args; environment variables in ABI 1).  The fused tick needs the
+// fp16-encoded tensor-core path and no draw injection bookkeeping beyond what the device functions already do; the
+// NCCL forms of observation sharding (replicated state, or reduce-scatter + all-gather slicing) keep the unfused loop.
 int glm_nuts_run(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
-  const char *v = getenv("B2M_NUTS_SCHED");
-  if (v && std::string(v) == "sync") return glm_nuts_run_sync(gm, a, st);
+  if (a.schedule == B2M_SCHED_SYNC) return glm_nuts_run_sync(gm, a, st);
+  const bool fused_ok = gm.use_tc == 2 && (!gm.comm || a.slice_state == B2M_SLICE_PEER);
+  if (a.slice_state == B2M_SLICE_PEER && !fused_ok) {
+    set_error("slice_state = PEER needs the fp16-encoded tensor-core path");
+    return 1;
+  }
+  if (fused_ok) return glm_nuts_run_fused(gm, a, st);
   return glm_nuts_run_async(gm, a, st);
 }
 

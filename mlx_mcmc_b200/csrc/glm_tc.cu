@@ -29,6 +29,7 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <vector>
 
 #include "glm.cuh"
@@ -216,6 +217,12 @@ struct EpiParams {
   // it a few launches late because it reads the counter without draining the stream)
   const int *skip_flag;
   int skip_target;
+  // PUSH (K6 of a peer-sliced observation shard): the finished tile goes, unscaled, straight into the window of the
+  // rank that owns its chains -- slot `push_rank` of that rank's [nranks][own][Dp] gradient block -- over NVLink
+  float *push_dst[kMaxPeers];
+  int push_own, push_rank;
+  const float *r_unscale;       // [Cp]
+  const float *inv_col_scale;   // [Dp]
 };
 
 template <int BLOCK_N, int NCTA>
@@ -229,15 +236,17 @@ struct Cfg {
   static constexpr int COLS_PER_WARP = BLOCK_N / 2;    // each promotion warp owns 32 rows x half of the columns
 };
 
-template <int BLOCK_N, bool RESID, int NCTA, bool F16>
+// MODE: 0 = PLAIN (split-K partial of G), 1 = RESID (K5 residual epilogue), 2 = PUSH (K6 tile -> owner's window)
+template <int BLOCK_N, int MODE, int NCTA, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int k_blocks_total,
                int k_blocks_per_split, int CHUNK_KB, int mma_mask, int Tm, int Tn, int n_tiles, EpiParams E) {
   using C = Cfg<BLOCK_N, NCTA>;
+  constexpr bool RESID = MODE == 1, PUSH = MODE == 2;
   if (E.skip_flag && *reinterpret_cast<const volatile int *>(E.skip_flag) >= E.skip_target) return;   // uniform over the grid
   constexpr int BLOCK_K = Enc<F16>::BLOCK_K;   // K elements per k-block (shadows the tf32 constant)
-  constexpr int SCRATCH_BYTES = RESID ? NUM_EPI_WARPS * 32 * 33 * 4 : 0;   // per-warp transpose scratch of the K5 epilogue
+  constexpr int SCRATCH_BYTES = (RESID || PUSH) ? NUM_EPI_WARPS * 32 * 33 * 4 : 0;   // per-warp transpose scratch of the epilogue
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float *scratch_base = reinterpret_cast<float *>(smem + C::STAGES * C::STAGE_BYTES);
@@ -452,6 +461,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         __syncwarp();
       }
       E.ss_part[((int64_t)nt * 2 + half) * E.Cp + m] = ss;
+    } else if (PUSH) {
+      // The tile's 128 rows belong to one owner rank (own % 128 == 0).  Each warp transposes its 32 x 32 blocks through
+      // the shared-memory scratch so that every store instruction writes one 128-byte row segment into the owner's
+      // window: plain NVLink stores, issued while the MMA warp is already accumulating the next tile.  The operand
+      // scales are undone here (the ranks' scales differ); the owner adds the per-source slots in rank order.
+      const int row0 = m0 + q * 32;
+      const int owner = row0 / E.push_own;
+      float *dst = E.push_dst[owner] + ((int64_t)E.push_rank * E.push_own + (row0 - owner * E.push_own)) * E.Dp + nb;
+      const float ru = E.r_unscale ? E.r_unscale[m] : 1.0f;   // lane r: scale of row r of this warp's 32 rows
+      float *scratch = scratch_base + (warp - 2) * (32 * 33);
+#pragma unroll
+      for (int b = 0; b < CW / 32; ++b) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = acc[b * 32 + j] * ru;
+        __syncwarp();
+        const float ics = E.inv_col_scale ? E.inv_col_scale[nb + b * 32 + lane] : 1.0f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) dst[(int64_t)r * E.Dp + b * 32 + lane] = scratch[r * 33 + lane] * ics;
+        __syncwarp();
+      }
     } else {
       float *g = E.Gpart + ((int64_t)zs * E.Cp + m) * E.Dp + nb;
 #pragma unroll
@@ -544,31 +573,34 @@ struct Prof {
   std::vector<cudaEvent_t> ev[2];   // [0] = K5 (residual epilogue), [1] = K6 (split-K gradient): start, stop, start, ...
 } g_prof;
 
-template <int BLOCK_N, bool RESID, int NCTA, bool F16>
+template <int BLOCK_N, int MODE, int NCTA, bool F16>
 int launch_tc_n(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &Bh, const CUtensorMap &Bl, dim3 grid,
                 int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st, int chunk_kb, int mma_mask) {
   using C = Cfg<BLOCK_N, NCTA>;
-  auto kernel = tc_gemm_kernel<BLOCK_N, RESID, NCTA, F16>;
-  constexpr int SMEM = C::SMEM_BYTES + (RESID ? NUM_EPI_WARPS * 32 * 33 * 4 : 0);
-  static bool configured[64] = {};   // per device: the attribute belongs to the function on the current device
+  constexpr bool RESID = MODE == 1;
+  auto kernel = tc_gemm_kernel<BLOCK_N, MODE, NCTA, F16>;
+  constexpr int SMEM = C::SMEM_BYTES + (MODE != 0 ? NUM_EPI_WARPS * 32 * 33 * 4 : 0);
+  // per device: the attribute belongs to the function on the current device.  Setting it again is harmless, so a plain
+  // atomic flag is enough for concurrent first calls from several threads.
+  static std::atomic<bool> configured[64];
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     B2M_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   // `grid` arrives as (128-row tiles, column tiles, K splits); the launch is one persistent CTA group per SM (pair)
   const int Tm = (int)grid.x / NCTA, Tn = (int)grid.y, n_tiles = Tm * Tn * (int)grid.z;
   int n_groups = n_tiles < 148 / NCTA ? n_tiles : 148 / NCTA;
-  if (const char *v = getenv(RESID ? "B2M_TC_GROUPS_RESID" : "B2M_TC_GROUPS_GRAD")) {   // experiments: persistent CTA groups
-    const int want = atoi(v);
+  {   // experiments: fewer persistent CTA groups (read once per process, glm.cuh)
+    const int want = RESID ? tuning().groups_resid : tuning().groups_grad;
     if (want > 0 && want < n_groups) n_groups = want;
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaEventRecord(e0, st);
+    B2M_CHECK_CUDA(cudaEventCreate(&e0));
+    B2M_CHECK_CUDA(cudaEventCreate(&e1));
+    B2M_CHECK_CUDA(cudaEventRecord(e0, st));
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(n_groups * NCTA), 1, 1);
@@ -584,7 +616,7 @@ int launch_tc_n(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap 
   cfg.numAttrs = NCTA == 2 ? 1 : 0;
   B2M_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, Ah, Al, Bh, Bl, kb_total, kb_per_split, chunk_kb, mma_mask, Tm, Tn, n_tiles, E));
   if (g_prof.on) {
-    cudaEventRecord(e1, st);
+    B2M_CHECK_CUDA(cudaEventRecord(e1, st));
     g_prof.ev[RESID ? 0 : 1].push_back(e0);
     g_prof.ev[RESID ? 0 : 1].push_back(e1);
   }
@@ -593,16 +625,21 @@ int launch_tc_n(const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap 
   return 0;
 }
 
-template <int BLOCK_N, bool RESID>
+template <int BLOCK_N, int MODE>
 int launch_tc(int ncta, const CUtensorMap &Ah, const CUtensorMap &Al, const CUtensorMap &Bh, const CUtensorMap &Bl,
               dim3 grid, int kb_total, int kb_per_split, const EpiParams &E, cudaStream_t st,
               int chunk_kb = DEFAULT_CHUNK_KB, int mma_mask = 7, bool f16 = false) {
-  if (f16) {
-    if (ncta == 2) return launch_tc_n<BLOCK_N, RESID, 2, true>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
-    return launch_tc_n<BLOCK_N, RESID, 1, true>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
+  if constexpr (MODE == 2) {   // the push epilogue exists for the shape it is used with: fp16 encoding, CTA pairs
+    B2M_REQUIRE(f16 && ncta == 2, "K6 push epilogue: needs the fp16 encoding and whole 256-row tiles");
+    return launch_tc_n<BLOCK_N, 2, 2, true>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
+  } else {
+    if (f16) {
+      if (ncta == 2) return launch_tc_n<BLOCK_N, MODE, 2, true>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
+      return launch_tc_n<BLOCK_N, MODE, 1, true>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
+    }
+    if (ncta == 2) return launch_tc_n<BLOCK_N, MODE, 2, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
+    return launch_tc_n<BLOCK_N, MODE, 1, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
   }
-  if (ncta == 2) return launch_tc_n<BLOCK_N, RESID, 2, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
-  return launch_tc_n<BLOCK_N, RESID, 1, false>(Ah, Al, Bh, Bl, grid, kb_total, kb_per_split, E, st, chunk_kb, mma_mask);
 }
 
 }  // namespace
@@ -633,19 +670,28 @@ int tc_profile_read(double *out4) {
   return 0;
 }
 
-// k-blocks (of 32) accumulated inside the tensor core between two fp32 promotions; tunable for experiments
-static int chunk_kb(const char *env, int dflt) {
-  const char *v = getenv(env);
-  const int c = v ? atoi(v) : 0;
-  return c > 0 ? c : dflt;
+const Tuning &tuning() {
+  static const Tuning t = [] {   // C++11 magic static: initialised once, thread safe
+    Tuning x;
+    auto geti = [](const char *name, int dflt) {
+      const char *v = getenv(name);
+      return v ? atoi(v) : dflt;
+    };
+    x.groups_resid = geti("B2M_TC_GROUPS_RESID", 0);
+    x.groups_grad = geti("B2M_TC_GROUPS_GRAD", 0);
+    x.chunk_resid = geti("B2M_TC_CHUNK_RESID", 0);
+    x.chunk_grad = geti("B2M_TC_CHUNK_GRAD", 0);
+    x.pair = geti("B2M_TC_PAIR", 1);
+    return x;
+  }();
+  return t;
 }
 
 int grad_block_n(const GlmModel &g) { return g.Dp % 256 == 0 ? 256 : (g.Dp % 128 == 0 ? 128 : 64); }
 
 // CTA pairs need whole 256-row tiles of chains; B2M_TC_PAIR=0 forces the single-CTA kernel (experiments)
 static int pair_mode(int64_t Cp) {
-  const char *v = getenv("B2M_TC_PAIR");
-  if (v && atoi(v) == 0) return 1;
+  if (tuning().pair == 0) return 1;
   return (Cp % 256 == 0) ? 2 : 1;
 }
 
@@ -688,8 +734,8 @@ int tc_gemm_resid(GlmModel &g, int64_t Cp, cudaStream_t st) {
   // promotion interval: 128 values of K for tf32; 256 for fp16 -- the MMAs of a tile take half as long there, and the
   // longer chunk lets the issuer run far enough into the next tile to cover the epilogue (measured at C4: 4.28 ->
   // 4.12 ms per evaluation, gradient error 1.3e-6 -> 2.1e-6; K5's accumulators only hold X (beta - beta0))
-  return launch_tc<256, true>(ncta, Ah, Al, Bh, Bl, grid, g.Dp / bk, g.Dp / bk, E, st,
-                              chunk_kb("B2M_TC_CHUNK_RESID", DEFAULT_CHUNK_KB), 7, f16);
+  const int ck = tuning().chunk_resid > 0 ? tuning().chunk_resid : DEFAULT_CHUNK_KB;
+  return launch_tc<256, 1>(ncta, Ah, Al, Bh, Bl, grid, g.Dp / bk, g.Dp / bk, E, st, ck, 7, f16);
 }
 
 int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
@@ -711,10 +757,35 @@ int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
   E.skip_flag = g.skip_flag; E.skip_target = g.skip_target;
   dim3 grid((unsigned)(Cp / BLOCK_M), g.Dp / bn, (unsigned)((kb_total + kb_per - 1) / kb_per));
   g.g_splits = (int)grid.z;
-  const int ck = chunk_kb("B2M_TC_CHUNK_GRAD", f16 ? DEFAULT_CHUNK_KB / 2 : DEFAULT_CHUNK_KB);
-  if (bn == 256) return launch_tc<256, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck, 7, f16);
-  if (bn == 128) return launch_tc<128, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck, 7, f16);
-  return launch_tc<64, false>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck, 7, f16);
+  const int ck = tuning().chunk_grad > 0 ? tuning().chunk_grad : (f16 ? DEFAULT_CHUNK_KB / 2 : DEFAULT_CHUNK_KB);
+  if (bn == 256) return launch_tc<256, 0>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck, 7, f16);
+  if (bn == 128) return launch_tc<128, 0>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck, 7, f16);
+  return launch_tc<64, 0>(ncta, Ah, Al, Bh, Bl, grid, kb_total, kb_per, E, st, ck, 7, f16);
+}
+
+// K6 of a peer-sliced observation shard: one K pass over the rank's rows (no split-K: every output tile is produced
+// once and leaves through the epilogue), tiles pushed into the owners' windows.
+int tc_gemm_grad_push(GlmModel &g, int64_t Cp, cudaStream_t st) {
+  const PeerWindow &w = g.pw;
+  B2M_REQUIRE(w.nranks >= 2 && g.use_tc == 2 && Cp == w.C && Cp % 256 == 0 && w.own % 128 == 0,
+              "K6 push epilogue: needs an attached peer window, the fp16 encoding and a full batch");
+  const int bk = 64, bn = grad_block_n(g);
+  const int kb_total = g.Np / bk;
+  CUtensorMap Ah, Al, Bh, Bl;
+  if (make_map(&Ah, g.R16h, Cp, g.Np, BLOCK_M, true) || make_map(&Al, g.R16l, Cp, g.Np, BLOCK_M, true) ||
+      make_map(&Bh, g.XT16h, g.Dp, g.Np, bn / 2, true) || make_map(&Bl, g.XT16l, g.Dp, g.Np, bn / 2, true))
+    return 2;
+  EpiParams E{};
+  E.Cp = Cp; E.Dp = g.Dp;
+  E.push_own = (int)w.own; E.push_rank = w.rank;
+  for (int s = 0; s < w.nranks; ++s) E.push_dst[s] = reinterpret_cast<float *>(w.base[s] + w.off_g);
+  E.r_unscale = g.r_unscale; E.inv_col_scale = g.inv_col_scale;
+  dim3 grid((unsigned)(Cp / BLOCK_M), g.Dp / bn, 1);
+  g.g_splits = 1;
+  const int ck = tuning().chunk_grad > 0 ? tuning().chunk_grad : DEFAULT_CHUNK_KB / 2;
+  if (bn == 256) return launch_tc<256, 2>(2, Ah, Al, Bh, Bl, grid, kb_total, kb_total, E, st, ck, 7, true);
+  if (bn == 128) return launch_tc<128, 2>(2, Ah, Al, Bh, Bl, grid, kb_total, kb_total, E, st, ck, 7, true);
+  return launch_tc<64, 2>(2, Ah, Al, Bh, Bl, grid, kb_total, kb_total, E, st, ck, 7, true);
 }
 
 
@@ -743,9 +814,9 @@ int debug_tc_gemm(const float *A, const float *Bm, int M, int N, int K, float *C
     EpiParams E{};
     E.Gpart = Cout; E.Cp = M; E.Dp = N;
     dim3 grid(M / BLOCK_M, N / bn, 1);
-    if (bn == 256) rc = launch_tc<256, false>(ncta, mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
-    else if (bn == 128) rc = launch_tc<128, false>(ncta, mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
-    else rc = launch_tc<64, false>(ncta, mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
+    if (bn == 256) rc = launch_tc<256, 0>(ncta, mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
+    else if (bn == 128) rc = launch_tc<128, 0>(ncta, mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
+    else rc = launch_tc<64, 0>(ncta, mAh, mAl, mBh, mBl, grid, K / BLOCK_K, K / BLOCK_K, E, st, chunk_kb, mma_mask);
   }
   cudaStreamSynchronize(st);
   cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl);

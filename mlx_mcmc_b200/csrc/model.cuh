@@ -34,7 +34,37 @@ struct KModel {
   // gradient evaluation, and theta / gradient never leave registers (no shared-memory mailbox).
   int32_t compact;
   b2m_term cterms[kCompactTerms];
+  // Constraint transforms (B2M_TF_*) per scalar parameter, pointwise class (D <= 16); has_tf = any non-zero entry.
+  // GLM-class models keep their table in device memory (GlmModel::tf).
+  int32_t has_tf;
+  uint8_t tf[16];
 };
+
+// theta = T(u) with d theta / du and the log-Jacobian terms (include/b200mcmc.h, B2M_TF_*)
+struct Tf {
+  float theta, jac, dlogjac, logjac;
+};
+__device__ __forceinline__ Tf tf_apply(int kind, float u) {
+  Tf t;
+  if (kind == B2M_TF_LOG) {
+    t.theta = expf(u); t.jac = t.theta; t.dlogjac = 1.0f; t.logjac = u;
+  } else if (kind == B2M_TF_LOGIT) {
+    const float e = expf(-fabsf(u));            // in (0, 1]: no overflow on either side
+    const float s = 1.0f / (1.0f + e);          // sigmoid(|u|)
+    t.theta = u >= 0.f ? s : e * s;
+    t.jac = e * s * s;                          // theta (1 - theta)
+    t.dlogjac = u >= 0.f ? (e - 1.0f) * s : (1.0f - e) * s;   // 1 - 2 theta
+    t.logjac = -fabsf(u) - 2.0f * log1pf(e);    // log theta + log(1 - theta)
+  } else {
+    t.theta = u; t.jac = 1.0f; t.dlogjac = 0.0f; t.logjac = 0.0f;
+  }
+  return t;
+}
+__device__ __forceinline__ float tf_constrain(int kind, float u) {
+  if (kind == B2M_TF_LOG) return expf(u);
+  if (kind == B2M_TF_LOGIT) { const float e = expf(-fabsf(u)), s = 1.0f / (1.0f + e); return u >= 0.f ? s : e * s; }
+  return u;
+}
 
 // Per-CTA copy in shared memory.
 struct SModel {

@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(64) nuts_kernel(const __grid_constant__ KModel
   float lp = evaluate<DMAX, COMPACT, true>(km, sm, L, q, g);
 
   StackEntry<DMAX> stack[B2M_MAX_TREE_DEPTH];
+  float im[DMAX], sqm[DMAX];   // diagonal mass matrix: all ones unless A.inv_mass is given (x * 1.0f is exact)
+  load_mass<DMAX>(A.inv_mass, D, im, sqm);
 
   for (int it = 0; it < A.n_iter; ++it) {
     const uint32_t giter = (uint32_t)(A.iter_offset + it);
@@ -80,7 +82,9 @@ __global__ void __launch_bounds__(64) nuts_kernel(const __grid_constant__ KModel
 
     float p0[DMAX];
     draw_normals<DMAX>(p0, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0);
-    const float h0 = __fadd_rn(-lp, kinetic<DMAX>(p0, D));
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) p0[d] = __fmul_rn(p0[d], sqm[d]);   // p ~ N(0, M)
+    const float h0 = __fadd_rn(-lp, kinetic_m<DMAX>(p0, im, D));
     // step size of this iteration: jittered when asked for (extension), else exactly eps
     const double eps_it = A.step_size_jitter > 0.f ? eps * (1.0 + (double)A.step_size_jitter * (2.0 * (double)u01(w0.w) - 1.0)) : eps;
     const float us = A.inj_slice ? A.inj_slice[row] : u01(w0.z);
@@ -126,13 +130,13 @@ __global__ void __launch_bounds__(64) nuts_kernel(const __grid_constant__ KModel
 #pragma unroll
         for (int d = 0; d < DMAX; ++d) {
           fp[d] = __fadd_rn(fp[d], __fmul_rn(half_eps, fg[d]));
-          fq[d] = __fadd_rn(fq[d], __fmul_rn(feps, fp[d]));
+          fq[d] = __fadd_rn(fq[d], __fmul_rn(feps, __fmul_rn(im[d], fp[d])));
         }
         const float flp = evaluate<DMAX, COMPACT, true>(km, sm, L, fq, fg);
 #pragma unroll
         for (int d = 0; d < DMAX; ++d) fp[d] = __fadd_rn(fp[d], __fmul_rn(half_eps, fg[d]));
         ++n_leaves;
-        const float h1 = __fadd_rn(-flp, kinetic<DMAX>(fp, D));
+        const float h1 = __fadd_rn(-flp, kinetic_m<DMAX>(fp, im, D));
         const int n1 = (log_slice <= -h1) ? 1 : 0;
         const bool s1 = log_slice < __fsub_rn(1000.0f, h1);
         float a1 = expf(__fadd_rn(-h1, h0));
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(64) nuts_kernel(const __grid_constant__ KModel
 
     if (A.adapt == B2M_ADAPT_DUAL_AVERAGING) {
       // nuts.py:298-310 with its float32 / float64 split
-      const double m = (double)giter;
+      const double m = (double)((int64_t)giter - A.adapt_origin);
       const double eta = 1.0 / (m + 10.0);
       h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - mean_alpha);
       float log_eps = __fsub_rn(mu, (float)((sqrt(m + 1.0) / 0.05) * h_bar));
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(64) nuts_kernel(const __grid_constant__ KModel
     }
 
     if (L.writer) {
-      if (A.draws) store_vec<DMAX>(A.draws + row * D, q, D);
+      if (A.draws) store_draw<DMAX>(A.draws + row * D, q, D, km, A.draws_unconstrained != 0);
       if (A.depths) A.depths[row] = j;
       if (A.alphas) A.alphas[row] = (float)mean_alpha;
     }

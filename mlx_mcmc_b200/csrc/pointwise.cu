@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ KModel
   }
 
   float lp = evaluate<DMAX, COMPACT, true>(km, sm, L, q, g);
+  float im[DMAX], sqm[DMAX];   // diagonal mass matrix: all ones unless A.inv_mass is given (x * 1.0f is exact)
+  load_mass<DMAX>(A.inv_mass, D, im, sqm);
 
   for (int it = 0; it < A.n_iter; ++it) {
     const uint32_t giter = (uint32_t)(A.iter_offset + it);
@@ -74,7 +76,9 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ KModel
 
     float p[DMAX];
     draw_normals<DMAX>(p, D, A.inj_normal ? A.inj_normal + row * D : nullptr, A.seed, gchain, giter, w0);
-    const float h_init = __fadd_rn(-lp, kinetic<DMAX>(p, D));
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) p[d] = __fmul_rn(p[d], sqm[d]);   // p ~ N(0, M)
+    const float h_init = __fadd_rn(-lp, kinetic_m<DMAX>(p, im, D));
 
     float qn[DMAX], gn[DMAX];
 #pragma unroll
@@ -85,13 +89,13 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ KModel
 #pragma unroll
       for (int d = 0; d < DMAX; ++d) {
         p[d] = __fadd_rn(p[d], __fmul_rn(half_eps, gn[d]));
-        qn[d] = __fadd_rn(qn[d], __fmul_rn(feps, p[d]));
+        qn[d] = __fadd_rn(qn[d], __fmul_rn(feps, __fmul_rn(im[d], p[d])));
       }
       lpn = evaluate<DMAX, COMPACT, true>(km, sm, L, qn, gn);
 #pragma unroll
       for (int d = 0; d < DMAX; ++d) p[d] = __fadd_rn(p[d], __fmul_rn(half_eps, gn[d]));
     }
-    const float h_prop = __fadd_rn(-lpn, kinetic<DMAX>(p, D));
+    const float h_prop = __fadd_rn(-lpn, kinetic_m<DMAX>(p, im, D));
     const float u = A.inj_uniform ? A.inj_uniform[row] : u01(w0.z);
     const float log_ratio = -(__fsub_rn(h_prop, h_init));
     const bool accept = logf(u) < log_ratio;  // NaN => false => reject
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ KModel
       // Hoffman & Gelman Alg. 5 recurrences with the constants the reference uses in nuts.py:62-68
       // a divergent trajectory (NaN / -inf energy) counts as acceptance probability 0
       float a = (log_ratio == log_ratio) ? expf(fminf(log_ratio, 0.f)) : 0.f;
-      const double m = (double)giter + 1.0, eta = 1.0 / (m + 10.0);
+      const double m = (double)((int64_t)giter - A.adapt_origin) + 1.0, eta = 1.0 / (m + 10.0);
       h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - (double)a);
       double log_eps = da_mu - sqrt(m) / 0.05 * h_bar;
       log_eps = fmin(fmax(log_eps, -10.0), 10.0);
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(128) hmc_kernel(const __grid_constant__ KModel
 
     if (L.writer) {
       if (A.draws)
-        store_vec<DMAX>(A.draws + row * D, q, D);
+        store_draw<DMAX>(A.draws + row * D, q, D, km, A.draws_unconstrained != 0);
       if (A.trace_energy) { A.trace_energy[row * 2] = h_init; A.trace_energy[row * 2 + 1] = h_prop; }
       if (A.trace_accept) A.trace_accept[row] = accept ? 1 : 0;
     }
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(128) mh_kernel(const __grid_constant__ KModel 
     }
     if (L.writer) {
       if (A.draws)
-        store_vec<DMAX>(A.draws + row * D, q, D);
+        store_draw<DMAX>(A.draws + row * D, q, D, km, false);
       if (A.trace_accept) A.trace_accept[row] = accept ? 1 : 0;
     }
   }

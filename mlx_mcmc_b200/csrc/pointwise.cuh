@@ -102,8 +102,8 @@ __device__ __forceinline__ Lane make_lane(int64_t n_chains, int G, unsigned char
 // One fused value(+gradient): compact models evaluate from registers and the constant bank, the general path goes
 // through the shared-memory mailbox.  Identical arithmetic either way.
 template <int DMAX, bool COMPACT, bool GRAD>
-__device__ __forceinline__ float evaluate(const KModel &km, const SModel &sm, const Lane &L, const float (&q)[DMAX],
-                                          float (&g)[DMAX]) {
+__device__ __forceinline__ float evaluate_plain(const KModel &km, const SModel &sm, const Lane &L, const float (&q)[DMAX],
+                                                float (&g)[DMAX]) {
   if constexpr (COMPACT) {
     return eval_model_c<GRAD, DMAX>(km, sm, q, g, L.lane, L.G, L.gmask);
   } else {
@@ -112,6 +112,56 @@ __device__ __forceinline__ float evaluate(const KModel &km, const SModel &sm, co
     if (GRAD) from_mailbox<DMAX>(g, L.gr, L.TS, sm.D);
     return lp;
   }
+}
+
+// With constraint transforms the chain state `q` is the unconstrained coordinate u: the model is evaluated at
+// theta = T(u), the gradient is chained through dT/du and the log-Jacobian joins value and gradient.  km.has_tf is a
+// kernel-parameter constant: models without transforms (the reference's behaviour) take the first branch unchanged.
+template <int DMAX, bool COMPACT, bool GRAD>
+__device__ __forceinline__ float evaluate(const KModel &km, const SModel &sm, const Lane &L, const float (&q)[DMAX],
+                                          float (&g)[DMAX]) {
+  if (!km.has_tf) return evaluate_plain<DMAX, COMPACT, GRAD>(km, sm, L, q, g);
+  float th[DMAX], jac[DMAX], dlj[DMAX], lj = 0.f;
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) {
+    const Tf t = tf_apply(d < 16 ? km.tf[d] : 0, q[d]);
+    th[d] = t.theta; jac[d] = t.jac; dlj[d] = t.dlogjac;
+    if (d < sm.D) lj += t.logjac;
+  }
+  const float lp = evaluate_plain<DMAX, COMPACT, GRAD>(km, sm, L, th, g);
+  if (GRAD) {
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) g[d] = fmaf(g[d], jac[d], dlj[d]);
+  }
+  return lp + lj;
+}
+
+// a draw as the caller wants it: the constrained value unless the call asks for the sampler's own coordinates
+template <int DMAX>
+__device__ __forceinline__ void store_draw(float *dst, const float (&q)[DMAX], int D, const KModel &km, bool unconstrained) {
+  if (!km.has_tf || unconstrained) { store_vec<DMAX>(dst, q, D); return; }
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d)
+    if (d < D) dst[d] = tf_constrain(d < 16 ? km.tf[d] : 0, q[d]);
+}
+
+// diagonal mass matrix (ABI 2): im = diag(M^-1) or all ones, sm_ = sqrt of the diagonal of M
+template <int DMAX>
+__device__ __forceinline__ void load_mass(const float *inv_mass, int D, float (&im)[DMAX], float (&sq)[DMAX]) {
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) {
+    im[d] = (inv_mass && d < D) ? inv_mass[d] : 1.0f;
+    sq[d] = (inv_mass && d < D) ? 1.0f / sqrtf(im[d]) : 1.0f;
+  }
+}
+// kinetic energy 0.5 * sum p_d^2 / m_d, summed left to right; identical to kinetic() when im == 1
+template <int DMAX>
+__device__ __forceinline__ float kinetic_m(const float (&p)[DMAX], const float (&im)[DMAX], int D) {
+  float s = 0.f;
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d)
+    if (d < D) s = __fadd_rn(s, __fmul_rn(__fmul_rn(p[d], p[d]), im[d]));
+  return __fmul_rn(0.5f, s);
 }
 
 // ---------------------------------------------------------------- host-side launchers

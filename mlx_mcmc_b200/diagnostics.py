@@ -119,3 +119,24 @@ def device_summary(draws, layout=None, ess: bool = True, ess_mode: int = 0):
     for name, (off, n, shp) in layout.items():
         table[name] = {k: (float(v[off]) if not shp else v[off:off + n].copy()) for k, v in cols.items()}
     return table
+
+
+def device_quantiles(x, q):
+    """Quantiles `q` (fractions in [0, 1]) of the float32 CUDA tensor `x` (any shape, pooled), numpy's default linear
+    interpolation, by the library's radix-select kernels (b2m_quantiles): three histogram passes over x resolve all
+    requested order statistics at once; replaces np.median / np.percentile of mlx_mcmc/inference/mcmc.py:221-224."""
+    import torch
+    from . import _cabi
+    if not (x.is_cuda and x.dtype == torch.float32):
+        raise ValueError("device_quantiles expects a float32 CUDA tensor")
+    x = x.contiguous().reshape(-1)
+    q = [float(v) for v in q]
+    if not q or len(q) > 8 or any(not 0.0 <= v <= 1.0 for v in q):
+        raise ValueError("device_quantiles: 1..8 quantiles in [0, 1]")
+    lib = _cabi.load()
+    qa = (C.c_double * len(q))(*q)
+    out = (C.c_double * len(q))()
+    with torch.cuda.device(x.device):
+        _cabi.check(lib.b2m_quantiles(C.c_void_p(x.data_ptr()), x.numel(), qa, len(q), out,
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return [float(v) for v in out]

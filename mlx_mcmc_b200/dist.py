@@ -207,16 +207,77 @@ class ObsComm:
             pass
 
 
-def compile_obs_sharded(log_prob_fn, initial_params, group=None, comm: Optional[ObsComm] = None):
-    """Trace once, keep this rank's rows, build the device model and attach the communicator."""
+class PeerWindow:
+    """The peer window of the fused gradient exchange (include/b200mcmc.h, B2M_SLICE_PEER): one cudaMalloc'd window per
+    rank, shared through CUDA IPC handles that travel over `torch.distributed`; collective over the group.  After
+    construction `nuts(..., slice_state='peer')` on `model` exchanges gradients through plain NVLink stores issued by
+    the kernels themselves -- K6's epilogue pushes every finished tile into its owner's window."""
+
+    def __init__(self, model, num_chains: int, group=None):
+        from . import _cabi
+        self.lib = _cabi.load()
+        self.rank, self.world = rank_world(group)
+        self.group = group
+        self.num_chains = int(num_chains)
+        self.own = C.c_void_p()
+        self.mapped = {}
+        nbytes = C.c_int64()
+        with torch.cuda.device(model.device):
+            _cabi.check(self.lib.b2m_model_peer_bytes(model.handle, self.num_chains, self.world, C.byref(nbytes)))
+            handle = (C.c_uint8 * 64)()
+            _cabi.check(self.lib.b2m_peer_alloc(nbytes.value, C.byref(self.own), handle))
+        self.bytes = nbytes.value
+        mine = torch.tensor(list(handle), dtype=torch.uint8)
+        nccl = td.get_backend(group) == "nccl"
+        carrier = mine.to(model.device) if nccl else mine
+        parts = [torch.zeros_like(carrier) for _ in range(self.world)]
+        td.all_gather(parts, carrier, group=group)
+        ptrs = (C.c_void_p * self.world)()
+        with torch.cuda.device(model.device):
+            for s in range(self.world):
+                if s == self.rank:
+                    ptrs[s] = self.own.value
+                    continue
+                raw = (C.c_uint8 * 64)(*parts[s].cpu().tolist())
+                p = C.c_void_p()
+                _cabi.check(self.lib.b2m_peer_open(raw, C.byref(p)))
+                self.mapped[s] = p
+                ptrs[s] = p.value
+            td.barrier(group=group)       # every window exists and is zeroed before anybody stores into it
+            _cabi.check(self.lib.b2m_model_peer_attach(model.handle, ptrs, self.world, self.rank, self.num_chains, self.bytes))
+        model._peer = self
+
+    def close(self):
+        mapped, self.mapped = self.mapped, {}
+        for p in mapped.values():
+            try:
+                self.lib.b2m_peer_close(p)
+            except Exception:
+                pass
+        own, self.own = self.own, C.c_void_p()
+        if own:
+            try:
+                if td.is_initialized():
+                    td.barrier(group=self.group)     # nobody still maps this window
+                self.lib.b2m_peer_free(own)
+            except Exception:
+                pass
+
+
+def compile_obs_sharded(log_prob_fn, initial_params, group=None, comm: Optional[ObsComm] = None,
+                        peer_chains: Optional[int] = None, glm_path: str = "auto"):
+    """Trace once, keep this rank's rows, build the device model and attach the communicator.  `peer_chains`: also set
+    up the peer window for sliced NUTS runs of that many chains (`nuts(..., slice_state='peer')`)."""
     from .engine import DeviceModel, _require_cuda
     from .tracer import trace
     rank, world = rank_world(group)
     traced = shard_observations(trace(log_prob_fn, initial_params), rank, world)
-    model = DeviceModel(traced, _require_cuda())
+    model = DeviceModel(traced, _require_cuda(), glm_path=glm_path)
     model._fn = log_prob_fn
     if world > 1:
         (comm or ObsComm(group, model.device)).attach(model)
+        if peer_chains:
+            PeerWindow(model, peer_chains, group)
     return model
 
 
@@ -256,7 +317,8 @@ def run_sharded(log_prob_fn, initial_params, method: str = "nuts", num_chains: i
         return samples, rate, info
     if kwargs.get("slice_state") and method != "nuts":
         raise ValueError("slice_state is a NUTS option")
-    model = compile_obs_sharded(log_prob_fn, initial_params, group)
+    peer = num_chains if kwargs.get("slice_state") in (True, "peer") and world > 1 else None
+    model = compile_obs_sharded(log_prob_fn, initial_params, group, peer_chains=peer)
     samples, rate, info = samplers[method](log_prob_fn, initial_params, num_chains=num_chains, model=model, **kwargs)
     if num_chains == 1:
         samples = {k: v[None] for k, v in samples.items()}

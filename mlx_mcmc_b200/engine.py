@@ -31,14 +31,28 @@ def _stream():
 
 
 class DeviceModel:
-    """A traced model resident on one GPU (observed arrays in HBM, term table inside the C handle)."""
+    """A traced model resident on one GPU (observed arrays in HBM, term table inside the C handle).
 
-    def __init__(self, traced: TracedModel, device: Optional[torch.device] = None):
+    ``glm_path`` ('auto' | 'simt' | 'tc' | 'tc16') and ``pointwise_path`` ('auto' | 'general') choose the arithmetic /
+    evaluation path (b2m_model_options; they were environment variables in ABI 1).  ``transforms``: None (the
+    reference: the sampler moves in the model's own coordinates) or 'auto' -- positive / unit-interval parameters,
+    recognised from the support of the distribution they are the value of, are sampled in log / logit coordinates."""
+
+    def __init__(self, traced: TracedModel, device: Optional[torch.device] = None, glm_path: str = "auto",
+                 pointwise_path: str = "auto", transforms=None):
         self.lib = _cabi.load()
         self.device = device or _require_cuda()
         self.traced = traced
         self.D = traced.D
         self.layout = traced.layout
+        if glm_path not in _cabi.GLM_PATHS:
+            raise ValueError(f"Unknown glm_path: {glm_path}")
+        if pointwise_path not in ("auto", "general"):
+            raise ValueError(f"Unknown pointwise_path: {pointwise_path}")
+        if transforms not in (None, "auto"):
+            raise ValueError(f"Unknown transforms option: {transforms}")
+        self.tf_codes = traced.transform_codes() if transforms == "auto" else np.zeros(traced.D, dtype=np.int32)
+        self.has_transforms = bool(np.any(self.tf_codes != 0))
         # observed arrays: uploaded once, kept alive by this object (the library never owns them)
         self._arrays = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device) for a in traced.arrays]
         n_t, n_a, n_l = len(traced.terms), len(traced.arrays), len(traced.lin)
@@ -58,8 +72,13 @@ class DeviceModel:
             arrays[i].rows = a.shape[0]
             arrays[i].cols = a.shape[1] if a.dim() == 2 else 1
         handle = C.c_void_p()
+        opt = _cabi.ModelOptions()
+        opt.glm_path = _cabi.GLM_PATHS[glm_path]
+        opt.pointwise_path = _cabi.POINTWISE_GENERAL if pointwise_path == "general" else _cabi.POINTWISE_AUTO
+        tf_arr = (C.c_int32 * self.D)(*[int(v) for v in self.tf_codes])
+        opt.transforms = tf_arr if self.has_transforms else None
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.b2m_model_create(terms, n_t, lin, n_l, arrays, n_a, self.D, C.byref(handle)))
+            _cabi.check(self.lib.b2m_model_create(terms, n_t, lin, n_l, arrays, n_a, self.D, C.byref(opt), C.byref(handle)))
         self.handle = handle
         self.model_class = self.lib.b2m_model_class(handle)
         self.glm_path = {0: "simt", 1: "tc", 2: "tc16"}.get(self.lib.b2m_model_glm_path(handle))
@@ -85,7 +104,28 @@ class DeviceModel:
                 flat[:, off:off + n] = v.reshape(n_chains, n)
             else:
                 raise ValueError(f"initial value of {name!r} has shape {v.shape}, expected {shp} or ({n_chains},)+{shp}")
+        if self.has_transforms:
+            flat = self.unconstrain(flat)
         return torch.from_numpy(flat).to(self.device)
+
+    def unconstrain(self, theta: np.ndarray) -> np.ndarray:
+        """model coordinates -> the sampler's coordinates (log / logit of the transformed parameters), float32 [.., D]"""
+        out = np.array(theta, dtype=np.float64, copy=True)
+        pos, unit = self.tf_codes == _cabi.TF_LOG, self.tf_codes == _cabi.TF_LOGIT
+        with np.errstate(divide="ignore", invalid="ignore"):
+            bad = (out[..., pos] <= 0).any() or (out[..., unit] <= 0).any() or (out[..., unit] >= 1).any()
+            if bad:
+                raise ValueError("transforms='auto': an initial value lies outside the support of its parameter")
+            out[..., pos] = np.log(out[..., pos])
+            out[..., unit] = np.log(out[..., unit]) - np.log1p(-out[..., unit])
+        return out.astype(np.float32)
+
+    def constrain(self, u: torch.Tensor) -> torch.Tensor:
+        """the sampler's coordinates -> model coordinates (device tensor [.., D]); identity without transforms"""
+        if not self.has_transforms:
+            return u
+        codes = torch.from_numpy(self.tf_codes).to(u.device)
+        return torch.where(codes == _cabi.TF_LOG, u.exp(), torch.where(codes == _cabi.TF_LOGIT, torch.sigmoid(u), u))
 
     def unpack(self, draws: torch.Tensor, squeeze_chain: bool, to_numpy: bool = True):
         """draws [S, C, D] -> {name: (S,) | (S, n) | (C, S) | (C, S, n)} in the reference's shapes.
@@ -152,7 +192,8 @@ class ChainState:
 
 def launch_hmc(st: ChainState, n_iter: int, n_leapfrog: int, adapt: int, target_accept: float, seed: int,
                iter_offset: int, draws: Optional[torch.Tensor] = None, lanes: int = 0, inj_normal=None,
-               inj_uniform=None, trace_energy=None, trace_accept=None):
+               inj_uniform=None, trace_energy=None, trace_accept=None, inv_mass=None, draws_unconstrained: bool = False,
+               adapt_origin: int = 0):
     m = st.model
     a = _cabi.HmcArgs()
     a.n_chains, a.chain_offset, a.iter_offset = st.n_chains, st.chain_offset, iter_offset
@@ -162,6 +203,8 @@ def launch_hmc(st: ChainState, n_iter: int, n_leapfrog: int, adapt: int, target_
     a.da_state, a.draws = _ptr(st.da_state), _ptr(draws)
     a.inj_normal, a.inj_uniform = _ptr(inj_normal), _ptr(inj_uniform)
     a.trace_energy, a.trace_accept = _ptr(trace_energy), _ptr(trace_accept)
+    a.inv_mass, a.draws_unconstrained = _ptr(inv_mass), int(bool(draws_unconstrained))
+    a.adapt_origin = int(adapt_origin)
     with torch.cuda.device(m.device):
         _cabi.check(m.lib.b2m_hmc_run(m.handle, C.byref(a), _stream()))
 
@@ -181,7 +224,8 @@ def launch_mh(st: ChainState, n_iter: int, proposal_scale: float, seed: int, ite
 
 def launch_nuts(st: ChainState, n_iter: int, max_tree_depth: int, adapt: int, compat: int, target_accept: float,
                 seed: int, iter_offset: int, draws=None, depths=None, alphas=None, lanes: int = 0, inj=None,
-                trace_doubling=None, trace_energy=None, step_size_jitter: float = 0.0):
+                trace_doubling=None, trace_energy=None, step_size_jitter: float = 0.0, inv_mass=None,
+                schedule: int = 0, slice_state: int = 0, draws_unconstrained: bool = False, adapt_origin: int = 0):
     m = st.model
     inj = inj or {}
     a = _cabi.NutsArgs()
@@ -195,22 +239,64 @@ def launch_nuts(st: ChainState, n_iter: int, max_tree_depth: int, adapt: int, co
     a.inj_normal, a.inj_slice = _ptr(inj.get("normal")), _ptr(inj.get("slice"))
     a.inj_dir, a.inj_take, a.inj_merge = _ptr(inj.get("dir")), _ptr(inj.get("take")), _ptr(inj.get("merge"))
     a.trace_doubling, a.trace_energy = _ptr(trace_doubling), _ptr(trace_energy)
+    a.inv_mass, a.schedule, a.slice_state = _ptr(inv_mass), int(schedule), int(slice_state)
+    a.draws_unconstrained = int(bool(draws_unconstrained))
+    a.adapt_origin = int(adapt_origin)
     with torch.cuda.device(m.device):
         _cabi.check(m.lib.b2m_nuts_run(m.handle, C.byref(a), _stream()))
 
 
-_MODEL_CACHE: Dict[tuple, DeviceModel] = {}
+# ---------------------------------------------------------------------------------------- model cache
+# The reference evaluates the user's log_prob afresh on every call (hmc.py:53-67), so data the function closes over may
+# change between run() calls.  Here every compile_model call RE-TRACES the function on the host (cheap: one Python call)
+# and the cache is keyed by a fingerprint of what the trace produced -- term table, parameter layout and the contents of
+# every observed array -- never by the function object.  Same trace => the resident device model is reused (no
+# re-upload of the observations); anything else builds a new one.  Least-recently-used models beyond `_CACHE_SIZE` are
+# dropped, so a `make_log_prob(y)` factory pattern cannot pile up device models.
+_MODEL_CACHE: "Dict[tuple, DeviceModel]" = {}
+_CACHE_SIZE = 4
 
 
-def compile_model(log_prob_fn, initial_params, cache: bool = True) -> DeviceModel:
-    """Trace `log_prob_fn` once and build its device model.  Cached per (function object, parameter
-    shapes, device) so repeated run() calls do not re-trace or re-upload the observations."""
+def _array_fingerprint(a: np.ndarray) -> tuple:
+    b = np.ascontiguousarray(a)
+    raw = b.view(np.uint8).reshape(-1)
+    n4 = raw.size // 4
+    words = raw[: n4 * 4].view(np.uint32)
+    # two position-dependent 64-bit sums over the raw words: any single changed element changes the first, a swap of
+    # two elements of different parity changes the second; memory-bound (tens of ms for the 400 MB design matrix)
+    return (b.shape, str(b.dtype), int(words.sum(dtype=np.uint64)), int(words[1::2].sum(dtype=np.uint64)),
+            bytes(raw[n4 * 4:]))
+
+
+def _trace_fingerprint(traced: TracedModel, extra: tuple) -> tuple:
+    terms = tuple((t.dist, t.length, t.weight, t.k, t.x.key(), t.p0.key(), t.p1.key()) for t in traced.terms)
+    layout = tuple((k, v) for k, v in traced.layout.items())
+    return (traced.D, layout, terms, tuple(traced.lin), tuple(_array_fingerprint(a) for a in traced.arrays), extra)
+
+
+def clear_model_cache() -> None:
+    """Drop every cached device model (their HBM is released when the last reference goes)."""
+    _MODEL_CACHE.clear()
+
+
+def compile_model(log_prob_fn, initial_params, cache: bool = True, glm_path: str = "auto", pointwise_path: str = "auto",
+                  transforms=None) -> DeviceModel:
+    """Trace `log_prob_fn` (always) and return its device model: a cached one when the trace -- terms, layout and the
+    contents of the observed arrays -- is identical to one already resident on this device, else a new one.
+    ``cache=False`` neither looks up nor stores."""
     dev = _require_cuda()
-    key = (id(log_prob_fn), tuple((k, np.asarray(v).shape) for k, v in initial_params.items()), dev.index)
-    if cache and key in _MODEL_CACHE and _MODEL_CACHE[key]._fn is log_prob_fn:
-        return _MODEL_CACHE[key]
-    model = DeviceModel(trace(log_prob_fn, initial_params), dev)
+    traced = trace(log_prob_fn, initial_params)
+    key = None
+    if cache:
+        key = _trace_fingerprint(traced, (dev.index, glm_path, pointwise_path, transforms))
+        hit = _MODEL_CACHE.pop(key, None)
+        if hit is not None:
+            _MODEL_CACHE[key] = hit          # most recently used goes last
+            return hit
+    model = DeviceModel(traced, dev, glm_path=glm_path, pointwise_path=pointwise_path, transforms=transforms)
     model._fn = log_prob_fn
     if cache:
         _MODEL_CACHE[key] = model
+        while len(_MODEL_CACHE) > _CACHE_SIZE:
+            _MODEL_CACHE.pop(next(iter(_MODEL_CACHE)))
     return model

@@ -87,23 +87,14 @@ class MCMC:
         table = {}
         for name, draws in self.samples.items():
             if hasattr(draws, "is_cuda") and draws.is_cuda:
-                # device draws (return_torch=True): moments from the diagnostics kernels, order statistics with
-                # torch.kthvalue on the device -- the draws never travel to the host
-                import torch
-                from ..diagnostics import device_summary
+                # device draws (return_torch=True): moments from the diagnostics kernels, the three order statistics from
+                # ONE radix-select pass set over the pooled draws (b2m_quantiles) -- the draws never travel to the host
+                from ..diagnostics import device_quantiles, device_summary
                 x = draws.reshape(1, -1, 1).permute(1, 0, 2).contiguous().float()      # one pooled series [S*, 1, 1]
                 cols = device_summary(x, None, ess=False)
-                flat = draws.reshape(-1).float()
-                n = flat.numel()
-
-                def pct(q):      # numpy's default (linear) interpolation between the two neighbouring order statistics
-                    pos = q / 100.0 * (n - 1)
-                    lo_i, hi_i = int(np.floor(pos)), int(np.ceil(pos))
-                    lo_v = flat.kthvalue(lo_i + 1).values
-                    hi_v = flat.kthvalue(hi_i + 1).values if hi_i != lo_i else lo_v
-                    return float(lo_v + (hi_v - lo_v) * (pos - lo_i))
-                table[name] = {'mean': float(cols["mean"][0]), 'std': float(cols["std"][0]), 'median': pct(50.0),
-                               f'{lo:.1f}%': pct(lo), f'{hi:.1f}%': pct(hi)}
+                med, q_lo, q_hi = device_quantiles(draws.reshape(-1).float(), [0.5, lo / 100.0, hi / 100.0])
+                table[name] = {'mean': float(cols["mean"][0]), 'std': float(cols["std"][0]), 'median': med,
+                               f'{lo:.1f}%': q_lo, f'{hi:.1f}%': q_hi}
                 continue
             x = np.asarray(draws.detach().cpu() if hasattr(draws, "detach") else draws)
             table[name] = {

@@ -425,6 +425,9 @@ class TraceContext:
                 return Operand(OP_CONST, c=float(c.reshape(-1)[0]))
             if c.ndim != 1:
                 raise UnsupportedOpError("distribution arguments must be scalars or 1-D arrays")
+            if c.shape[0] != length:
+                raise UnsupportedOpError(f"cannot broadcast an observed array of length {c.shape[0]} against a term of "
+                                         f"length {length}")
             return Operand(OP_DATA, a=self.add_array(c))
         const_scalar = sum(c.scale for c in v.const if c.array < 0)
         const_arrays = [c for c in v.const if c.array >= 0]
@@ -454,6 +457,9 @@ class TraceContext:
 
     def log_density(self, dist: int, value, p0=None, p1=None, k=(0.0, 0.0, 0.0)) -> LogProb:
         """Called by the distribution classes when any argument is traced."""
+        # python lists / tuples are data like numpy arrays (the reference does `value = mx.array(value)`)
+        value, p0, p1 = (np.asarray(v, dtype=np.float32) if isinstance(v, (list, tuple)) and _concrete(v) is not None else v
+                         for v in (value, p0, p1))
         length = 1
         for v in (value, p0, p1):
             if v is None:
@@ -500,6 +506,30 @@ class TracedModel:
     @property
     def is_glm(self):
         return any(o.kind == OP_MATVEC for t in self.terms for o in (t.x, t.p0, t.p1))
+
+    def transform_codes(self) -> np.ndarray:
+        """Per flat parameter index: 0 none, 1 log, 2 logit (include/b200mcmc.h B2M_TF_*), chosen from the support of
+        the library distribution the parameter is the VALUE of: HalfNormal / Exponential / Gamma => positive => log;
+        Beta => unit interval => logit.  A parameter claimed by both kinds keeps its own coordinate."""
+        want = {HALFNORMAL: 1, EXPONENTIAL: 1, GAMMA: 1, BETA: 2}
+        codes = np.zeros(self.D, dtype=np.int32)
+        clash = np.zeros(self.D, dtype=bool)
+        for t in self.terms:
+            code = want.get(t.dist)
+            if code is None:
+                continue
+            if t.x.kind == OP_PARAM:
+                idx = [t.x.a]
+            elif t.x.kind == OP_PARAMVEC:
+                idx = range(t.x.a, t.x.a + t.length)
+            else:
+                continue
+            for i in idx:
+                if codes[i] not in (0, code):
+                    clash[i] = True
+                codes[i] = code
+        codes[clash] = 0
+        return codes
 
     def describe(self) -> str:
         rows = []

@@ -126,9 +126,11 @@ def test_sliced_state_preconditions():
     from types import SimpleNamespace as NS
     from mlx_mcmc_b200.kernels.nuts import _sliced_world
     comm2 = NS(world=2)
-    assert _sliced_world(NS(_comm=comm2, model_class=1), 512) == 2
+    assert _sliced_world(NS(_comm=comm2, model_class=1), 512, "async") == 2
+    with pytest.raises(ValueError):
+        _sliced_world(NS(_comm=comm2, model_class=1), 512, "sync")
     for model, chains in ((NS(_comm=None, model_class=1), 512), (NS(_comm=NS(world=1), model_class=1), 512),
                           (NS(_comm=comm2, model_class=0), 512), (NS(_comm=comm2, model_class=1), 384),
                           (NS(_comm=NS(world=3), model_class=1), 512)):
         with pytest.raises(ValueError):
-            _sliced_world(model, chains)
+            _sliced_world(model, chains, "async")

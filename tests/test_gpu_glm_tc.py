@@ -16,16 +16,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _model(path, n, d, seed):
-    old = os.environ.get("B2M_GLM_PATH")
-    os.environ["B2M_GLM_PATH"] = path
-    try:
-        fn, init, meta = W.regression(B.ns, n, d, seed=seed)
-        return compile_model(fn, init, cache=False), meta
-    finally:
-        if old is None:
-            os.environ.pop("B2M_GLM_PATH", None)
-        else:
-            os.environ["B2M_GLM_PATH"] = old
+    fn, init, meta = W.regression(B.ns, n, d, seed=seed)
+    return compile_model(fn, init, cache=False, glm_path=path), meta
 
 
 def _float64(meta, theta):

@@ -203,14 +203,21 @@ def test_nuts_tree_decisions_match_reference(cuda, name, lanes):
 
 
 @pytest.mark.parametrize("name", ["nuts_regression", "nuts_regression_sigma"])
-def test_nuts_tree_decisions_match_reference_sync_schedule(cuda, name, monkeypatch):
-    """GLM class: the synchronous lock-step schedule (B2M_NUTS_SCHED=sync) against the same reference transitions
-    (the default, iteration-asynchronous schedule is what the test above runs)."""
-    monkeypatch.setenv("B2M_NUTS_SCHED", "sync")
-    _replay_nuts(name, 1)
+def test_nuts_tree_decisions_match_reference_sync_schedule(cuda, name):
+    """GLM class: the synchronous lock-step schedule (b2m_nuts_args.schedule = B2M_SCHED_SYNC) against the same
+    reference transitions (the default, iteration-asynchronous fused-tick schedule is what the test above runs)."""
+    _replay_nuts(name, 1, schedule=_cabi.SCHED_SYNC)
 
 
-def _replay_nuts(name, lanes):
+@pytest.mark.parametrize("name", ["nuts_regression", "nuts_regression_sigma"])
+@pytest.mark.parametrize("path", ["tc", "simt"])
+def test_nuts_tree_decisions_match_reference_unfused_paths(cuda, name, path):
+    """GLM class: the tf32 / fp32 arithmetic paths keep the unfused asynchronous loop (tick, pack, K5, K6, finish as
+    separate launches); the default fp16-encoded path runs the fused state kernel.  Same decisions either way."""
+    _replay_nuts(name, 1, glm_path=path)
+
+
+def _replay_nuts(name, lanes, schedule=0, glm_path="auto"):
     """Every NUTS transition of the reference run is replayed on the GPU from the reference's own state
     (position, step size, dual-averaging state) with the reference's draws injected.  Replaying transition by
     transition keeps one-ulp differences of exp/log from being amplified by the step-size feedback loop, so
@@ -218,7 +225,7 @@ def _replay_nuts(name, lanes):
     g = golden(name)
     kw = g["kwargs"]
     fn, init, _ = W.ALL_SMALL[g["model"]](B.ns)
-    model = compile_model(fn, init)
+    model = compile_model(fn, init, glm_path=glm_path)
     nw, ns_, md = kw["num_warmup"], kw["num_samples"], kw["max_tree_depth"]
     tape = g["tape"]
     iters = tape["iters"]
@@ -239,7 +246,8 @@ def _replay_nuts(name, lanes):
         h0 = torch.zeros(1, 1, device="cuda")
         draw = torch.zeros(1, 1, model.D, device="cuda")
         launch_nuts(st, 1, md, _cabi.ADAPT_DUAL_AVERAGING if m < nw else _cabi.ADAPT_NONE, _cabi.COMPAT_REFERENCE, 0.65,
-                    0, m, draws=draw, depths=depth, alphas=alpha, lanes=lanes, inj=inj, trace_doubling=tr, trace_energy=h0)
+                    0, m, draws=draw, depths=depth, alphas=alpha, lanes=lanes, inj=inj, trace_doubling=tr, trace_energy=h0,
+                    schedule=schedule)
         torch.cuda.synchronize()
         assert int(depth[0, 0]) == it["depth"], (m, int(depth[0, 0]), it["depth"])
         trc = tr.cpu().numpy()[0, 0]
@@ -299,7 +307,7 @@ def test_nuts_free_running_matches_reference(cuda, name):
 
 
 @pytest.mark.parametrize("name", ["c1_normal", "c2_event_rate", "c5_ab_test", "t_halfnormal_scale", "t_vector_normal"])
-def test_compact_and_general_pointwise_paths_agree_bit_for_bit(cuda, name, monkeypatch):
+def test_compact_and_general_pointwise_paths_agree_bit_for_bit(cuda, name):
     """Compact models (table in the kernel parameters, theta / gradient in registers) and the general path
     (shared-memory term table + mailbox) run the same arithmetic in the same order."""
     import mlx_mcmc_b200 as B
@@ -307,9 +315,7 @@ def test_compact_and_general_pointwise_paths_agree_bit_for_bit(cuda, name, monke
     from mlx_mcmc_b200.engine import compile_model
     fn, init, _ = W.ALL_SMALL[name](B.ns)
     fast = compile_model(fn, init, cache=False)
-    monkeypatch.setenv("B2M_POINTWISE_PATH", "general")
-    slow = compile_model(fn, init, cache=False)
-    monkeypatch.delenv("B2M_POINTWISE_PATH")
+    slow = compile_model(fn, init, cache=False, pointwise_path="general")
     rng = np.random.default_rng(5)
     theta = fast.pack(init, 257) + torch.from_numpy(0.3 * rng.standard_normal((257, fast.D)).astype(np.float32)).cuda()
     for lanes in (1, 4):

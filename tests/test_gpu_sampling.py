@@ -415,7 +415,7 @@ def test_step_size_jitter_keeps_the_posterior_and_is_off_by_default(cuda):
         B.nuts(fn, init, step_size_jitter=1.5, num_chains=2)
 
 
-def test_async_and_sync_nuts_schedules_agree(cuda, monkeypatch):
+def test_async_and_sync_nuts_schedules_agree(cuda):
     """The iteration-asynchronous schedule (default) and the synchronous one run the same per-chain algorithm with
     the same Philox slots: tree depths are identical and the first draws agree to the batch-dependent rounding of the
     contractions; both match the closed-form posterior."""
@@ -423,10 +423,8 @@ def test_async_and_sync_nuts_schedules_agree(cuda, monkeypatch):
     m, V = W.regression_posterior(meta)
     kw = dict(num_samples=60, num_warmup=80, step_size=0.02, num_chains=300, compat="correct", key=mx.random.key(6),
               return_info=True)
-    monkeypatch.setenv("B2M_NUTS_SCHED", "sync")
-    a, ra, ia = B.nuts(fn, init, **kw)
-    monkeypatch.setenv("B2M_NUTS_SCHED", "async")
-    b, rb, ib = B.nuts(fn, init, **kw)
+    a, ra, ia = B.nuts(fn, init, schedule="sync", **kw)
+    b, rb, ib = B.nuts(fn, init, schedule="async", **kw)
     # per-chain dual averaging: every chain is an independent replica in both schedules
     same_depth = (ia.warmup_depths[:5] == ib.warmup_depths[:5]).mean()
     assert same_depth > 0.98, same_depth

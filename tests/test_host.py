@@ -41,14 +41,27 @@ def test_library_is_sm100a_only():
 
 def test_bad_arguments_return_errors_not_crashes():
     lib = _cabi.load()
-    assert lib.b2m_model_create(None, 0, None, 0, None, 0, 1, ctypes.byref(ctypes.c_void_p())) != 0
+    assert lib.b2m_model_create(None, 0, None, 0, None, 0, 1, None, ctypes.byref(ctypes.c_void_p())) != 0
     assert b"terms" in lib.b2m_last_error()
     t = (_cabi.Term * 1)()
     t[0].dist = 99
     t[0].length = 1
-    assert lib.b2m_model_create(t, 1, None, 0, None, 0, 1, ctypes.byref(ctypes.c_void_p())) != 0
+    assert lib.b2m_model_create(t, 1, None, 0, None, 0, 1, None, ctypes.byref(ctypes.c_void_p())) != 0
     assert b"unknown distribution" in lib.b2m_last_error()
+    # options travel in the ABI (they were environment variables in ABI 1): bad values are errors, not defaults
+    opt = _cabi.ModelOptions()
+    opt.glm_path = 9
+    assert lib.b2m_model_create(t, 1, None, 0, None, 0, 1, ctypes.byref(opt), ctypes.byref(ctypes.c_void_p())) != 0
+    assert b"glm_path" in lib.b2m_last_error()
+    opt.glm_path = 0
+    opt.reserved[2] = 1
+    assert lib.b2m_model_create(t, 1, None, 0, None, 0, 1, ctypes.byref(opt), ctypes.byref(ctypes.c_void_p())) != 0
+    assert b"reserved" in lib.b2m_last_error()
     assert lib.b2m_hmc_run(None, None, None) != 0
+    assert lib.b2m_quantiles(None, 0, None, 0, None, None) != 0
+    assert lib.b2m_mass_from_draws(None, 0, 0, 0, None, None) != 0
+    assert lib.b2m_peer_alloc(0, None, None) != 0
+    assert lib.b2m_model_peer_attach(None, None, 2, 0, 512, 0) != 0
 
 
 # ----------------------------------------------------------------------------- tracer

@@ -24,7 +24,6 @@ ap.add_argument("--spread", type=float, default=0.01)
 ap.add_argument("--where", default="near", choices=["near", "zero", "mixed"],
                 help="chains near the mode (beta* + spread z), all at 0, or half and half")
 args = ap.parse_args()
-os.environ["B2M_GLM_PATH"] = args.path
 
 import mlx_mcmc_b200 as B
 from mlx_mcmc_b200 import workloads as W
@@ -32,7 +31,7 @@ from mlx_mcmc_b200.engine import compile_model
 
 t0 = time.time()
 fn, init, meta = W.regression(B.ns, args.n, args.d, seed=0)
-model = compile_model(fn, init, cache=False)
+model = compile_model(fn, init, cache=False, glm_path=args.path)
 torch.cuda.synchronize()
 print(f"model built in {time.time() - t0:.1f}s", file=sys.stderr)
 rng = np.random.default_rng(1)

@@ -25,9 +25,8 @@ for name in ("c1_normal", "c2_event_rate", "c5_ab_test", "t_vector_normal"):
     B.nuts(fn, init, num_samples=4, num_warmup=4, num_chains=70, max_tree_depth=4, key=mx.random.key(2))
     B.metropolis_hastings(fn, init, num_samples=6, num_chains=70, random_seed=3)
 for path in ("simt", "tc", "tc16"):
-    os.environ["B2M_GLM_PATH"] = path
     fn, init, meta = W.regression(B.ns, 700, 70, seed=1)
-    m = compile_model(fn, init, cache=False)
+    m = compile_model(fn, init, cache=False, glm_path=path)
     th = torch.from_numpy((meta.beta_true[None] + 0.1 * np.random.default_rng(0).standard_normal((300, 70))).astype(np.float32)).cuda()
     m.logp_grad(th)
     s, _ = B.nuts(fn, init, num_samples=3, num_warmup=3, num_chains=300, max_tree_depth=3, compat="correct",
