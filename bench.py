@@ -1,11 +1,15 @@
 #!/usr/bin/env python
 """Benchmark of the sampling hot path (BASELINE.json metric: leapfrog grad-evals/sec, min-ESS/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c1|c5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c1|c5] [--scaling strong|weak] [--impl reference]
 
 Default workload = BASELINE.json's Target configuration (configs[3], "C4"): Bayesian linear regression with 1000
-coefficients and 100,000 observations, NUTS, 4096 chains per GPU in lock-step (it fits one GPU: X is 400 MB).  With N
-GPUs the chains shard (weak scaling: 4096 chains per GPU, no data-path collective).  The other configurations
+coefficients and 100,000 observations, NUTS, 4096 chains in lock-step (it fits one GPU: X is 400 MB).  With N GPUs the
+default is the configuration as BASELINE.json writes it -- the SAME 4096 chains with the observations sharded over the
+ranks (strong scaling): every rank contracts its 100000 / N rows for all chains, K6's epilogue stores each finished
+gradient tile into its owner's peer window over NVLink, the owner finishes / advances its 4096 / N chains and publishes
+the next leaf's packed rows to every rank.  `--scaling weak` shards the chains instead (4096 per GPU, no data-path
+collective).  The other configurations
 (`--workload`, and the `other_workloads` object of the default line) are C3 (100 x 10K regression, NUTS, 1024 chains),
 C2 (examples/04 event-rate model, 65,536 HMC chains), C1 and C5 (examples/03, 1M Metropolis chains).
 
@@ -59,6 +63,11 @@ UNIT = "grad-evals/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
 NCU_TRAFFIC = {"c4": {"bytes": 2.25e9 + 4.27e9, "source": "profiles/r01_tc_gemm_c4_v4_f16_ncu_summary.md (K5 0.64 GB read + 1.62 GB "
                       "written, K6 4.13 GB read + 0.13 GB written)"}}
+
+
+# issue-side evidence of the pointwise kernels from the committed ncu captures (profiles/): the bound of these paths
+PW_ISSUE = {"c2": {"source": "profiles/r01_hmc_kernel_c2_v2_ncu_summary.md", "issue_slots_busy_pct": 51.0, "warp_occupancy_pct": 20.0,
+                   "waves": 0.43, "registers": 64, "per_evaluation_setup_share_of_instructions": 0.657}}
 
 
 # ----------------------------------------------------------------------------------------- clocks
@@ -138,8 +147,15 @@ def _cpu_glm(wl_name: str, threads: int, n_iter: int, seed: int = 0):
     return tape.leapfrogs, dt, tape.grad_evals
 
 
+def _ref_compute_ess(x):
+    """the estimator of examples/06_nuts_comparison.py:22-41, restated (oracle/refport/diagnostics.py holds the pinned copy)"""
+    from oracle.refport.diagnostics import compute_ess
+    return float(compute_ess(np.asarray(x, dtype=np.float64)))
+
+
 def _cpu_chain(args):
-    """one chain of the oracle restatement of a pointwise workload (runs in a worker process)"""
+    """one chain of the oracle restatement of a pointwise workload (runs in a worker process); returns
+    (evals, seconds, mx.grad calls, min over parameters of the reference-estimator ESS of the kept draws)"""
     wl_name, seed, n_warm, n_samp = args
     from oracle.ns import Tape, ns as ons, samplers
     from mlx_mcmc_b200 import workloads as W
@@ -148,31 +164,41 @@ def _cpu_chain(args):
     tape = Tape()
     t0 = time.perf_counter()
     if wl["method"] == "hmc":
-        samplers.hmc_port(fn, init, num_samples=n_samp, num_warmup=n_warm, step_size=wl["step_size"],
-                          num_leapfrog_steps=wl["L"], key=ons.mx.random.key(seed), tape=tape)
+        out = samplers.hmc_port(fn, init, num_samples=n_samp, num_warmup=n_warm, step_size=wl["step_size"],
+                                num_leapfrog_steps=wl["L"], key=ons.mx.random.key(seed), tape=tape)
         evals = tape.leapfrogs
     else:
-        samplers.run_port(fn, init, num_samples=n_samp, num_warmup=n_warm, method="metropolis",
-                          proposal_scale=wl["proposal_scale"], random_seed=seed, tape=tape)
+        out = samplers.run_port(fn, init, num_samples=n_samp, num_warmup=n_warm, method="metropolis",
+                                proposal_scale=wl["proposal_scale"], random_seed=seed, tape=tape)
         evals = n_samp + n_warm
-    return evals, time.perf_counter() - t0, tape.grad_evals
+    dt = time.perf_counter() - t0
+    try:
+        ess = min(_ref_compute_ess(np.asarray(v)) for v in out[0].values())
+    except Exception:
+        ess = float("nan")
+    return evals, dt, tape.grad_evals, ess
 
 
-def cpu_baseline(wl_name: str, cores: int, scale: float = 1.0):
+def cpu_baseline(wl_name: str, cores: int, scale: float = 1.0, full_length: bool = False):
     """The oracle port on `cores` host cores on a bounded sample of the workload.  Returns the cpu_baseline object.
     GLM: one chain, the matvecs use `cores` torch threads.  Pointwise: one independent chain per core (the
-    reference is a single Python thread per chain)."""
+    reference is a single Python thread per chain).  `full_length`: the example's own run length (1000 warm-up + 5000
+    draws) so that min-ESS/s (examples/06_nuts_comparison.py:22-41 estimator) is the reference's own figure."""
     wl = WORKLOADS[wl_name]
     t0 = time.perf_counter()
+    extra = {}
     if wl["kind"] == "glm":
-        n_iter = max(1, int(round((10 if wl_name == "c4" else 60) * scale)))   # ~10-15 s of host work
+        n_iter = max(1, int(round((10 if wl_name == "c4" else 60) * scale)))   # ~10-15 s of host work at scale 1
         evals, busy, grads = _cpu_glm(wl_name, cores, n_iter)
         sample = (f"1 chain x {n_iter} NUTS transition(s) (+1 warm-up transition) from the posterior mode, step size "
                   f"{wl['eps0']}, no adaptation, on the oracle restatement (reference source semantics on a torch-CPU "
                   f"stand-in for MLX) with {cores} torch threads; one leaf counted as one grad-eval (the reference spends "
                   f"2 mx.grad + 2 value traces per leaf: {grads} mx.grad calls here)")
+        extra["min_ess_per_s"] = None
+        extra["min_ess_note"] = (f"{n_iter} transitions carry no autocorrelation estimate; the full-length single-chain runs "
+                                 "with the reference's estimator are in cpu_baseline.full_length (C1, C2, C5)")
     else:
-        n_warm, n_samp = max(10, int(150 * scale)), max(20, int(350 * scale))
+        n_warm, n_samp = (1000, 5000) if full_length else (max(10, int(150 * scale)), max(20, int(350 * scale)))
         jobs = [(wl_name, 1000 + i, n_warm, n_samp) for i in range(cores)]
         if cores == 1:
             res = [_cpu_chain(jobs[0])]
@@ -181,33 +207,64 @@ def cpu_baseline(wl_name: str, cores: int, scale: float = 1.0):
             with mp.get_context("spawn").Pool(cores) as pool:
                 res = pool.map(_cpu_chain, jobs)
         evals, busy, grads = sum(r[0] for r in res), max(r[1] for r in res), sum(r[2] for r in res)
+        ess = [r[3] for r in res if r[3] == r[3]]
         sample = (f"{cores} chain(s) x ({n_warm} warm-up + {n_samp} draws) of the same model/sampler settings on the "
                   f"oracle restatement (reference source semantics on a torch-CPU stand-in for MLX); one leapfrog step "
                   f"counted as one grad-eval (the reference spends 2 mx.grad + value traces per step: {grads} mx.grad "
                   f"calls here)")
+        extra["min_ess_per_s"] = (sum(ess) / busy) if ess else None
+        extra["min_ess_note"] = ("sum over chains of min-over-parameters ESS (examples/06_nuts_comparison.py:22-41 estimator) / "
+                                 "wall time including warm-up")
     wall = time.perf_counter() - t0
-    return {"value": evals / busy, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f"; wall {wall:.1f}s"}
+    out = {"value": evals / busy, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f"; wall {wall:.1f}s"}
+    out.update(extra)
+    return out
+
+
+def _full_length_job(name):
+    """worker: one chain, the example's full run length, for cpu_baseline.full_length"""
+    r = cpu_baseline(name, 1, 1.0, full_length=True)
+    return name, {"grad_evals_per_s": r["value"], "min_ess_per_s": r["min_ess_per_s"], "sample": r["sample"]}
+
+
+def cpu_full_length(names=("c1", "c2", "c5")):
+    """C1 / C2 / C5 at the reference examples' own length (1000 + 5000), one chain each, run side
+    by side on separate host cores: grad-evals/s and min-ESS/s of the reference arithmetic (oracle port)."""
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(len(names)) as pool:
+        return dict(pool.map(_full_length_job, list(names)))
 
 
 def reference_arm(args, wl, config):
+    """The reference's CPU implementation of the path on the box's host cores (`--impl reference`): the oracle
+    restatement -- pinned bit-equal to the unmodified reference source by oracle/make_golden.py; MLX itself is not
+    installable here and /root/reference does not exist on the GPU box, so the unmodified source cannot run there --
+    with all the host threads it can use.  W warm-up + exactly K timed steps, each a bounded sample of the workload;
+    `run` says what one step was."""
     cores = os.cpu_count() or 1
     if wl["kind"] == "pointwise":
         cores = min(cores, 32)
     W_, K = max(args.warmup, 0), max(args.steps, 1)
-    for _ in range(min(W_, 1)):
-        cpu_baseline(args.workload, cores, 0.2)
+    # a step sized so that K of them end within a few minutes: C4 ~ 1 s (2 transitions), C3 / pointwise ~ 2-4 s
+    scale = 0.2 if args.workload == "c4" else 0.3
+    for _ in range(min(W_, 2)):
+        cpu_baseline(args.workload, cores, scale)
     vals, t0, per = [], time.perf_counter(), None
     for _ in range(K):
-        per = cpu_baseline(args.workload, cores, 0.5)
+        per = cpu_baseline(args.workload, cores, scale)
         vals.append(per["value"])
-        if time.perf_counter() - t0 > 150:
+        if time.perf_counter() - t0 > 240:      # safety only: never reached at the driver's K
             break
     v = float(np.mean(vals))
     per["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-            "warmup": min(W_, 1), "ms_per_step": 1e3 * (time.perf_counter() - t0) / len(vals), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "warmup": W_, "ms_per_step": 1e3 * (time.perf_counter() - t0) / len(vals), "higher_is_better": True,
+            "scaling": config.pop("_scaling", "weak"), "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "run": {"what": "reference arm: CPU, no GPU, none of this repo's kernels", "chains": 1 if wl["kind"] == "glm" else cores,
+                    "kind": "port", "cores": cores, "one_step": per["sample"]},
             "cpu_baseline": per, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if "min_ess_per_s" in per:
+        line["min_ess_per_s"] = per["min_ess_per_s"]
     emit(line)
     return 0
 
@@ -270,13 +327,14 @@ class Timed:
 
 
 # ----------------------------------------------------------------------------------------- GLM workloads (c4, c3)
-def glm_setup(torch, B, wl, C, chain_offset, seed, obs_sharded=False):
+def glm_setup(torch, B, wl, C, chain_offset, seed, obs_sharded=False, peer=False):
     """model + chains started in the posterior's typical set + dual-averaging warm-up (all untimed).
-    obs_sharded: every rank holds all C chains (same ids, same seed) and a row shard of (X, y)."""
+    obs_sharded: every rank holds all C chains (same ids, same seed) and a row shard of (X, y); peer: with the peer
+    window of the fused gradient exchange attached."""
     from mlx_mcmc_b200 import _cabi, dist as D_, workloads as W
     from mlx_mcmc_b200.engine import ChainState, compile_model, launch_nuts
     fn, init, meta = W.regression(B.ns, wl["n"], wl["d"], seed=0)
-    model = D_.compile_obs_sharded(fn, init) if obs_sharded else compile_model(fn, init)
+    model = D_.compile_obs_sharded(fn, init, peer_chains=C if peer else None) if obs_sharded else compile_model(fn, init)
     N, D = wl["n"], wl["d"]
     # posterior mode by Richardson iteration on the device gradient (X'X ~ N I for this synthetic X)
     th = torch.zeros(128, D, device="cuda")
@@ -299,6 +357,56 @@ def glm_setup(torch, B, wl, C, chain_offset, seed, obs_sharded=False):
     torch.cuda.synchronize()
     log(f"adapted: median step size {float(st.step_size.median()):.3e}")
     return fn, meta, model, st, mode
+
+
+def glm_roofline(torch, four, leaves, N, D, C, total_ms, model, wl_name, rows_note=""):
+    """roofline of the dominant kernels: every GEMM launch of the timed region was timed with CUDA events inside the
+    library (b2m_profile).  N = observation rows this rank contracts (all of them, or its shard)."""
+    peaks = load_peaks()
+    tf32_probe = tf32_peak_probe(torch)
+    k5_ms, k5_n, k6_ms, k6_n = [float(x) for x in four]
+    # flops of one contraction for the batch the timed launches ran on (compacted batches are smaller: use the leaves)
+    useful_per_gemm = 2.0 * N * D * (leaves / max(k5_n, 1))
+    k5 = k5_ms / max(k5_n, 1)
+    k6 = k6_ms / max(k6_n, 1)
+    both = k5 + k6
+    executed_tflops = 3 * 2 * useful_per_gemm / (both * 1e-3) / 1e12
+    f16 = getattr(model, "glm_path", "tc") == "tc16"
+    bf16_sus = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 0.0)) or 0.0)
+    bf16_half = 0.5 * bf16_sus
+    if f16:      # kind::f16 MMAs: fp16 and bf16 share the tensor rate; the kernels run inside a long step => sustained figure
+        peak = bf16_sus if bf16_sus else 2.0 * tf32_probe
+        peak_source = (f"bf16_tflops_sustained of MEASURED_PEAKS.json = {bf16_sus:.1f} (kind::f16 runs at the bf16 rate; "
+                       f"cuBLAS tf32 probe in this run = {tf32_probe:.1f})")
+    else:
+        peak = max(tf32_probe, bf16_half) if bf16_half else tf32_probe
+        peak_source = (f"max(cuBLAS tf32 8192^3 probe in this run = {tf32_probe:.1f}, 0.5 x bf16_tflops_sustained of "
+                       f"MEASURED_PEAKS.json = {bf16_half:.1f})")
+    enc = "fp16" if f16 else "tf32"
+    alg_bytes = 4.0 * (N * D + N + 2 * C * D)
+    traffic = NCU_TRAFFIC.get(wl_name) if not rows_note else None
+    return {
+        "bound": "tensor", "achieved": executed_tflops, "peak": peak, "unit": "TFLOP/s", "frac": executed_tflops / peak,
+        "traffic": traffic["bytes"] if traffic else None,
+        "kernel": "tc_gemm_kernel<256,RESID> (K5: M = (beta-beta0) X^T + residual epilogue) + tc_gemm_kernel<*,PLAIN|PUSH> (K6: G = R X)",
+        "avg_launch_ms": {"K5": k5, "K6": k6}, "launches_timed": int(k5_n + k6_n),
+        "gemm_share_of_step": (k5_ms + k6_ms) / total_ms,
+        "encoding": f"3x{enc.upper()} split (hi.hi + hi.lo + lo.hi), fp32 accumulate in TMEM with round-to-nearest promotion",
+        "executed_tflops": {"K5": 3 * useful_per_gemm / (k5 * 1e-3) / 1e12, "K6": 3 * useful_per_gemm / (k6 * 1e-3) / 1e12},
+        "useful_tflops": 2 * useful_per_gemm / (both * 1e-3) / 1e12,
+        "peak_source": peak_source,
+        "algorithmic_bytes_per_eval": alg_bytes,
+        "logical_GBps_per_chain_view": 2 * useful_per_gemm / (both * 1e-3) / 1e9,
+        "hbm_peak_GBps": float(peaks.get("hbm_gbs", 6650.0)),
+        "traffic_source": traffic["source"] if traffic else None,
+        "rows": rows_note or f"all {N} observation rows on this GPU",
+        "note": "achieved = executed tensor flops (3 MMAs per useful product: the hi/lo split is what holds the 1e-5 gate; "
+                "north_star names 3xTF32, the fp16 split is the same construction at twice the MMA rate and is checked "
+                "against float64 at full size in tests/test_gpu_glm_tc.py) of one lock-step value+gradient / (K5 + K6 "
+                "launch time); useful_tflops = 4 N D C / t.  "
+                "logical_GBps_per_chain_view = C x 4 N D / t is the north-star's 'HBM roofline per gradient eval' reading "
+                "(each chain would stream X once per gradient if it ran alone); the batch actually moves "
+                "algorithmic_bytes_per_eval."}
 
 
 def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, full=True):
@@ -386,128 +494,211 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
            "config_extra": {"chains_per_gpu": C, "iters_per_step": ITERS, "mean_tree_depth": mean_depth,
                             "grad_evals_per_step_per_gpu": leaves / args.steps,
                             "adapted_step_size_median": eps_host}}
-    # ---- N > 1: the same 4096 chains in TOTAL with the observations sharded over the ranks (BASELINE configs[3] as
-    # written: strong scaling, one NCCL all-reduce of the [C, D+1] gradient || sum z^2 buffer per gradient)
-    if world > 1 and full:
-        fn_o, _, model_o, st_o, _ = glm_setup(torch, B, wl, C, 0, seed, obs_sharded=True)
-        it_o = [wl["adapt_iters"]]
-
-        def obs_step():
-            launch_nuts(st_o, ITERS, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, it_o[0], draws=draws, depths=depths)
-            it_o[0] += ITERS
-
-        timed_o = Timed(torch, args.steps)
-        for _ in range(warm):
-            obs_step()
-        barrier()
-        l0 = int(st_o.n_leaves.sum().item())
-        barrier()
-        timed_o.run(obs_step)
-        barrier()
-        l1 = int(st_o.n_leaves.sum().item())
-        to = torch.tensor([timed_o.total_ms()], dtype=torch.float64, device="cuda")
-        dist.all_reduce(to, op=dist.ReduceOp.MAX)
-        out["obs_sharded"] = {"value": (l1 - l0) / (float(to[0]) * 1e-3), "unit": UNIT, "scaling": "strong",
-                              "chains_total": C, "rows_per_gpu": -(-N // world), "ms_per_step": float(to[0]) / args.steps,
-                              "collective": f"ncclAllReduce(sum, f32) of [C, D+1] = {4 * C * (D + 1) / 1e6:.1f} MB per gradient, "
-                                            "on the compute stream between K6 and finish",
-                              "note": "every rank holds all chains and takes identical decisions; grad-evals counted once"}
-        log(f"obs-sharded: {out['obs_sharded']['ms_per_step']:.1f} ms/step")
-        # the same again with sliced per-chain state (reduce-scatter + all-gather instead of the all-reduce; rank r
-        # finishes / advances C / N chains): per-chain counters are written by the owning rank only -> sum over ranks
-        if C % world == 0 and C % 256 == 0:
-            os.environ["B2M_OBS_SLICE"] = "1"
-            try:
-                for _ in range(warm):
-                    obs_step()
-                barrier()
-                base = st_o.n_leaves.clone()
-                barrier()
-                timed_s = Timed(torch, args.steps)
-                timed_s.run(obs_step)
-                barrier()
-            finally:
-                os.environ.pop("B2M_OBS_SLICE", None)
-            dl = (st_o.n_leaves - base).sum().double().reshape(1)
-            ts = torch.tensor([timed_s.total_ms()], dtype=torch.float64, device="cuda")
-            dist.all_reduce(dl, op=dist.ReduceOp.SUM)
-            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-            out["obs_sharded_sliced"] = {"value": float(dl[0]) / (float(ts[0]) * 1e-3), "unit": UNIT, "scaling": "strong",
-                                         "chains_total": C, "chains_advanced_per_gpu": C // world,
-                                         "ms_per_step": float(ts[0]) / args.steps,
-                                         "collective": "ncclReduceScatter of the [C, D] gradient and [C] sum z^2 + ncclAllGather "
-                                                       "of the [C, D] leaf positions per gradient, on the compute stream"}
-            log(f"obs-sharded, sliced state: {out['obs_sharded_sliced']['ms_per_step']:.1f} ms/step")
     if rank != 0:
         return out
 
-    # ---- roofline of the dominant kernels: every GEMM launch of the timed region was timed with CUDA events
-    peaks = load_peaks()
-    tf32_probe = tf32_peak_probe(torch)
-    k5_ms, k5_n, k6_ms, k6_n = [float(x) for x in four]
-    # flops of one contraction for a full batch of C chains (compacted batches are smaller: the timed launches
-    # are all full-size here only if every chain reaches the same depth -- use the measured leaves instead)
-    useful_per_gemm = 2.0 * N * D * (leaves / max(k5_n, 1))
-    k5 = k5_ms / max(k5_n, 1)
-    k6 = k6_ms / max(k6_n, 1)
-    both = k5 + k6
-    executed_tflops = 3 * 2 * useful_per_gemm / (both * 1e-3) / 1e12
-    f16 = getattr(model, "glm_path", "tc") == "tc16"
-    bf16_sus = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 0.0)) or 0.0)
-    bf16_half = 0.5 * bf16_sus
-    if f16:      # kind::f16 MMAs: fp16 and bf16 share the tensor rate; the kernels run inside a long step => sustained figure
-        peak = bf16_sus if bf16_sus else 2.0 * tf32_probe
-        peak_source = (f"bf16_tflops_sustained of MEASURED_PEAKS.json = {bf16_sus:.1f} (kind::f16 runs at the bf16 rate; "
-                       f"cuBLAS tf32 probe in this run = {tf32_probe:.1f})")
-    else:
-        peak = max(tf32_probe, bf16_half) if bf16_half else tf32_probe
-        peak_source = (f"max(cuBLAS tf32 8192^3 probe in this run = {tf32_probe:.1f}, 0.5 x bf16_tflops_sustained of "
-                       f"MEASURED_PEAKS.json = {bf16_half:.1f})")
-    enc = "fp16" if f16 else "tf32"
-    alg_bytes = 4.0 * (N * D + N + 2 * C * D)
-    useful_full = 2.0 * N * D * C
-    traffic = NCU_TRAFFIC.get(wl_name)
-    out["roofline"] = {
-        "bound": "tensor", "achieved": executed_tflops, "peak": peak, "unit": "TFLOP/s", "frac": executed_tflops / peak,
-        "traffic": traffic["bytes"] if traffic else None,
-        "kernel": "tc_gemm_kernel<256,RESID> (K5: M = (beta-beta0) X^T + residual epilogue) + tc_gemm_kernel<*,PLAIN> (K6: G = R X)",
-        "avg_launch_ms": {"K5": k5, "K6": k6}, "launches_timed": int(k5_n + k6_n),
-        "gemm_share_of_step": (k5_ms + k6_ms) / total_ms,
-        "encoding": f"3x{enc.upper()} split (hi.hi + hi.lo + lo.hi), fp32 accumulate in TMEM with round-to-nearest promotion",
-        "executed_tflops": {"K5": 3 * useful_per_gemm / (k5 * 1e-3) / 1e12, "K6": 3 * useful_per_gemm / (k6 * 1e-3) / 1e12},
-        "useful_tflops": 2 * useful_per_gemm / (both * 1e-3) / 1e12,
-        "peak_source": peak_source,
-        "algorithmic_bytes_per_eval": alg_bytes,
-        "logical_GBps_per_chain_view": 2 * useful_per_gemm / (both * 1e-3) / 1e9,
-        "hbm_peak_GBps": float(peaks.get("hbm_gbs", 6650.0)),
-        "traffic_source": traffic["source"] if traffic else None,
-        "note": "achieved = executed tensor flops (3 MMAs per useful product: the hi/lo split is what holds the 1e-5 gate; "
-                "north_star names 3xTF32, the fp16 split is the same construction at twice the MMA rate and is checked "
-                "against float64 at full size in tests/test_gpu_glm_tc.py) of one lock-step value+gradient / (K5 + K6 "
-                "launch time); useful_tflops = 4 N D C / t.  "
-                "logical_GBps_per_chain_view = C x 4 N D / t is the north-star's 'HBM roofline per gradient eval' reading "
-                "(each chain would stream X once per gradient if it ran alone); the batch actually moves "
-                "algorithmic_bytes_per_eval."}
+    out["roofline"] = glm_roofline(torch, four, leaves, N, D, C, total_ms, model, wl_name)
+    both = out["roofline"]["avg_launch_ms"]["K5"] + out["roofline"]["avg_launch_ms"]["K6"]
     out["issue"] = {"grad_evals_per_s_per_gpu": value / world, "lockstep_eval_ms": both, "nuts_step_ms": total_ms / args.steps}
 
     log("roofline pass done")
     if full and not args.no_ess:
-        S = 40
-        dr = torch.empty((S, C, D), dtype=torch.float32, device="cuda")
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        launch_nuts(st, S, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, it0[0], draws=dr)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        it0[0] += S
-        from mlx_mcmc_b200.diagnostics import device_summary
-        tab = device_summary(dr)                                   # all C x D series, on the device
-        out["ess"] = {"min_ess_per_s_geyer": float(tab["ess_geyer"].min()) / wall,
-                      "min_ess_per_s_reference_estimator": float(tab["ess"].min()) / wall,
-                      "max_rhat": float(np.nanmax(tab["rhat"])), "draws": S, "wall_s": wall, "chains": C,
-                      "note": "sampling phase only (adapted chains); ESS of every (chain, coefficient) series computed on the "
-                              "device (b2m_diag_series), summed over chains, minimum over the coefficients; per GPU"}
+        out["ess"] = glm_ess_public_run(torch, B, wl, fn, C, chain_offset)
     return out
+
+
+def bench_glm_strong(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank):
+    """N > 1, BASELINE.json configs[3] as written: the SAME C chains in total, observations sharded over the ranks
+    (strong scaling).  Timed path: sliced state through the peer window -- per gradient, K6's epilogue stores every
+    finished [256, D] tile into its owner's window over NVLink while the next tile's MMAs run, the owner sums the
+    per-source slots in rank order, advances its C / N chains and publishes the next leaf's packed fp16 rows to every
+    rank; flags with release / acquire semantics at system scope, no NCCL call inside the sampling loop."""
+    import ctypes
+    import mlx_mcmc_b200.core as mx
+    from mlx_mcmc_b200 import _cabi
+    from mlx_mcmc_b200.engine import ChainState, compile_model, launch_nuts
+    C = args.chains or wl["chains"]
+    seed = 1234
+    N, D, MD = wl["n"], wl["d"], wl["max_tree_depth"]
+    ITERS = wl["iters"]
+    if C % (128 * world) or C % 256:
+        raise SystemExit(f"--scaling strong needs chains % (128 x ranks) == 0 and % 256 == 0 (got {C} on {world} ranks)")
+    fn, meta, model, st, mode = glm_setup(torch, B, wl, C, 0, seed, obs_sharded=True, peer=True)
+    rows_local = next(int(a_.shape[0]) for a_ in model._arrays if a_.dim() == 2)   # this rank's rows of X
+    it0 = [wl["adapt_iters"]]
+    draws = torch.zeros((ITERS, C, D), dtype=torch.float32, device="cuda")
+    depths = torch.zeros((ITERS, C), dtype=torch.int32, device="cuda")
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(mode_):
+        launch_nuts(st, ITERS, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, it0[0], draws=draws, depths=depths,
+                    slice_state=mode_)
+        it0[0] += ITERS
+
+    def leaves_all():       # sliced: every rank counts its own chains; replicated: every rank counts all of them
+        return st.n_leaves.sum().double().reshape(1)
+
+    # ---- parity self-check (untimed), part 1: observation-sharded log p / gradient against the unsharded model
+    parity = {}
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(99)
+    probe = (mode[None, :] + torch.randn(256, D, device="cuda", generator=gen) / (N ** 0.5)).contiguous()
+    lp_s, g_s = model.logp_grad(probe)                      # collective: NCCL all-reduce of the partials
+    if rank == 0:
+        from mlx_mcmc_b200 import workloads as W
+        fn_full, init_full, _ = W.regression(B.ns, N, D, seed=0)
+        full = compile_model(fn_full, init_full, cache=False)
+        lp_f, g_f = full.logp_grad(probe)
+        parity["obs_sharded_logp_rel_err"] = float(((lp_s - lp_f).abs() / lp_f.abs()).max())
+        parity["obs_sharded_grad_normwise_err"] = float((g_s - g_f).abs().max() / g_f.abs().max())
+        del full
+        torch.cuda.empty_cache()
+    # part 2: one transition of every chain, peer exchange vs the replicated NCCL all-reduce, from identical states
+    saved = (st.theta.clone(), st.n_leaves.clone(), st.n_accept.clone(), st.n_diverge.clone())
+    d1 = torch.zeros((1, C, D), device="cuda")
+    launch_nuts(st, 1, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, 10 ** 6, draws=d1, slice_state=_cabi.SLICE_OFF)
+    rep_leaves = int((st.n_leaves - saved[1]).sum().item())
+    for t_, s_ in zip((st.theta, st.n_leaves, st.n_accept, st.n_diverge), saved):
+        t_.copy_(s_)
+    d2 = torch.zeros((1, C, D), device="cuda")
+    launch_nuts(st, 1, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, 10 ** 6, draws=d2, slice_state=_cabi.SLICE_PEER)
+    peer_leaves = (st.n_leaves - saved[1]).sum().double().reshape(1)
+    dist.all_reduce(d2)                                     # merge the slices (each rank wrote its own chains' rows)
+    dist.all_reduce(peer_leaves)
+    spread = float((d1 - mode[None, None, :]).std().item())
+    parity["peer_vs_allreduce_first_draw_maxdiff_in_posterior_sd"] = float((d1 - d2).abs().max().item()) / max(spread, 1e-30)
+    parity["peer_vs_allreduce_grad_evals"] = [int(peer_leaves.item()), rep_leaves]
+    chk = torch.stack([d2.double().sum(), d2.double().abs().sum(), (d2.double() ** 2).sum()])
+    allc = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    parity["merged_draws_bit_equal_across_ranks"] = bool(all(torch.equal(allc[0], c_) for c_ in allc))
+    for t_, s_ in zip((st.theta, st.n_leaves, st.n_accept, st.n_diverge), saved):
+        t_.copy_(s_)
+    log(f"parity self-check: {parity}")
+
+    # ---- timed: peer-sliced steps
+    warm = max(args.warmup, 3)
+    timed = Timed(torch, args.steps)
+    for _ in range(warm):
+        timed.flush.fill_(1)
+        step(_cabi.SLICE_PEER)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = leaves_all()
+    n0 = lib.b2m_launch_count()
+    four = (ctypes.c_double * 4)()
+    lib.b2m_profile(1)
+    barrier()
+    timed.run(lambda: step(_cabi.SLICE_PEER))
+    barrier()
+    lib.b2m_profile_read(four)
+    lib.b2m_profile(0)
+    launches = lib.b2m_launch_count() - n0
+    dl = leaves_all() - l0
+    total_ms = timed.total_ms()
+    own_depths = depths[:, rank * (C // world):(rank + 1) * (C // world)]
+    mean_depth = float(own_depths.float().mean().item())
+    leaves_local = float(dl.item())
+
+    # ---- e2e: public API with host buffers; the front-end merges the slices' draws over torch.distributed
+    S_e2e, e2e_steps = ITERS, max(2, min(args.steps, 3))
+    host_theta = st.theta.cpu().numpy().copy()
+    host_init = {"beta": np.zeros(D, dtype=np.float32)}
+    eps_host = float(st.step_size.median().item())
+
+    def api_call(k):
+        return B.nuts(fn, host_init, num_samples=S_e2e, num_warmup=1, step_size=eps_host, max_tree_depth=MD,
+                      adapt_step_size=False, key=mx.random.key(100 + k), num_chains=C, compat="correct", return_info=True,
+                      theta0=host_theta, model=model, slice_state="peer")
+
+    api_call(0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_evals = 0
+    for k in range(e2e_steps):
+        _, _, info = api_call(k + 1)
+        e2e_evals += info.grad_evals
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clock_info = clocks.stop()
+
+    # ---- for the record: the same steps through NCCL (replicated state + all-reduce; sliced reduce-scatter / all-gather)
+    others = {}
+    for name_, mode_ in (("nccl_allreduce_replicated", _cabi.SLICE_OFF), ("nccl_reduce_scatter_sliced", _cabi.SLICE_NCCL)):
+        tm = Timed(torch, 2)
+        step(mode_)
+        barrier()
+        b0 = leaves_all()
+        tm.run(lambda: step(mode_))
+        barrier()
+        d_ = leaves_all() - b0
+        tt = torch.tensor([tm.total_ms()], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if mode_ != _cabi.SLICE_OFF:
+            dist.all_reduce(d_)
+        others[name_] = {"value": float(d_.item()) / (float(tt[0]) * 1e-3), "ms_per_step": float(tt[0]) / 2}
+
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([leaves_local, launches], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms, e2e_s = float(t[0]), float(t[1])
+    leaves_tot, launches_all = float(cnt[0]), int(cnt[1])
+    value = leaves_tot / (total_ms * 1e-3)
+    log(f"strong scaling, {world} ranks: {total_ms / args.steps:.1f} ms/step of {ITERS} transitions, mean depth {mean_depth:.2f}")
+    out = {"value": value, "ms_per_step": total_ms / args.steps, "gpu_launches": launches_all, "clocks": clock_info,
+           "e2e": {"value": e2e_evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": C * D * 4, "d2h_bytes_per_step": S_e2e * C * D * 4,
+                   "call": f"nuts(num_warmup=1, num_samples={S_e2e}, num_chains={C}, adapt_step_size=False, model=<obs-sharded>, "
+                           f"slice_state='peer') with [C, D] host initial values on every rank; merged draws returned as host numpy"},
+           "parity": parity, "obs_sharded_nccl": others,
+           "config_extra": {"chains_total": C, "chains_advanced_per_gpu": C // world, "rows_per_gpu": rows_local,
+                            "iters_per_step": ITERS, "mean_tree_depth": mean_depth,
+                            "grad_evals_per_step_total": leaves_tot / args.steps, "adapted_step_size_median": eps_host,
+                            "exchange": "peer window: K6 epilogue -> owner's slot (NVLink stores), owner -> all: packed fp16 rows; "
+                                        f"{4 * C * D * (world - 1) / world / 1e6:.1f} MB out per rank per gradient, no NCCL in the loop"}}
+    if rank != 0:
+        return out
+    out["roofline"] = glm_roofline(torch, four, leaves_tot, rows_local, D, C, total_ms, model, wl_name,
+                                   rows_note=f"{rows_local} of {N} observation rows per GPU (observation shard)")
+    both = out["roofline"]["avg_launch_ms"]["K5"] + out["roofline"]["avg_launch_ms"]["K6"]
+    ticks = out["roofline"]["launches_timed"] / 2 / args.steps
+    out["issue"] = {"lockstep_eval_ms_gemms": both, "tick_ms": total_ms / args.steps / max(ticks, 1), "ticks_per_step": ticks,
+                    "non_gemm_ms_per_tick": total_ms / args.steps / max(ticks, 1) - both}
+    return out
+
+
+def glm_ess_public_run(torch, B, wl, fn, C, chain_offset, n_warm=150, n_samp=500):
+    """min-ESS/s as SURVEY.md 8(d) defines it: the public MCMC.run from beta = 0 -- warm-up included in the wall time --
+    then the ESS of every (chain, coefficient) series on the device, summed over chains, minimum over coefficients."""
+    import mlx_mcmc_b200.core as mx  # noqa: F401
+    D = wl["d"]
+    m = B.MCMC(fn)
+    kw = dict(num_samples=n_samp, num_warmup=n_warm, method="nuts", step_size=wl["eps0"], max_tree_depth=wl["max_tree_depth"],
+              num_chains=C, chain_offset=chain_offset, compat="correct", step_size_adaptation="pooled", adapt_mass_matrix=True,
+              step_size_jitter=0.2, return_torch=True, return_info=True, verbose=False, random_seed=7)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    m.run({"beta": np.zeros(D, dtype=np.float32)}, **kw)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    tab = m.diagnostics()["beta"]
+    info = m.info
+    log(f"public run(): {n_warm}+{n_samp} iterations x {C} chains in {wall:.1f}s, mean depth {float(info.depths.mean()):.2f}")
+    return {"min_ess_per_s_geyer": float(tab["ess_geyer"].min()) / wall,
+            "min_ess_per_s_reference_estimator": float(tab["ess"].min()) / wall,
+            "max_rhat": float(np.nanmax(tab["rhat"])), "draws": n_samp, "warmup": n_warm, "wall_s": wall, "chains": C,
+            "grad_evals": int(info.grad_evals), "grad_evals_per_s_incl_warmup": info.grad_evals / wall,
+            "mean_tree_depth": float(info.depths.mean()), "step_size": float(np.median(info.step_size)),
+            "call": "MCMC(log_prob).run({'beta': 0}, num_warmup=%d, num_samples=%d, method='nuts', num_chains=%d, compat='correct', "
+                    "step_size_adaptation='pooled', adapt_mass_matrix=True, step_size_jitter=0.2, return_torch=True)" % (n_warm, n_samp, C),
+            "note": "wall time of the whole run() call from beta = 0 including warm-up (windowed step-size + diagonal mass-matrix "
+                    "adaptation); ESS of every (chain, coefficient) series computed on the device (b2m_diag_series), summed over "
+                    "chains, minimum over the coefficients; per GPU.  The reference estimator (examples/06:22-41) goes negative "
+                    "on antithetic chains; the Geyer figure is the one to read (SURVEY.md 8d)."}
 
 
 # ----------------------------------------------------------------------------------------- pointwise workloads
@@ -594,13 +785,29 @@ def bench_pointwise(torch, dist, B, lib, args, wl, wl_name, rank, world, local_r
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     launch_ms = total_ms / max(launches, 1)
     alg_bytes = ITERS * C * D * 4 + C * (D * 4 + 8 + 16) * 2     # draws written + chain state read and written back
-    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-    out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+    hbm_achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    # these configurations are bound by FP32 / SFU instruction issue, not by HBM or the tensor pipe.
+    # Algorithmic flops per evaluation = N x f_term (Normal likelihood 10, Exponential likelihood 4 per observation) +
+    # the scalar prior terms (~12 each: a log, a divide, a few multiply-adds) + the integrator (6 D per leapfrog step).
+    n_obs = int(getattr(meta, "N", 0))
+    f_term = {"c1_normal": 10.0, "c2_event_rate": 4.0}.get(wl["model"], 0.0)
+    n_prior = {"c1_normal": 2, "c2_event_rate": 1, "c5_ab_test": 4}.get(wl["model"], 1)
+    flops_per_eval = n_obs * f_term + 12.0 * n_prior + 6.0 * D
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12                  # 148 SMs x 128 FP32 lanes x FMA, at the maximum SM clock
+    achieved_tf = (value / world) * flops_per_eval / 1e12
+    out["roofline"] = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
                        "traffic": None, "kernel": "hmc_kernel" if wl["method"] == "hmc" else "mh_kernel",
-                       "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-                       "note": "observations live in shared memory; the kernel is FP32-issue bound, not HBM bound -- see `issue` "
-                               "and profiles/r01_hmc_kernel_c2_v2_ncu_summary.md"}
-    out["issue"] = {"grad_evals_per_s_per_gpu": value / world, "obs_terms_per_s_per_gpu": value / world * getattr(meta, "N", 0),
+                       "flops_per_eval": flops_per_eval,
+                       "peak_source": f"148 SMs x 128 FP32 lanes x 2 (FMA) x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); no tensor-pipe work "
+                                      "on this path",
+                       "hbm": {"achieved_GBps": hbm_achieved, "peak_GBps": hbm_peak, "frac": hbm_achieved / hbm_peak,
+                               "bytes": "draws written + chain state in/out; observations live in shared memory"},
+                       "issue_profile": PW_ISSUE.get(wl_name),
+                       "note": "FP32-issue bound (SURVEY.md 8d): achieved = algorithmic flops (N x f_term + priors + integrator) x grad-evals/s "
+                               "against the FP32 FMA peak.  The executed instruction mix per evaluation (interpreter control, Philox, "
+                               "logf / expf) and the issue-slot utilisation are in issue_profile, from the committed ncu capture."}
+    out["issue"] = {"grad_evals_per_s_per_gpu": value / world, "obs_terms_per_s_per_gpu": value / world * n_obs,
                     "avg_launch_ms": launch_ms}
     if full and not args.no_ess and wl["method"] == "hmc":
         torch.cuda.synchronize()
@@ -619,6 +826,52 @@ def bench_pointwise(torch, dist, B, lib, args, wl, wl_name, rank, world, local_r
                       "note": "ESS of every chain computed on the device (b2m_diag_series), summed over chains, minimum over "
                               "the parameters; per GPU"}
     return out
+
+
+def c1_single_chain(torch, B):
+    """BASELINE.json configs[0]: the reference's own CPU-runnable case through the public API, ONE chain, exactly the
+    settings of examples/02_hmc_comparison.py:87-97 (HMC eps0 = 0.1, L = 10, target 0.8, 1000 warm-up + 5000 draws, seed 42)."""
+    import mlx_mcmc_b200.core as mx
+    from mlx_mcmc_b200 import workloads as W
+    from mlx_mcmc_b200.diagnostics import compute_ess, ess_geyer
+    fn, init, _ = W.c1_normal(B.ns)
+    B.hmc(fn, init, num_samples=10, num_warmup=10, key=mx.random.key(1))      # trace + first launch outside the timing
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s, rate = B.hmc(fn, init, num_samples=5000, num_warmup=1000, step_size=0.1, num_leapfrog_steps=10, target_accept=0.8,
+                    key=mx.random.key(42))
+    wall = time.perf_counter() - t0
+    ess_ref = min(compute_ess(v) for v in s.values())
+    ess_g = min(ess_geyer(v) for v in s.values())
+    return {"call": "hmc(log_prob, {'mu': 0, 'sigma': 1}, num_samples=5000, num_warmup=1000, step_size=0.1, num_leapfrog_steps=10, "
+                    "target_accept=0.8, key=mx.random.key(42))  [1 chain, reference's +-5 % step-size rule, host numpy draws]",
+            "wall_s": wall, "grad_evals_per_s": 6000 * 10 / wall, "accept_rate": rate,
+            "min_ess_reference_estimator": ess_ref, "min_ess_geyer": ess_g, "min_ess_per_s_reference_estimator": ess_ref / wall,
+            "min_ess_per_s_geyer": ess_g / wall,
+            "posterior_mean": {k: float(np.mean(v)) for k, v in s.items()},
+            "note": "one chain cannot fill a GPU: the launch is latency bound (32 lanes of one warp stride the 100 observations); "
+                    "the reference's rule collapses the step size on this model exactly as the reference does (BASELINE.md section 2)"}
+
+
+def c1_chain_sweep(torch, B, lib):
+    """C1 throughput against the number of lock-step chains (device-timed, one launch of 50 iterations x L = 10)."""
+    from mlx_mcmc_b200 import _cabi, workloads as W
+    from mlx_mcmc_b200.engine import ChainState, compile_model, launch_hmc
+    fn, init, _ = W.c1_normal(B.ns)
+    model = compile_model(fn, init)
+    rows = []
+    for C in (1, 32, 1024, 16384, 65536, 262144, 1048576):
+        st = ChainState(model, model.pack(init, C), 0.01, 0)
+        launch_hmc(st, 20, 10, _cabi.ADAPT_NONE, 0.8, 7, 0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        launch_hmc(st, 50, 10, _cabi.ADAPT_NONE, 0.8, 7, 20)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        rows.append({"chains": C, "ms": ms, "grad_evals_per_s": C * 50 * 10 / (ms * 1e-3)})
+    return rows
 
 
 # ----------------------------------------------------------------------------------------- main
@@ -644,6 +897,9 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
+                    help="multi-GPU partitioning: strong = observation sharding of the same chains (default for c4), "
+                         "weak = chain sharding")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other configurations")
@@ -652,20 +908,27 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": wl["desc"], "chains_per_gpu": args.chains or wl["chains"],
-              "sharding": "chains (no data-path collective; weak scaling: per-GPU chains fixed)",
-              "l2": "flushed between timed steps (256 MiB write)"}
+    scaling = args.scaling
+    if scaling == "auto":      # BASELINE.json configs[3] is written observation-sharded; every other configuration shards chains
+        scaling = "strong" if args.workload == "c4" else "weak"
+    if scaling == "strong" and wl["kind"] != "glm":
+        raise SystemExit("--scaling strong (observation sharding) is defined for the regression workloads")
+    # `config` describes the workload and is the same object for both arms; what an arm actually executed is in `run`
+    config = {"workload": wl["desc"], "l2": "flushed between timed steps (256 MiB write)", "_scaling": scaling}
     if wl["kind"] == "glm":
-        config.update({"n_obs": wl["n"], "n_params": wl["d"], "sampler": "NUTS (iterative tree, iteration-asynchronous lock-step schedule, compat=correct, "
-                       f"max_tree_depth={wl['max_tree_depth']}, step size from pooled dual averaging over the rank's chains, "
-                       "identity mass matrix, no jitter)",
-                       "arithmetic": "tcgen05 GEMMs on hi/lo split operands (3xFP16 with power-of-two operand scaling when the data's dynamic "
-                                     "range allows, else 3xTF32), fp32 accumulate, centred contraction"})
+        config.update({"n_obs": wl["n"], "n_params": wl["d"], "chains": args.chains or wl["chains"],
+                       "sampler": f"NUTS, max_tree_depth={wl['max_tree_depth']}, identity mass matrix, no jitter, slice kept in log space "
+                                  "(compat=correct), chains at stationarity (started in the typical set), fixed adapted step size",
+                       "multi_gpu": ("strong scaling: the same chains in total, observations sharded over the ranks" if scaling == "strong"
+                                     else "weak scaling: chains sharded, per-GPU chains fixed, no data-path collective")})
+    else:
+        config.update({"chains_per_gpu": args.chains or wl["chains"], "multi_gpu": "weak scaling: chains sharded, no data-path collective"})
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         return reference_arm(args, wl, config)
+    config.pop("_scaling")
 
     import torch
     import torch.distributed as dist
@@ -678,20 +941,27 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _cabi.load(build_if_missing=False)
 
-    run = bench_glm if wl["kind"] == "glm" else bench_pointwise
-    res = run(torch, dist, B, lib, args, wl, args.workload, rank, world, local_rank)
+    if wl["kind"] == "glm" and scaling == "strong" and world > 1:
+        res = bench_glm_strong(torch, dist, B, lib, args, wl, args.workload, rank, world, local_rank)
+    else:
+        run = bench_glm if wl["kind"] == "glm" else bench_pointwise
+        res = run(torch, dist, B, lib, args, wl, args.workload, rank, world, local_rank)
 
     if rank == 0:
-        config.update(res.pop("config_extra"))
+        run_info = res.pop("config_extra")
+        run_info["what"] = ("b200 arm: hand-written sm_100a kernels through libb200mcmc.so; GLM arithmetic = tcgen05 GEMMs on hi/lo split "
+                            "operands (3xFP16 with power-of-two operand scaling when the data's dynamic range allows, else 3xTF32), fp32 "
+                            "accumulate, centred contraction; NUTS = iterative tree, iteration-asynchronous lock-step schedule with a "
+                            "fused per-chain state kernel")
         line = {"metric": METRIC, "value": res.pop("value"), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config}
+                "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "run": run_info}
         line.update(res)
         if world == 1 and not args.no_others:
             others = {}
             small = argparse.Namespace(**vars(args))
             small.steps, small.warmup, small.chains, small.no_ess = 5, 3, 0, True
-            for name in ("c3", "c2", "c5"):
+            for name in ("c3", "c2", "c1", "c5"):
                 if name == args.workload:
                     continue
                 w2 = WORKLOADS[name]
@@ -699,13 +969,20 @@ def main():
                                                                              local_rank, full=False)
                 others[name] = {"workload": w2["desc"], "value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms_per_step"],
                                 "e2e": r2["e2e"]["value"], "roofline": {k: r2["roofline"][k] for k in
-                                                                       ("bound", "achieved", "peak", "unit", "frac", "kernel")
+                                                                       ("bound", "achieved", "peak", "unit", "frac", "kernel", "hbm")
                                                                        if k in r2["roofline"]},
                                 "config": r2["config_extra"]}
+            others["c1"]["single_chain_drop_in"] = c1_single_chain(torch, B)
+            others["c1"]["chain_sweep"] = c1_chain_sweep(torch, B, lib)
             line["other_workloads"] = others
         log("device part done; cpu baseline")
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.workload, (os.cpu_count() or 1) if wl["kind"] == "glm" else 1)
+            if not args.no_others:
+                try:
+                    line["cpu_baseline"]["full_length"] = cpu_full_length()
+                except Exception as e:      # a worker died: say so, keep the line
+                    line["cpu_baseline"]["full_length"] = {"error": repr(e)}
         emit(line)
     if world > 1:
         dist.barrier()

@@ -181,6 +181,15 @@ def t_regression_small(ns, n=40, d=3):
     return fn, init, meta
 
 
+def t_regression_mid(ns, n=2048, d=64):
+    """A mid-size instance of the regression model: large enough for the tcgen05 contractions to run whole 128 x 256
+    tiles with a real K loop (the decision-level NUTS parity of the tensor-core path), small enough for the reference
+    to run a dozen transitions in seconds.  H0 is far above the reference's float32 slice underflow."""
+    fn, init, meta = regression(ns, n, d, seed=7)
+    meta.name = "t_regression_mid"
+    return fn, init, meta
+
+
 def t_regression_sigma(ns, n=60, d=4):
     """Regression with an unknown noise scale: sigma is a scalar parameter next to the coefficient vector."""
     mx, Normal, HalfNormal = ns.mx, ns.Normal, ns.HalfNormal
@@ -201,4 +210,5 @@ ALL_SMALL = {
     "t_normal_1d": t_normal_1d, "t_normal_2d": t_normal_2d, "t_halfnormal_scale": t_halfnormal_scale,
     "t_halfnormal": t_halfnormal, "t_vector_normal": t_vector_normal,
     "t_regression_small": t_regression_small, "t_regression_sigma": t_regression_sigma,
+    "t_regression_mid": t_regression_mid,
 }

@@ -89,6 +89,8 @@ RUNS = [
     ("nuts_regression", "t_regression_small", "nuts", dict(num_samples=40, num_warmup=40, step_size=0.05, max_tree_depth=6, seed=21)),
     ("nuts_regression_sigma", "t_regression_sigma", "nuts", dict(num_samples=30, num_warmup=40, step_size=0.05, max_tree_depth=6, seed=22)),
     ("nuts_c2", "c2_event_rate", "nuts", dict(num_samples=40, num_warmup=40, step_size=0.1, max_tree_depth=5, seed=11)),
+    # 64 coefficients x 2048 observations: the decision-level fixture of the tensor-core path (round 2)
+    ("nuts_regression_mid", "t_regression_mid", "nuts", dict(num_samples=8, num_warmup=8, step_size=0.002, max_tree_depth=5, seed=31)),
 ]
 
 
@@ -162,11 +164,15 @@ def check(names):
 def main():
     if len(sys.argv) > 2 and sys.argv[1] == "--check":
         return check(sys.argv[2:])
+    only = sys.argv[2:] if len(sys.argv) > 2 and sys.argv[1] == "--only" else None   # (re)write the named run fixtures only
     os.makedirs(OUT, exist_ok=True)
-    with open(os.path.join(OUT, "logp_grad.json"), "w") as f:
-        json.dump(golden_points(), f)
-    print("logp_grad.json written")
+    if only is None:
+        with open(os.path.join(OUT, "logp_grad.json"), "w") as f:
+            json.dump(golden_points(), f)
+        print("logp_grad.json written")
     for name, model, method, kw in RUNS:
+        if only is not None and name not in only:
+            continue
         g = golden_run(model, method, kw)
         with open(os.path.join(OUT, f"{name}.json"), "w") as f:
             json.dump(g, f)

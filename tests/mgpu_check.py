@@ -5,9 +5,10 @@
 2. observation sharding: log p / gradient of the row-sharded model agree with the unsharded model to float32
    rounding and are bit-identical on every rank;
 3. observation-sharded NUTS: every rank produces bit-identical draws, and they agree with the closed-form posterior;
-4. the same with sliced state (slice_state=True: reduce-scatter / all-gather inside the library): the merged draws are
-   identical on every rank, start out equal to the replicated schedule's (same Philox streams, rounding-level
-   differences only) and agree with the closed-form posterior; counters match the depth record.
+4. the same with sliced state, both forms -- 'nccl' (reduce-scatter / all-gather inside the library) and 'peer' (the
+   peer window: K6's epilogue stores gradient tiles into the owner's window over NVLink, release / acquire flags): the
+   merged draws are identical on every rank, start out equal to the replicated schedule's (same Philox streams,
+   rounding-level differences only) and agree with the closed-form posterior; counters match the depth record.
 Prints one line `MGPU_CHECK OK ...` from rank 0 on success; any failure raises on the failing rank.
 """
 import os
@@ -76,30 +77,37 @@ def main():
     report["obs_nuts_max_z"] = float(z.max())
     report["obs_nuts_grad_evals"] = info.grad_evals
 
-    # ---- 4. sliced state
+    # ---- 4. sliced state: NCCL reduce-scatter / all-gather, and the peer window (K6 push epilogue over NVLink)
     kw = dict(method="nuts", num_chains=256 * world, shard="obs", num_samples=40, num_warmup=80, step_size=0.05,
               compat="correct", key=mx.random.key(4), return_torch=True)
     s_rep, r_rep, i_rep = D.run_sharded(fr, initr, **kw)
-    s_sl, r_sl, i_sl = D.run_sharded(fr, initr, slice_state=True, **kw)
-    d_rep, d_sl = s_rep["beta"].contiguous(), s_sl["beta"].contiguous()
-    assert d_sl.shape == d_rep.shape == (256 * world, 40, 48)
-    allr = [torch.empty_like(d_sl) for _ in range(world)]
-    td.all_gather(allr, d_sl)
-    assert all(torch.equal(allr[0], a) for a in allr), "ranks hold different merged draws after a sliced run"
-    first = float((d_sl[:, 0] - d_rep[:, 0]).abs().max())        # first kept draw: same streams, rounding only
-    assert first < 5e-4, first
-    assert torch.isfinite(d_sl).all()
-    mean = d_sl.double().mean(dim=(0, 1)).cpu().numpy()
-    z = np.abs(mean - m) / np.sqrt(np.diag(V) / (256 * world * 40 / 4))
-    assert z.max() < 6.0, z.max()
-    assert i_sl.depths.shape == i_rep.depths.shape and i_sl.depths.min() >= 1
-    leaves = int((2 ** i_sl.depths.astype(np.int64) - 1).sum())   # leaves of the sampling phase follow from the depths
-    assert i_sl.grad_evals - i_sl.warmup_grad_evals <= leaves + i_sl.depths.size * 2, (i_sl.grad_evals, leaves)
-    assert abs(i_sl.grad_evals - i_rep.grad_evals) < 0.05 * i_rep.grad_evals, (i_sl.grad_evals, i_rep.grad_evals)
-    assert abs(r_sl - r_rep) < 0.05, (r_sl, r_rep)
-    report["sliced_first_draw_maxdiff"] = first
-    report["sliced_max_z"] = float(z.max())
-    report["sliced_grad_evals"] = (i_sl.grad_evals, i_rep.grad_evals)
+    d_rep = s_rep["beta"].contiguous()
+    for mode in ("nccl", "peer"):
+        s_sl, r_sl, i_sl = D.run_sharded(fr, initr, slice_state=mode, **kw)
+        d_sl = s_sl["beta"].contiguous()
+        assert d_sl.shape == d_rep.shape == (256 * world, 40, 48)
+        allr = [torch.empty_like(d_sl) for _ in range(world)]
+        td.all_gather(allr, d_sl)
+        assert all(torch.equal(allr[0], a) for a in allr), f"ranks hold different merged draws after a sliced run ({mode})"
+        first = float((d_sl[:, 0] - d_rep[:, 0]).abs().max())        # first kept draw: same streams, rounding only
+        assert first < 5e-4, (mode, first)
+        assert torch.isfinite(d_sl).all()
+        mean = d_sl.double().mean(dim=(0, 1)).cpu().numpy()
+        z = np.abs(mean - m) / np.sqrt(np.diag(V) / (256 * world * 40 / 4))
+        assert z.max() < 6.0, (mode, z.max())
+        assert i_sl.depths.shape == i_rep.depths.shape and i_sl.depths.min() >= 1
+        leaves = int((2 ** i_sl.depths.astype(np.int64) - 1).sum())   # leaves of the sampling phase follow from the depths
+        assert i_sl.grad_evals - i_sl.warmup_grad_evals <= leaves + i_sl.depths.size * 2, (mode, i_sl.grad_evals, leaves)
+        assert abs(i_sl.grad_evals - i_rep.grad_evals) < 0.05 * i_rep.grad_evals, (mode, i_sl.grad_evals, i_rep.grad_evals)
+        assert abs(r_sl - r_rep) < 0.05, (mode, r_sl, r_rep)
+        same_depth = float((i_sl.depths == i_rep.depths).mean())
+        report[f"sliced_{mode}_first_draw_maxdiff"] = first
+        report[f"sliced_{mode}_max_z"] = float(z.max())
+        report[f"sliced_{mode}_same_depths"] = same_depth
+        report[f"sliced_{mode}_grad_evals"] = (i_sl.grad_evals, i_rep.grad_evals)
+    # a second peer call on a fresh model: sequence numbers and flags of the windows start over cleanly
+    s2, _, _ = D.run_sharded(fr, initr, slice_state="peer", **{**kw, "num_samples": 10, "num_warmup": 20})
+    assert torch.isfinite(s2["beta"]).all()
 
     td.barrier()
     if rank == 0:

@@ -217,7 +217,7 @@ def test_nuts_tree_decisions_match_reference_unfused_paths(cuda, name, path):
     _replay_nuts(name, 1, glm_path=path)
 
 
-def _replay_nuts(name, lanes, schedule=0, glm_path="auto"):
+def _replay_nuts(name, lanes, schedule=0, glm_path="auto", copies=1, draw_tol=1e-5, alpha_tol=1e-4):
     """Every NUTS transition of the reference run is replayed on the GPU from the reference's own state
     (position, step size, dual-averaging state) with the reference's draws injected.  Replaying transition by
     transition keeps one-ulp differences of exp/log from being amplified by the step-size feedback loop, so
@@ -236,28 +236,30 @@ def _replay_nuts(name, lanes, schedule=0, glm_path="auto"):
     n_hits = 0
     for m in range(tot):
         it = iters[m]
-        st = ChainState(model, dev(q_prev[None, :]), it["eps"])
+        # `copies` identical chains fed the same draws: more than 128 rows puts the GLM contractions on CTA pairs
+        st = ChainState(model, dev(np.repeat(q_prev[None, :], copies, axis=0)), it["eps"])
         h_bar, eps_bar = da[min(m, nw)]
-        st.da_state[0, 0], st.da_state[0, 1], st.da_state[0, 2] = h_bar, eps_bar, mu
-        inj = {k: dev(v[m:m + 1]) for k, v in inj_all.items()}
-        tr = torch.full((1, 1, md, 6), -7, dtype=torch.int32, device="cuda")
-        depth = torch.zeros(1, 1, dtype=torch.int32, device="cuda")
-        alpha = torch.zeros(1, 1, device="cuda")
-        h0 = torch.zeros(1, 1, device="cuda")
-        draw = torch.zeros(1, 1, model.D, device="cuda")
+        st.da_state[:, 0], st.da_state[:, 1], st.da_state[:, 2] = h_bar, eps_bar, mu
+        inj = {k: dev(np.repeat(v[m:m + 1], copies, axis=1)) for k, v in inj_all.items()}
+        tr = torch.full((1, copies, md, 6), -7, dtype=torch.int32, device="cuda")
+        depth = torch.zeros(1, copies, dtype=torch.int32, device="cuda")
+        alpha = torch.zeros(1, copies, device="cuda")
+        h0 = torch.zeros(1, copies, device="cuda")
+        draw = torch.zeros(1, copies, model.D, device="cuda")
         launch_nuts(st, 1, md, _cabi.ADAPT_DUAL_AVERAGING if m < nw else _cabi.ADAPT_NONE, _cabi.COMPAT_REFERENCE, 0.65,
                     0, m, draws=draw, depths=depth, alphas=alpha, lanes=lanes, inj=inj, trace_doubling=tr, trace_energy=h0,
                     schedule=schedule)
         torch.cuda.synchronize()
-        assert int(depth[0, 0]) == it["depth"], (m, int(depth[0, 0]), it["depth"])
-        trc = tr.cpu().numpy()[0, 0]
-        for dbl in it["doublings"]:
-            want = [dbl["v"], dbl["n_sub"], int(dbl["s_sub"]), int(dbl["took"]), int(dbl["s"]), dbl["n"]]
-            assert trc[dbl["j"]].tolist() == want, (m, dbl, trc[dbl["j"]])
-        assert abs(float(h0[0, 0]) - it["H0"]) <= 1e-5 * max(1.0, abs(it["H0"]))
-        assert abs(float(alpha[0, 0]) - it["alpha"]) <= 1e-4 * max(it["alpha"], 1e-3), (m, float(alpha[0, 0]), it["alpha"])
         q_new = flat_params(model.layout, it["q_new"])
-        assert rel_err(draw.cpu().numpy()[0, 0], q_new) <= 1e-5 + 1e-6 / max(np.max(np.abs(q_new)), 1e-30), (m, draw, q_new)
+        for c in sorted({0, copies - 1}):
+            assert int(depth[0, c]) == it["depth"], (m, c, int(depth[0, c]), it["depth"])
+            trc = tr.cpu().numpy()[0, c]
+            for dbl in it["doublings"]:
+                want = [dbl["v"], dbl["n_sub"], int(dbl["s_sub"]), int(dbl["took"]), int(dbl["s"]), dbl["n"]]
+                assert trc[dbl["j"]].tolist() == want, (m, c, dbl, trc[dbl["j"]])
+            assert abs(float(h0[0, c]) - it["H0"]) <= 1e-5 * max(1.0, abs(it["H0"]))
+            assert abs(float(alpha[0, c]) - it["alpha"]) <= alpha_tol * max(it["alpha"], 1e-3), (m, float(alpha[0, c]), it["alpha"])
+            assert rel_err(draw.cpu().numpy()[0, c], q_new) <= draw_tol + 1e-6 / max(np.max(np.abs(q_new)), 1e-30), (m, draw, q_new)
         if m < nw:   # dual averaging: step size for the next iteration and the running average
             want_eps = iters[m + 1]["eps"] if m + 1 < nw else None
             if want_eps is not None:
