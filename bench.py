@@ -568,8 +568,17 @@ def bench_glm_strong(torch, dist, B, lib, args, wl, wl_name, rank, world, local_
     peer_leaves = (st.n_leaves - saved[1]).sum().double().reshape(1)
     dist.all_reduce(d2)                                     # merge the slices (each rank wrote its own chains' rows)
     dist.all_reduce(peer_leaves)
+    # Energies of this model are ~N/2 = 5e4, where float32 resolves 0.004: the two summation orders (NCCL ring vs
+    # per-source slots in rank order) differ at that level, so a slice / multinomial decision that sits on its boundary
+    # flips for a few chains and those chains continue on different -- equally valid -- trajectories.  Report how many
+    # chains agree and how closely, not a max over all 4 M entries.
     spread = float((d1 - mode[None, None, :]).std().item())
-    parity["peer_vs_allreduce_first_draw_maxdiff_in_posterior_sd"] = float((d1 - d2).abs().max().item()) / max(spread, 1e-30)
+    per_chain = (d1 - d2).abs().amax(dim=2)[0] / max(spread, 1e-30)          # [C] max |diff| in posterior sds
+    parity["peer_vs_allreduce_first_draw"] = {
+        "chains_agreeing_within_1e-2_sd": float((per_chain < 1e-2).float().mean().item()),
+        "median_chain_maxdiff_in_posterior_sd": float(per_chain.median().item()),
+        "grand_mean_diff_in_standard_errors": float(((d1.mean(dim=(0, 1)) - d2.mean(dim=(0, 1))).abs().max().item())
+                                                    / max(spread / C ** 0.5, 1e-30))}
     parity["peer_vs_allreduce_grad_evals"] = [int(peer_leaves.item()), rep_leaves]
     chk = torch.stack([d2.double().sum(), d2.double().abs().sum(), (d2.double() ** 2).sum()])
     allc = [torch.empty_like(chk) for _ in range(world)]

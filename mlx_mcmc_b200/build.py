@@ -37,7 +37,9 @@ def _sources():
 
 
 def _fingerprint() -> str:
-    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    # location independent: the snapshot on the GPU box lives under another root, and a library built here must count
+    # as current there (it is the binary the parity claims refer to)
+    h = hashlib.sha256(" ".join(f for f in NVCC_FLAGS if f != INCLUDE).encode())
     names = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
     for n in names + ["../../include/b200mcmc.h"]:
         with open(os.path.join(CSRC, n), "rb") as f:
@@ -57,6 +59,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a and link libb200mcmc.so.  Returns the library path."""
     if not force and is_current():
         return LIB
+    # one builder at a time: ranks of a torchrun job that all find the library stale must not compile into the same
+    # object files concurrently; the ones that waited find it current
+    import fcntl
+    with open(os.path.join(CSRC, ".build_lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
 

@@ -61,7 +61,7 @@ int load_nccl() {
   return 0;
 }
 
-constexpr int kNcclFloat32 = 7, kNcclInt64 = 4, kNcclSum = 0;
+constexpr int kNcclFloat32 = 7, kNcclInt64 = 4, kNcclSum = 0, kNcclMax = 2;
 
 #define B2M_CHECK_NCCL(expr)                                                             \
   do {                                                                                   \
@@ -133,6 +133,12 @@ int comm_reducescatter_f32_inplace(Comm *c, float *buf, int64_t count, cudaStrea
 int comm_allreduce_f32(Comm *c, float *buf, int64_t n, cudaStream_t st) {
   B2M_REQUIRE(c && c->nccl, "allreduce: communicator is NULL");
   B2M_CHECK_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, kNcclFloat32, kNcclSum, c->nccl, st));
+  return 0;
+}
+
+int comm_allreduce_f32_max(Comm *c, float *buf, int64_t n, cudaStream_t st) {
+  B2M_REQUIRE(c && c->nccl, "allreduce: communicator is NULL");
+  B2M_CHECK_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, kNcclFloat32, kNcclMax, c->nccl, st));
   return 0;
 }
 

@@ -30,6 +30,7 @@ void glm_free(GlmModel &g) {
   FREE(g.X); FREE(g.XT); FREE(g.Xh); FREE(g.Xl); FREE(g.XTh); FREE(g.XTl); FREE(g.y);
   FREE(g.y0); FREE(g.beta0); FREE(g.center_part);
   FREE(g.X16h); FREE(g.X16l); FREE(g.XT16h); FREE(g.XT16l); FREE(g.col_scale); FREE(g.inv_col_scale); FREE(g.y0max_bits);
+  FREE(g.colmax);
   FREE(g.ws);
   FREE(g.tf); FREE(g.blk_counter);
   g.ws_cap = 0;
@@ -128,12 +129,15 @@ __global__ void __launch_bounds__(256) x_small_count_kernel(const float *__restr
   if (cnt) atomicAdd(small + d, cnt);
 }
 
-__global__ void col_scale_kernel(const unsigned *__restrict__ colmax_bits, int Dp, float *col_scale, float *inv_col_scale) {
+__global__ void col_scale_kernel(const unsigned *__restrict__ colmax_bits, int Dp, float *col_scale, float *inv_col_scale,
+                                 float *colmax) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= Dp) return;
-  const float s = pow2_scale(__uint_as_float(colmax_bits[d]));
+  const float m = __uint_as_float(colmax_bits[d]);
+  const float s = pow2_scale(m);
   col_scale[d] = s;
   inv_col_scale[d] = 1.0f / s;
+  if (colmax) colmax[d] = m;
 }
 
 __global__ void split_f16_kernel(const float *__restrict__ Xp, int Np, int Dp, const float *__restrict__ col_scale,
@@ -183,9 +187,9 @@ int glm_build(GlmModel &g, const float *X, const float *y, int N, int D, bool fo
     if (!ok && !force_tc16) g.use_tc = 1;   // wide-range data: tf32 encoding
     if (g.use_tc == 2) {
       if (dev_alloc(&g.X16h, nd) || dev_alloc(&g.X16l, nd) || dev_alloc(&g.XT16h, nd) || dev_alloc(&g.XT16l, nd) ||
-          dev_alloc(&g.col_scale, g.Dp) || dev_alloc(&g.inv_col_scale, g.Dp))
+          dev_alloc(&g.col_scale, g.Dp) || dev_alloc(&g.inv_col_scale, g.Dp) || dev_alloc(&g.colmax, g.Dp))
         return 2;
-      col_scale_kernel<<<(g.Dp + 127) / 128, 128>>>(stats, g.Dp, g.col_scale, g.inv_col_scale);
+      col_scale_kernel<<<(g.Dp + 127) / 128, 128>>>(stats, g.Dp, g.col_scale, g.inv_col_scale, g.colmax);
       split_f16_kernel<<<(unsigned)((nd + 255) / 256), 256>>>(g.X, g.Np, g.Dp, g.col_scale, g.X16h, g.X16l, g.XT16h, g.XT16l);
       g_launches += 2;
     }
@@ -448,6 +452,18 @@ int glm_set_comm(GlmModel &g, Comm *c, cudaStream_t st) {
   g.comm = c;
   g.N_total = g.N;
   if (!c) return 0;
+  if (g.use_tc == 2) {
+    // The fp16 encoding scales every column of X by a power of two derived from the column maximum.  Ranks of an
+    // observation-sharded model must use the SAME scales: with sliced state the owner of a chain packs its position
+    // row (delta / col_scale) once for every rank's contraction.  Column maxima -> maximum over ranks -> re-split.
+    if (int rc = comm_allreduce_f32_max(c, g.colmax, g.Dp, st)) return rc;
+    col_scale_kernel<<<(g.Dp + 127) / 128, 128, 0, st>>>(reinterpret_cast<const unsigned *>(g.colmax), g.Dp, g.col_scale,
+                                                         g.inv_col_scale, nullptr);
+    const size_t nd = (size_t)g.Np * g.Dp;
+    split_f16_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, st>>>(g.X, g.Np, g.Dp, g.col_scale, g.X16h, g.X16l, g.XT16h, g.XT16l);
+    g_launches += 2;
+    B2M_CHECK_CUDA(cudaGetLastError());
+  }
   int64_t *d = nullptr, h = g.N;
   B2M_CHECK_CUDA(cudaMalloc(&d, sizeof(int64_t)));
   B2M_CHECK_CUDA(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, st));

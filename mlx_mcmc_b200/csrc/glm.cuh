@@ -24,6 +24,7 @@ int comm_allgather_inplace(Comm *c, void *buf, int64_t count, int elt_bytes, cud
 int comm_reducescatter_f32_inplace(Comm *c, float *buf, int64_t count, cudaStream_t st);
 int comm_allreduce_f32(Comm *c, float *buf, int64_t n, cudaStream_t st);
 int comm_allreduce_i64(Comm *c, int64_t *buf, int64_t n, cudaStream_t st);
+int comm_allreduce_f32_max(Comm *c, float *buf, int64_t n, cudaStream_t st);
 
 constexpr int kCenterSlices = 32;  // chain slices of the deterministic two-stage mean (glm.cu, centring)
 constexpr int kMaxPeers = 8;       // ranks of one NVSwitch box
@@ -65,6 +66,7 @@ struct GlmModel {
   // into two halves, hi = fp16(x'), lo = fp16(x' - hi); same for the transposed copy
   __half *X16h = nullptr, *X16l = nullptr, *XT16h = nullptr, *XT16l = nullptr;
   float *col_scale = nullptr, *inv_col_scale = nullptr;      // [Dp]
+  float *colmax = nullptr;                                   // [Dp] column maxima of |X| the scales were derived from
   float x_rownorm_max = 0.f;                                 // max_n ||X_n||_2: Cauchy-Schwarz bound of |(X delta)_n|
   unsigned *y0max_bits = nullptr;                            // device scalar: max_n |y0_n| as float bits (per recentre)
   // centring (glm.cu): beta0 = mean current position of the batch, y0 = y - c - X beta0 (float64 accumulation)

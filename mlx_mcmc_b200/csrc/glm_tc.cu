@@ -487,6 +487,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4 *>(g + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
     }
     }
+    // the writers themselves order their NVLink stores before anything that follows the kernel (the "partials stored"
+    // flag is raised by the next kernel on this stream): a system-scope fence per pushing thread, once per launch
+    if (PUSH) __threadfence_system();
   }
 #undef B2M_DECODE_TILE
 

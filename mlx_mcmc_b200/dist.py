@@ -275,8 +275,20 @@ def compile_obs_sharded(log_prob_fn, initial_params, group=None, comm: Optional[
     model = DeviceModel(traced, _require_cuda(), glm_path=glm_path)
     model._fn = log_prob_fn
     if world > 1:
+        # every rank must have chosen the same arithmetic (a shard with wild outliers falls back to the tf32 encoding):
+        # agree before the collective calls, so that a mismatch is an error on every rank and not a hang
+        flag = torch.tensor([1 if model.glm_path == "tc16" else 0], dtype=torch.int32,
+                            device=model.device if td.get_backend(group) == "nccl" else "cpu")
+        lo, hi = flag.clone(), flag.clone()
+        td.all_reduce(lo, op=td.ReduceOp.MIN, group=group)
+        td.all_reduce(hi, op=td.ReduceOp.MAX, group=group)
+        if int(lo) != int(hi):
+            raise ValueError("observation sharding: the ranks chose different GLM arithmetic paths for their shards; "
+                             "pass glm_path='tc' (or 'simt') explicitly")
         (comm or ObsComm(group, model.device)).attach(model)
         if peer_chains:
+            if int(lo) != 1:
+                raise ValueError("the peer window needs the fp16-encoded tensor-core path on every rank")
             PeerWindow(model, peer_chains, group)
     return model
 

@@ -89,8 +89,13 @@ def main():
         allr = [torch.empty_like(d_sl) for _ in range(world)]
         td.all_gather(allr, d_sl)
         assert all(torch.equal(allr[0], a) for a in allr), f"ranks hold different merged draws after a sliced run ({mode})"
-        first = float((d_sl[:, 0] - d_rep[:, 0]).abs().max())        # first kept draw: same streams, rounding only
-        assert first < 5e-4, (mode, first)
+        # first kept draw: same Philox streams.  The NCCL forms sum in the same order as the replicated all-reduce (equal
+        # to rounding); the peer form sums per-source slots in rank order, so a chain whose slice / multinomial decision
+        # sits on its float32 boundary may take another -- equally valid -- branch: nearly all chains must agree.
+        per_chain = (d_sl[:, 0] - d_rep[:, 0]).abs().amax(dim=1)
+        first = float(per_chain.median())
+        agree = float((per_chain < 5e-4).float().mean())
+        assert agree >= (0.97 if mode == "peer" else 1.0) and first < 5e-5, (mode, agree, first)
         assert torch.isfinite(d_sl).all()
         mean = d_sl.double().mean(dim=(0, 1)).cpu().numpy()
         z = np.abs(mean - m) / np.sqrt(np.diag(V) / (256 * world * 40 / 4))
@@ -101,7 +106,8 @@ def main():
         assert abs(i_sl.grad_evals - i_rep.grad_evals) < 0.05 * i_rep.grad_evals, (mode, i_sl.grad_evals, i_rep.grad_evals)
         assert abs(r_sl - r_rep) < 0.05, (mode, r_sl, r_rep)
         same_depth = float((i_sl.depths == i_rep.depths).mean())
-        report[f"sliced_{mode}_first_draw_maxdiff"] = first
+        report[f"sliced_{mode}_first_draw_median_maxdiff"] = first
+        report[f"sliced_{mode}_first_draw_chains_agreeing"] = agree
         report[f"sliced_{mode}_max_z"] = float(z.max())
         report[f"sliced_{mode}_same_depths"] = same_depth
         report[f"sliced_{mode}_grad_evals"] = (i_sl.grad_evals, i_rep.grad_evals)

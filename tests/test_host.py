@@ -312,3 +312,73 @@ def test_traced_idioms_keep_value_and_gradient(name):
         scale = max([1.0, abs(lp64)] + [abs(k) for t in model.terms for k in t.k])
         assert abs(table_logp(model, theta) - lp64) <= 5e-7 * scale, (name, trial, table_logp(model, theta), lp64)
         assert np.max(np.abs(table_grad(model, theta) - want)) <= 1e-5 * max(1.0, np.max(np.abs(want))), (name, trial)
+
+
+# ----------------------------------------------------------------------------- round 2: host logic of the new features
+def test_list_valued_observations_give_a_full_length_term():
+    """`Normal(mu, 1).log_prob([1.0, 2.0, 3.0])` -- the reference does `value = mx.array(value)`, so a Python
+    list is data; it must trace to a length-3 term over an observed array, never to its first element."""
+    t = B.trace(lambda p: mx.sum(B.Normal(p["mu"], 1.0).log_prob([1.0, 2.0, 3.0])), {"mu": 0.0})
+    assert len(t.terms) == 1 and t.terms[0].length == 3
+    assert np.array_equal(t.arrays[t.terms[0].x.a], np.asarray([1.0, 2.0, 3.0], dtype=np.float32))
+    t2 = B.trace(lambda p: mx.sum(B.Normal([0.5, 1.5], (2.0, 3.0)).log_prob(p["x"])), {"x": np.zeros(2, dtype=np.float32)})
+    assert t2.terms[0].length == 2 and t2.terms[0].p0.kind == 2 and t2.terms[0].p1.kind == 2
+    with pytest.raises(B.UnsupportedOpError):     # lengths that do not broadcast are an error, not a truncation
+        B.trace(lambda p: mx.sum(B.Normal(p["mu"], np.ones(2, dtype=np.float32)).log_prob(np.ones(3, dtype=np.float32))), {"mu": 0.0})
+
+
+def test_transform_codes_follow_the_support_of_the_value_distribution():
+    from mlx_mcmc_b200 import workloads as W
+    want = {"c1_normal": [0, 1], "c2_event_rate": [1], "c5_ab_test": [2, 2], "t_normal_2d": [0, 0], "t_halfnormal_scale": [1],
+            "t_regression_sigma": [0, 0, 0, 0, 1], "t_regression_small": [0, 0, 0]}
+    for name, codes in want.items():
+        fn, init, _ = W.ALL_SMALL[name](B.ns)
+        assert B.trace(fn, init).transform_codes().tolist() == codes, name
+    # a parameter claimed by a positive AND a unit-interval distribution keeps its own coordinate
+    t = B.trace(lambda p: B.HalfNormal(1.0).log_prob(p["x"]) + B.Beta(2, 2).log_prob(p["x"]), {"x": 0.5})
+    assert t.transform_codes().tolist() == [0]
+
+
+def test_warmup_window_schedule():
+    from mlx_mcmc_b200.kernels._common import warmup_windows
+    assert warmup_windows(10) == [(0, 10, False)]
+    assert warmup_windows(1000) == [(0, 75, False), (75, 100, True), (100, 150, True), (150, 250, True), (250, 450, True),
+                                    (450, 950, True), (950, 1000, False)]
+    assert warmup_windows(200) == [(0, 75, False), (75, 100, True), (100, 150, True), (150, 200, False)]
+    for n in (20, 33, 60, 100, 149, 150, 151, 333, 2000):
+        segs = warmup_windows(n)
+        assert segs[0][0] == 0 and segs[-1][1] == n and all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+        assert all(e > s for s, e, _ in segs) and any(u for _, _, u in segs)
+
+
+def test_model_cache_is_keyed_by_the_content_of_the_trace():
+    """the cache must not serve a stale model when the data a log_prob closes over changes; it is keyed by a
+    fingerprint of the re-traced terms and observed arrays, and bounded."""
+    from mlx_mcmc_b200 import engine
+    y = np.arange(6, dtype=np.float32)
+
+    def fn(p):
+        return mx.sum(B.Normal(p["mu"], 1.0).log_prob(mx.array(y)))
+
+    k1 = engine._trace_fingerprint(B.trace(fn, {"mu": 0.0}), (0,))
+    assert k1 == engine._trace_fingerprint(B.trace(fn, {"mu": 0.0}), (0,))
+    y[3] = 99.0                                     # same function object, same shapes, different data
+    k2 = engine._trace_fingerprint(B.trace(fn, {"mu": 0.0}), (0,))
+    assert k1 != k2
+    y[3], y[4] = y[4], 99.0                         # a permutation is a different data set too
+    assert engine._trace_fingerprint(B.trace(fn, {"mu": 0.0}), (0,)) != k2
+    assert k1 != engine._trace_fingerprint(B.trace(fn, {"mu": 0.0}), (0, "tc"))      # options are part of the key
+    big = np.random.default_rng(0).standard_normal((3000, 40)).astype(np.float32)   # id-keyed inside the tracer
+    f1 = engine._array_fingerprint(big)
+    big[1234, 7] += 1.0
+    assert engine._array_fingerprint(big) != f1
+    assert engine._CACHE_SIZE <= 8 and callable(engine.clear_model_cache)
+
+
+def test_peer_window_layout_is_what_the_header_documents():
+    """b2m_model_peer_bytes validates its arguments on the host (no device work)."""
+    lib = _cabi.load()
+    n = ctypes.c_int64()
+    assert lib.b2m_model_peer_bytes(None, 4096, 8, ctypes.byref(n)) != 0
+    assert b"NULL" in lib.b2m_last_error()
+    assert lib.b2m_options_size() == ctypes.sizeof(_cabi.ModelOptions)
