@@ -216,3 +216,28 @@ def test_nuts_tree_decisions_match_reference_at_mid_size(cuda, copies):
     direction, n', s', candidate taken, U-turn and depth must be the reference's."""
     from test_gpu_parity import _replay_nuts
     _replay_nuts("nuts_regression_mid", 1, copies=copies, draw_tol=1e-4, alpha_tol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------ parity check 3 at the Target size
+def test_c4_size_nuts_from_zero_matches_closed_form_posterior(cuda):
+    """BASELINE.json configs[3] through the user-facing call: 1000 coefficients x 100,000 observations, 4096 lock-step
+    chains from beta = 0, 60 warm-up + 40 kept transitions.  Posterior mean of every coefficient within 0.05 posterior sd
+    of the closed-form N(m, V), pooled sd within 3 %, R-hat ~ 1 (the numbers tools/c4_full_run.py prints)."""
+    n, d, C = 100000, 1000, 4096
+    fn, init, meta = W.regression(B.ns, n, d, seed=0)
+    m = B.MCMC(fn)
+    m.run(init, num_samples=40, num_warmup=60, method="nuts", step_size=1e-3, num_chains=C, compat="correct",
+          step_size_adaptation="pooled", step_size_jitter=0.2, return_torch=True, return_info=True, verbose=False, random_seed=1)
+    diag = m.diagnostics(ess=False)["beta"]
+    X = torch.from_numpy(meta.X).cuda().double()
+    A = (X.T @ X + torch.eye(d, device="cuda", dtype=torch.float64) / meta.prior_scale ** 2)
+    V = torch.linalg.inv(A)
+    post_m = (V @ (X.T @ torch.from_numpy(meta.y).cuda().double())).cpu().numpy()
+    sd = torch.sqrt(torch.diag(V)).cpu().numpy()
+    err = np.abs(diag["mean"] - post_m) / sd
+    ratio = diag["std"] / sd
+    assert err.max() < 0.05, err.max()
+    assert 0.97 < ratio.min() and ratio.max() < 1.03, (ratio.min(), ratio.max())
+    assert np.nanmax(diag["rhat"]) < 1.05
+    assert m.info.depths.mean() <= 5.0, m.info.depths.mean()
+    assert m.info.grad_evals > 0 and int(m.info.n_diverge.sum()) == 0
