@@ -743,6 +743,21 @@ def bench_pointwise(torch, dist, B, lib, args, wl, wl_name, rank, world, local_r
             dist.barrier()
         torch.cuda.synchronize()
 
+    # first the generic kernels (term table interpreted on every evaluation), for the record; then the kernels NVRTC
+    # specialised to this model (mlx_mcmc_b200/jit.py: same source, table baked in as literals) -- the timed path
+    from mlx_mcmc_b200.jit import specialize
+    generic_ms = None
+    if not args.no_jit:
+        tg = Timed(torch, 3)
+        for _ in range(3):
+            one_step()
+        barrier()
+        tg.run(one_step)
+        barrier()
+        generic_ms = tg.total_ms() / 3
+    t_jit = time.perf_counter()
+    jit_on = False if args.no_jit else specialize(model, "auto")
+    t_jit = time.perf_counter() - t_jit
     timed = Timed(torch, args.steps)
     for _ in range(max(args.warmup, 3)):
         timed.flush.fill_(1)
@@ -787,7 +802,9 @@ def bench_pointwise(torch, dist, B, lib, args, wl, wl_name, rank, world, local_r
                    "d2h_bytes_per_step": ITERS * C * D * 4,
                    "call": f"hmc(num_warmup={n_warm_e2e}, num_samples={ITERS}, num_chains={C})" if wl["method"] == "hmc"
                    else f"metropolis_hastings(num_samples={ITERS}, num_chains={C})"},
-           "config_extra": {"chains_per_gpu": C, "iters_per_step": ITERS}}
+           "config_extra": {"chains_per_gpu": C, "iters_per_step": ITERS, "specialised_kernels": bool(jit_on),
+                            "nvrtc_compile_s": t_jit if jit_on else None,
+                            "generic_interpreter_kernels_value": (world * evals_per_step / (generic_ms * 1e-3)) if generic_ms else None}}
     if rank != 0:
         return out
     peaks = load_peaks()
@@ -912,6 +929,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other configurations")
+    ap.add_argument("--no-jit", action="store_true", help="pointwise workloads: keep the generic interpreter kernels")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

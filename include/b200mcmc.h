@@ -21,7 +21,18 @@
 #ifndef B200MCMC_H
 #define B200MCMC_H
 
+#ifdef __CUDACC_RTC__
+/* NVRTC (the per-model pointwise kernels, mlx_mcmc_b200/jit.py) has no libc headers: the fixed-width types by hand */
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -216,6 +227,7 @@ typedef struct {
 } b2m_nuts_args;
 
 /* ---- entry points ---- */
+#ifndef __CUDACC_RTC__   /* (the NVRTC-compiled per-model kernels include this header for the structs above only) */
 
 const char *b2m_last_error(void);
 int b2m_abi_version(void);
@@ -230,6 +242,15 @@ int b2m_model_create(const b2m_term *terms, int32_t n_terms, const b2m_lin_entry
                      const b2m_array *arrays, int32_t n_arrays, int32_t D, const b2m_model_options *opt /* or NULL */,
                      b2m_model **out);
 void b2m_model_destroy(b2m_model *m);
+/* Per-model specialised kernels, pointwise class.  `cubin` = the translation unit mlx_mcmc_b200/jit.py generates from the
+ * traced model (this library's own device headers with the term table baked in as literals, so the interpreter of the
+ * generic kernels folds away) compiled by NVRTC for sm_100a; exports b2m_jit_logp_grad / _hmc / _mh / _nuts with the
+ * parameter lists of the generic kernels.  Afterwards b2m_logp_grad / b2m_hmc_run / b2m_mh_run / b2m_nuts_run of this model
+ * launch those entry points (same grid, same Philox slots, same arithmetic in the same order: bit-identical results).
+ * The reference re-traces the Python log_prob on every gradient (kernels/hmc.py:53-67) and names JIT compilation as its
+ * intended speed-up (TECHNICAL_OVERVIEW.md:232-236). */
+int b2m_model_attach_module(b2m_model *m, const void *cubin, int64_t bytes, int32_t dmax);
+int b2m_model_has_module(const b2m_model *m);
 int b2m_model_dim(const b2m_model *m);
 /* 0 = pointwise class (persistent register-resident kernels), 1 = GLM class (X @ beta, GEMM kernels) */
 int b2m_model_class(const b2m_model *m);
@@ -316,6 +337,8 @@ int b2m_profile_read(double *out4);
 
 /* number of kernel launches this library has issued since load (bench.py's gpu_launches) */
 int64_t b2m_launch_count(void);
+
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -14,11 +14,14 @@ int64_t g_launches = 0;
 void set_error(const std::string &msg) { tl_error = msg; }
 
 int pick_lanes(const KModel &km, int64_t n_chains, int requested);
+struct JitModule;
+int jit_load(const void *image, int dmax, JitModule **out);
+void jit_unload(JitModule *m);
 int launch_logp_grad(const KModel &km, const float *theta, int64_t C, float *logp, float *grad, int lanes,
-                     cudaStream_t st);
-int launch_hmc(const KModel &km, b2m_hmc_args a, cudaStream_t st);
-int launch_mh(const KModel &km, b2m_mh_args a, cudaStream_t st);
-int launch_nuts(const KModel &km, b2m_nuts_args a, cudaStream_t st);
+                     cudaStream_t st, JitModule *jit);
+int launch_hmc(const KModel &km, b2m_hmc_args a, cudaStream_t st, JitModule *jit);
+int launch_mh(const KModel &km, b2m_mh_args a, cudaStream_t st, JitModule *jit);
+int launch_nuts(const KModel &km, b2m_nuts_args a, cudaStream_t st, JitModule *jit);
 int glm_build(GlmModel &g, const float *X, const float *y, int N, int D, bool force_tc16);
 int mass_from_draws(const float *draws, int64_t S, int64_t C, int64_t D, float *inv_mass, cudaStream_t st);
 int quantiles(const float *x, int64_t n, const double *q, int n_q, double *out, cudaStream_t st);
@@ -47,6 +50,7 @@ struct b2m_model {
   std::vector<b2m_array> arrays;
   b2m::GlmModel glm;           // model_class == 1
   void *dev_prior_terms = nullptr;
+  b2m::JitModule *jit = nullptr;   // per-model specialised kernels (b2m_model_attach_module), pointwise class
 };
 
 using b2m::set_error;
@@ -311,8 +315,22 @@ void b2m_model_destroy(b2m_model *m) {
   if (m->dev_arrays) cudaFree(m->dev_arrays);
   if (m->dev_prior_terms) cudaFree(m->dev_prior_terms);
   if (m->model_class == 1) b2m::glm_free(m->glm);
+  b2m::jit_unload(m->jit);
   delete m;
 }
+
+int b2m_model_attach_module(b2m_model *m, const void *cubin, int64_t bytes, int32_t dmax) {
+  B2M_REQUIRE(m && cubin && bytes > 0, "b2m_model_attach_module: bad argument");
+  B2M_REQUIRE(m->model_class == 0, "b2m_model_attach_module: specialised kernels exist for the pointwise class only");
+  B2M_REQUIRE(dmax == 2 || dmax == 4 || dmax == 8 || dmax == 16, "b2m_model_attach_module: dmax must be 2, 4, 8 or 16");
+  B2M_REQUIRE(dmax >= m->km.D, "b2m_model_attach_module: dmax is smaller than the model's parameter count");
+  b2m::JitModule *j = nullptr;
+  if (int rc = b2m::jit_load(cubin, dmax, &j)) return rc;
+  b2m::jit_unload(m->jit);
+  m->jit = j;
+  return 0;
+}
+int b2m_model_has_module(const b2m_model *m) { return (m && m->jit) ? 1 : 0; }
 
 int b2m_model_dim(const b2m_model *m) { return m ? m->km.D : -1; }
 int b2m_model_class(const b2m_model *m) { return m ? m->model_class : -1; }
@@ -325,7 +343,7 @@ int b2m_logp_grad(b2m_model *m, const float *theta, int64_t n_chains, float *log
   B2M_REQUIRE(valid_lanes(lanes), "b2m_logp_grad: lanes must be 0 or a power of two <= 32");
   if (m->model_class == 1)
     return b2m::glm_logp_grad(m->glm, theta, n_chains, logp, grad, static_cast<cudaStream_t>(stream), true);
-  return b2m::launch_logp_grad(m->km, theta, n_chains, logp, grad, lanes, static_cast<cudaStream_t>(stream));
+  return b2m::launch_logp_grad(m->km, theta, n_chains, logp, grad, lanes, static_cast<cudaStream_t>(stream), m->jit);
 }
 
 struct b2m_comm {
@@ -420,7 +438,7 @@ int b2m_hmc_run(b2m_model *m, const b2m_hmc_args *a, void *stream) {
   B2M_REQUIRE(a->adapt != B2M_ADAPT_DUAL_AVERAGING || a->da_state, "b2m_hmc_run: dual averaging needs da_state");
   if (a->n_iter == 0) return 0;
   if (m->model_class == 1) return b2m::glm_hmc_run(m->glm, *a, static_cast<cudaStream_t>(stream));
-  return b2m::launch_hmc(m->km, *a, static_cast<cudaStream_t>(stream));
+  return b2m::launch_hmc(m->km, *a, static_cast<cudaStream_t>(stream), m->jit);
 }
 
 int b2m_mh_run(b2m_model *m, const b2m_mh_args *a, void *stream) {
@@ -430,7 +448,7 @@ int b2m_mh_run(b2m_model *m, const b2m_mh_args *a, void *stream) {
   B2M_REQUIRE(valid_lanes(a->lanes), "b2m_mh_run: lanes must be 0 or a power of two <= 32");
   if (a->n_iter == 0) return 0;
   if (m->model_class == 1) return b2m::glm_mh_run(m->glm, *a, static_cast<cudaStream_t>(stream));
-  return b2m::launch_mh(m->km, *a, static_cast<cudaStream_t>(stream));
+  return b2m::launch_mh(m->km, *a, static_cast<cudaStream_t>(stream), m->jit);
 }
 
 int b2m_nuts_run(b2m_model *m, const b2m_nuts_args *a, void *stream) {
@@ -451,7 +469,7 @@ int b2m_nuts_run(b2m_model *m, const b2m_nuts_args *a, void *stream) {
               "b2m_nuts_run: slice_state needs an observation-sharded GLM-class model, the asynchronous schedule and no adaptation");
   if (a->n_iter == 0) return 0;
   if (m->model_class == 1) return b2m::glm_nuts_run(m->glm, *a, static_cast<cudaStream_t>(stream));
-  return b2m::launch_nuts(m->km, *a, static_cast<cudaStream_t>(stream));
+  return b2m::launch_nuts(m->km, *a, static_cast<cudaStream_t>(stream), m->jit);
 }
 
 }  // extern "C"

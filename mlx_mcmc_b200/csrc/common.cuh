@@ -1,16 +1,30 @@
 // Shared device helpers: Philox4x32-10 counter RNG, uniform/normal transforms, error plumbing.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#endif
 
+#ifdef B2M_JIT
+#include "b200mcmc.h"      // NVRTC: headers are handed over by name (mlx_mcmc_b200/jit.py)
+#else
 #include "../../include/b200mcmc.h"
+#endif
+
+#ifdef __CUDACC_RTC__
+#ifndef INFINITY
+#define INFINITY __int_as_float(0x7f800000)
+#endif
+#endif
 
 namespace b2m {
 
+#ifndef __CUDACC_RTC__
 // ---------------------------------------------------------------- error plumbing (host)
 void set_error(const std::string &msg);
 extern int64_t g_launches;
+#endif
 
 #define B2M_CHECK_CUDA(expr)                                                                   \
   do {                                                                                         \

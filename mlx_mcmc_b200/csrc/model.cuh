@@ -76,10 +76,12 @@ struct SModel {
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
+#ifndef __CUDACC_RTC__
 __host__ inline size_t model_smem_bytes(const KModel &km) {
   return align16(sizeof(b2m_term) * km.n_terms) + align16(sizeof(b2m_lin_entry) * (km.n_lin > 0 ? km.n_lin : 1)) +
          align16(sizeof(DevArray) * (km.n_arrays > 0 ? km.n_arrays : 1)) + align16(sizeof(float) * km.stage_floats);
 }
+#endif
 
 // Cooperative copy of the term table (+ float4-staged observation vectors) into shared memory.
 // Returns the first free byte after the model region.
@@ -412,8 +414,122 @@ __device__ __forceinline__ void op_scatter_c(const b2m_operand &o, int n, float 
   else if (o.kind == B2M_OP_PARAMVEC) reg_add<DMAX>(g, o.a + n, adj);
 }
 
-// Same arithmetic, in the same order, as eval_model (so the two paths agree bit for bit); `km` must be the
-// kernel's __grid_constant__ parameter so that km.cterms[t] resolves to constant-bank operands.
+// One term of a compact / specialised model: same arithmetic, in the same order, as eval_model (so the paths agree bit
+// for bit).  Generic kernels pass `km.cterms[t]` of their __grid_constant__ parameter (constant-bank operands); the
+// NVRTC-specialised kernels (jit.cu, mlx_mcmc_b200/jit.py) pass a term built from literals, so that after inlining
+// every switch on the distribution, every operand kind and every constant folds away.
+template <bool GRAD, int DMAX>
+__device__ __forceinline__ void eval_term_c(const b2m_term &T, const SModel &sm, const float (&q)[DMAX], float (&g)[DMAX],
+                                            int lane, int G, float &total) {
+  const int dist = T.dist, len = T.length;
+  const float k0 = T.k0, k1 = T.k1, k2 = T.k2, w = T.weight;
+  float acc = 0.f, ax = 0.f, a0 = 0.f, a1 = 0.f;
+  const bool params_fixed = !op_varies(T.p0) && !op_varies(T.p1);
+  if (params_fixed && T.x.kind == B2M_OP_DATA && dist == B2M_NORMAL) {
+    const float mu = op_fetch_c<DMAX>(T.p0, 0, q, sm), sg = op_fetch_c<DMAX>(T.p1, 0, q, sm);
+    const float inv_var = 1.0f / (sg * sg), base = -kHalfLog2Pi - logf(sg);
+    const float *y = sm.arrays[T.x.a].ptr;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    int n = lane;
+    if (G == 1 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+      const float4 *y4 = reinterpret_cast<const float4 *>(y);
+      for (; n + 3 < len; n += 4) {
+        const float4 v = y4[n >> 2];
+        const float z0 = v.x - mu, z1 = v.y - mu, z2 = v.z - mu, z3 = v.w - mu;
+        s1[0] += z0; s1[1] += z1; s1[2] += z2; s1[3] += z3;
+        s2[0] = fmaf(z0, z0, s2[0]); s2[1] = fmaf(z1, z1, s2[1]);
+        s2[2] = fmaf(z2, z2, s2[2]); s2[3] = fmaf(z3, z3, s2[3]);
+      }
+    } else {
+      for (; n + 3 * G < len; n += 4 * G) {
+        const float z0 = y[n] - mu, z1 = y[n + G] - mu, z2 = y[n + 2 * G] - mu, z3 = y[n + 3 * G] - mu;
+        s1[0] += z0; s1[1] += z1; s1[2] += z2; s1[3] += z3;
+        s2[0] = fmaf(z0, z0, s2[0]); s2[1] = fmaf(z1, z1, s2[1]);
+        s2[2] = fmaf(z2, z2, s2[2]); s2[3] = fmaf(z3, z3, s2[3]);
+      }
+    }
+    for (; n < len; n += G) {
+      const float z = y[n] - mu;
+      s1[0] += z;
+      s2[0] = fmaf(z, z, s2[0]);
+    }
+    const float t1 = (s1[0] + s1[1]) + (s1[2] + s1[3]), t2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+    const float cnt = (float)((len - lane + G - 1) / G);
+    acc = cnt * base - 0.5f * t2 * inv_var;
+    a0 = t1 * inv_var;
+    a1 = (t2 * inv_var - cnt) / sg;
+  } else if (params_fixed && T.x.kind == B2M_OP_DATA && dist == B2M_EXPONENTIAL) {
+    const float rate = op_fetch_c<DMAX>(T.p0, 0, q, sm);
+    const float lr = logf(rate), ir = 1.0f / rate;
+    const float *y = sm.arrays[T.x.a].ptr;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f};
+    float lo = INFINITY;
+    int n = lane;
+    if (G == 1 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+      const float4 *y4 = reinterpret_cast<const float4 *>(y);
+      for (; n + 3 < len; n += 4) {
+        const float4 v = y4[n >> 2];
+        s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+        lo = fminf(fminf(lo, fminf(v.x, v.y)), fminf(v.z, v.w));
+      }
+    } else {
+      for (; n + 3 * G < len; n += 4 * G) {
+        const float v0 = y[n], v1 = y[n + G], v2 = y[n + 2 * G], v3 = y[n + 3 * G];
+        s1[0] += v0; s1[1] += v1; s1[2] += v2; s1[3] += v3;
+        lo = fminf(fminf(lo, fminf(v0, v1)), fminf(v2, v3));
+      }
+    }
+    for (; n < len; n += G) {
+      const float v = y[n];
+      s1[0] += v;
+      lo = fminf(lo, v);
+    }
+    const float t1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+    const float cnt = (float)((len - lane + G - 1) / G);
+    const bool bad = !(lo >= 0.f) || !(t1 == t1);
+    if (!bad) {
+      acc = cnt * lr - rate * t1;
+      a0 = cnt * ir - t1;
+    } else {
+      acc = -INFINITY;
+      a0 = 0.f;
+      for (int m = lane; m < len; m += G) {
+        const float v = y[m];
+        if (v >= 0.f) a0 += ir - v;
+      }
+    }
+  } else {
+    for (int n = lane; n < len; n += G) {
+      const float x = op_fetch_c<DMAX>(T.x, n, q, sm);
+      const float p0 = op_fetch_c<DMAX>(T.p0, n, q, sm);
+      const float p1 = op_fetch_c<DMAX>(T.p1, n, q, sm);
+      Elem e = dist_eval<GRAD>(dist, x, p0, p1, k0, k1, k2);
+      acc += e.lp;
+      if (GRAD) {
+        if (T.x.kind == B2M_OP_PARAM) ax += e.dx; else op_scatter_c<DMAX>(T.x, n, w * e.dx, g);
+        if (T.p0.kind == B2M_OP_PARAM) a0 += e.d0; else op_scatter_c<DMAX>(T.p0, n, w * e.d0, g);
+        if (T.p1.kind == B2M_OP_PARAM) a1 += e.d1; else op_scatter_c<DMAX>(T.p1, n, w * e.d1, g);
+      }
+    }
+  }
+  total += w * acc;
+  if (GRAD) {
+    if (T.x.kind == B2M_OP_PARAM) reg_add<DMAX>(g, T.x.a, w * ax);
+    if (T.p0.kind == B2M_OP_PARAM) reg_add<DMAX>(g, T.p0.a, w * a0);
+    if (T.p1.kind == B2M_OP_PARAM) reg_add<DMAX>(g, T.p1.a, w * a1);
+  }
+}
+
+#ifdef B2M_JIT
+// the generated translation unit defines B2M_JIT_TERMS(F): one F(dist, length, weight, k0, k1, k2, x.kind, x.a, x.b, x.c,
+// p0.kind, p0.a, p0.b, p0.c, p1.kind, p1.a, p1.b, p1.c) per term of the traced model
+#define B2M_JIT_ONE_TERM(DIST, LEN, W, K0, K1, K2, XK, XA, XB, XC, AK, AA, AB, AC, BK, BA, BB, BC)                      \
+  {                                                                                                                      \
+    const b2m_term T = {DIST, LEN, W, K0, K1, K2, {XK, XA, XB, XC}, {AK, AA, AB, AC}, {BK, BA, BB, BC}};                  \
+    eval_term_c<GRAD, DMAX>(T, sm, q, g, lane, G, total);                                                                \
+  }
+#endif
+
 template <bool GRAD, int DMAX>
 __device__ __forceinline__ float eval_model_c(const KModel &km, const SModel &sm, const float (&q)[DMAX], float (&g)[DMAX],
                                               int lane, int G, unsigned gmask) {
@@ -422,108 +538,16 @@ __device__ __forceinline__ float eval_model_c(const KModel &km, const SModel &sm
 #pragma unroll
     for (int d = 0; d < DMAX; ++d) g[d] = 0.f;
   }
+#ifdef B2M_JIT
+  (void)km;
+  B2M_JIT_TERMS(B2M_JIT_ONE_TERM)
+#else
 #pragma unroll
   for (int t = 0; t < kCompactTerms; ++t) {
     if (t >= km.n_terms) break;
-    const b2m_term &T = km.cterms[t];
-    const int dist = T.dist, len = T.length;
-    const float k0 = T.k0, k1 = T.k1, k2 = T.k2, w = T.weight;
-    float acc = 0.f, ax = 0.f, a0 = 0.f, a1 = 0.f;
-    const bool params_fixed = !op_varies(T.p0) && !op_varies(T.p1);
-    if (params_fixed && T.x.kind == B2M_OP_DATA && dist == B2M_NORMAL) {
-      const float mu = op_fetch_c<DMAX>(T.p0, 0, q, sm), sg = op_fetch_c<DMAX>(T.p1, 0, q, sm);
-      const float inv_var = 1.0f / (sg * sg), base = -kHalfLog2Pi - logf(sg);
-      const float *y = sm.arrays[T.x.a].ptr;
-      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-      int n = lane;
-      if (G == 1 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
-        const float4 *y4 = reinterpret_cast<const float4 *>(y);
-        for (; n + 3 < len; n += 4) {
-          const float4 v = y4[n >> 2];
-          const float z0 = v.x - mu, z1 = v.y - mu, z2 = v.z - mu, z3 = v.w - mu;
-          s1[0] += z0; s1[1] += z1; s1[2] += z2; s1[3] += z3;
-          s2[0] = fmaf(z0, z0, s2[0]); s2[1] = fmaf(z1, z1, s2[1]);
-          s2[2] = fmaf(z2, z2, s2[2]); s2[3] = fmaf(z3, z3, s2[3]);
-        }
-      } else {
-        for (; n + 3 * G < len; n += 4 * G) {
-          const float z0 = y[n] - mu, z1 = y[n + G] - mu, z2 = y[n + 2 * G] - mu, z3 = y[n + 3 * G] - mu;
-          s1[0] += z0; s1[1] += z1; s1[2] += z2; s1[3] += z3;
-          s2[0] = fmaf(z0, z0, s2[0]); s2[1] = fmaf(z1, z1, s2[1]);
-          s2[2] = fmaf(z2, z2, s2[2]); s2[3] = fmaf(z3, z3, s2[3]);
-        }
-      }
-      for (; n < len; n += G) {
-        const float z = y[n] - mu;
-        s1[0] += z;
-        s2[0] = fmaf(z, z, s2[0]);
-      }
-      const float t1 = (s1[0] + s1[1]) + (s1[2] + s1[3]), t2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
-      const float cnt = (float)((len - lane + G - 1) / G);
-      acc = cnt * base - 0.5f * t2 * inv_var;
-      a0 = t1 * inv_var;
-      a1 = (t2 * inv_var - cnt) / sg;
-    } else if (params_fixed && T.x.kind == B2M_OP_DATA && dist == B2M_EXPONENTIAL) {
-      const float rate = op_fetch_c<DMAX>(T.p0, 0, q, sm);
-      const float lr = logf(rate), ir = 1.0f / rate;
-      const float *y = sm.arrays[T.x.a].ptr;
-      float s1[4] = {0.f, 0.f, 0.f, 0.f};
-      float lo = INFINITY;
-      int n = lane;
-      if (G == 1 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
-        const float4 *y4 = reinterpret_cast<const float4 *>(y);
-        for (; n + 3 < len; n += 4) {
-          const float4 v = y4[n >> 2];
-          s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
-          lo = fminf(fminf(lo, fminf(v.x, v.y)), fminf(v.z, v.w));
-        }
-      } else {
-        for (; n + 3 * G < len; n += 4 * G) {
-          const float v0 = y[n], v1 = y[n + G], v2 = y[n + 2 * G], v3 = y[n + 3 * G];
-          s1[0] += v0; s1[1] += v1; s1[2] += v2; s1[3] += v3;
-          lo = fminf(fminf(lo, fminf(v0, v1)), fminf(v2, v3));
-        }
-      }
-      for (; n < len; n += G) {
-        const float v = y[n];
-        s1[0] += v;
-        lo = fminf(lo, v);
-      }
-      const float t1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
-      const float cnt = (float)((len - lane + G - 1) / G);
-      const bool bad = !(lo >= 0.f) || !(t1 == t1);
-      if (!bad) {
-        acc = cnt * lr - rate * t1;
-        a0 = cnt * ir - t1;
-      } else {
-        acc = -INFINITY;
-        a0 = 0.f;
-        for (int m = lane; m < len; m += G) {
-          const float v = y[m];
-          if (v >= 0.f) a0 += ir - v;
-        }
-      }
-    } else {
-      for (int n = lane; n < len; n += G) {
-        const float x = op_fetch_c<DMAX>(T.x, n, q, sm);
-        const float p0 = op_fetch_c<DMAX>(T.p0, n, q, sm);
-        const float p1 = op_fetch_c<DMAX>(T.p1, n, q, sm);
-        Elem e = dist_eval<GRAD>(dist, x, p0, p1, k0, k1, k2);
-        acc += e.lp;
-        if (GRAD) {
-          if (T.x.kind == B2M_OP_PARAM) ax += e.dx; else op_scatter_c<DMAX>(T.x, n, w * e.dx, g);
-          if (T.p0.kind == B2M_OP_PARAM) a0 += e.d0; else op_scatter_c<DMAX>(T.p0, n, w * e.d0, g);
-          if (T.p1.kind == B2M_OP_PARAM) a1 += e.d1; else op_scatter_c<DMAX>(T.p1, n, w * e.d1, g);
-        }
-      }
-    }
-    total += w * acc;
-    if (GRAD) {
-      if (T.x.kind == B2M_OP_PARAM) reg_add<DMAX>(g, T.x.a, w * ax);
-      if (T.p0.kind == B2M_OP_PARAM) reg_add<DMAX>(g, T.p0.a, w * a0);
-      if (T.p1.kind == B2M_OP_PARAM) reg_add<DMAX>(g, T.p1.a, w * a1);
-    }
+    eval_term_c<GRAD, DMAX>(km.cterms[t], sm, q, g, lane, G, total);
   }
+#endif
   for (int o = G >> 1; o > 0; o >>= 1) total += __shfl_xor_sync(gmask, total, o);
   if (GRAD && G > 1) {
 #pragma unroll

@@ -1,6 +1,8 @@
 // Helpers shared by the pointwise-class kernels (pointwise.cu, nuts_pointwise.cu).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <math.h>
+#endif
 
 #include "model.cuh"
 
@@ -117,14 +119,27 @@ __device__ __forceinline__ float evaluate_plain(const KModel &km, const SModel &
 // With constraint transforms the chain state `q` is the unconstrained coordinate u: the model is evaluated at
 // theta = T(u), the gradient is chained through dT/du and the log-Jacobian joins value and gradient.  km.has_tf is a
 // kernel-parameter constant: models without transforms (the reference's behaviour) take the first branch unchanged.
+#ifdef B2M_JIT
+// specialised kernels: the transform codes are literals of the generated translation unit
+__device__ constexpr int jit_tf(int d) {
+  constexpr int codes[16] = B2M_JIT_TF_LIST;
+  return d < 16 ? codes[d] : 0;
+}
+#define B2M_HAS_TF(km) (B2M_JIT_HAS_TF != 0)
+#define B2M_TF_CODE(km, d) jit_tf(d)
+#else
+#define B2M_HAS_TF(km) ((km).has_tf != 0)
+#define B2M_TF_CODE(km, d) ((d) < 16 ? (int)(km).tf[d] : 0)
+#endif
+
 template <int DMAX, bool COMPACT, bool GRAD>
 __device__ __forceinline__ float evaluate(const KModel &km, const SModel &sm, const Lane &L, const float (&q)[DMAX],
                                           float (&g)[DMAX]) {
-  if (!km.has_tf) return evaluate_plain<DMAX, COMPACT, GRAD>(km, sm, L, q, g);
+  if (!B2M_HAS_TF(km)) return evaluate_plain<DMAX, COMPACT, GRAD>(km, sm, L, q, g);
   float th[DMAX], jac[DMAX], dlj[DMAX], lj = 0.f;
 #pragma unroll
   for (int d = 0; d < DMAX; ++d) {
-    const Tf t = tf_apply(d < 16 ? km.tf[d] : 0, q[d]);
+    const Tf t = tf_apply(B2M_TF_CODE(km, d), q[d]);
     th[d] = t.theta; jac[d] = t.jac; dlj[d] = t.dlogjac;
     if (d < sm.D) lj += t.logjac;
   }
@@ -139,10 +154,10 @@ __device__ __forceinline__ float evaluate(const KModel &km, const SModel &sm, co
 // a draw as the caller wants it: the constrained value unless the call asks for the sampler's own coordinates
 template <int DMAX>
 __device__ __forceinline__ void store_draw(float *dst, const float (&q)[DMAX], int D, const KModel &km, bool unconstrained) {
-  if (!km.has_tf || unconstrained) { store_vec<DMAX>(dst, q, D); return; }
+  if (!B2M_HAS_TF(km) || unconstrained) { store_vec<DMAX>(dst, q, D); return; }
 #pragma unroll
   for (int d = 0; d < DMAX; ++d)
-    if (d < D) dst[d] = tf_constrain(d < 16 ? km.tf[d] : 0, q[d]);
+    if (d < D) dst[d] = tf_constrain(B2M_TF_CODE(km, d), q[d]);
 }
 
 // diagonal mass matrix (ABI 2): im = diag(M^-1) or all ones, sm_ = sqrt of the diagonal of M
@@ -164,10 +179,19 @@ __device__ __forceinline__ float kinetic_m(const float (&p)[DMAX], const float (
   return __fmul_rn(0.5f, s);
 }
 
+#ifndef __CUDACC_RTC__
 // ---------------------------------------------------------------- host-side launchers
 inline int pick_dmax(int D) { return D <= 2 ? 2 : D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 0; }
 
 int pick_lanes(const KModel &km, int64_t n_chains, int requested);
+
+// per-model specialised kernels (jit.cu): entry points of a loaded module, indexed in this order
+struct JitModule;
+enum { JIT_LOGP_GRAD = 0, JIT_HMC = 1, JIT_MH = 2, JIT_NUTS = 3 };
+int jit_load(const void *image, int dmax, JitModule **out);
+void jit_unload(JitModule *m);
+int jit_dmax(const JitModule *m);
+int jit_launch(JitModule *m, int which, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void **params);
 
 struct Geometry {
   dim3 grid, block;
@@ -201,6 +225,6 @@ static int prep(K kernel, size_t smem) {
     case 16: { constexpr int DM = 16; constexpr bool CP = false; __VA_ARGS__; } break; \
     default: b2m::set_error("pointwise models support at most 16 scalar parameters"); return 1; \
   }
-
+#endif  // !__CUDACC_RTC__
 
 }  // namespace b2m

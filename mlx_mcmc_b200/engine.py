@@ -80,6 +80,7 @@ class DeviceModel:
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.b2m_model_create(terms, n_t, lin, n_l, arrays, n_a, self.D, C.byref(opt), C.byref(handle)))
         self.handle = handle
+        self.jit = False            # set by jit.specialize once a specialised module is attached
         self.model_class = self.lib.b2m_model_class(handle)
         self.glm_path = {0: "simt", 1: "tc", 2: "tc16"}.get(self.lib.b2m_model_glm_path(handle))
 

@@ -17,13 +17,22 @@ def philox_seed(key, random_seed=None) -> int:
     return int(random_seed or 0)
 
 
+JIT_MIN_CHAINS = 1024      # jit='auto': a ~3 s NVRTC compile per model pays off from about this many lock-step chains
+
+
 def prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, model=None, theta0=None, cache=True,
-            transforms=None):
+            transforms=None, jit="auto"):
     """Trace/compile (cached by the content of the trace, engine.compile_model) and build the per-chain state.
     `theta0` ([num_chains, D], in the sampler's coordinates) overrides the common starting point -- used to hand
     the warm-up's final positions to the sampling call."""
     model = model if isinstance(model, DeviceModel) else compile_model(log_prob_fn, initial_params, cache=cache,
                                                                        transforms=transforms)
+    if jit not in ("auto", True, False, "on", "off"):
+        raise ValueError(f"Unknown jit option: {jit}")
+    if not getattr(model, "jit", False) and (jit in (True, "on") or (jit == "auto" and num_chains >= JIT_MIN_CHAINS)):
+        # pointwise class: kernels specialised to this model's term table (mlx_mcmc_b200/jit.py); bit-identical results
+        from ..jit import specialize
+        specialize(model, True if jit in (True, "on") else "auto")
     if theta0 is not None:
         theta0 = torch.as_tensor(theta0)          # a host array is copied to the device here (pinned staging)
         if tuple(theta0.shape) != (num_chains, model.D):

@@ -38,6 +38,7 @@ def hmc(
     adapt_mass_matrix: bool = False,
     transforms=None,
     cache: bool = True,
+    jit="auto",
 ) -> Tuple[Dict[str, object], float]:
     """Same arguments and return value as the reference's ``hmc``: ``(samples, acceptance_rate)`` with
     ``samples[name]`` of shape ``(num_samples,)`` (sampling-phase acceptance rate, hmc.py:200-206).
@@ -56,7 +57,7 @@ def hmc(
     if adapt not in ("reference", "dual_averaging"):
         raise ValueError(f"Unknown adapt mode: {adapt}")
     seed = philox_seed(key, 0)
-    model, st = prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, model, theta0, cache, transforms)
+    model, st = prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, model, theta0, cache, transforms, jit)
     mode = _cabi.ADAPT_NONE
     if adapt_step_size:
         mode = _cabi.ADAPT_REFERENCE if adapt == "reference" else _cabi.ADAPT_DUAL_AVERAGING

@@ -21,13 +21,14 @@ def metropolis_hastings(
     model=None,
     theta0=None,
     cache: bool = True,
+    jit="auto",
 ):
     """Same arguments and return value as the reference: ``(samples, acceptance_rate)`` where
     ``samples[name]`` holds ``num_samples`` values (a numpy array here, a python list there) and the
     rate is accepted / num_samples (metropolis.py:99).  One launch of `mh_kernel` runs all steps for
     all chains with the current log-prob cached on device (metropolis.py:55,87)."""
     seed = philox_seed(None, random_seed)
-    model, st = prepare(log_prob_fn, initial_params, num_chains, 0.0, chain_offset, model, theta0, cache)
+    model, st = prepare(log_prob_fn, initial_params, num_chains, 0.0, chain_offset, model, theta0, cache, None, jit)
     draws = alloc_draws(model, num_samples, num_chains)
     launch_mh(st, num_samples, float(proposal_scale), seed, 0, draws=draws, lanes=lanes)
     rate = float(st.n_accept.double().sum().item() / max(num_samples * num_chains, 1))

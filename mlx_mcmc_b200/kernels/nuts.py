@@ -53,6 +53,7 @@ def nuts(
     adapt_mass_matrix: bool = False,
     transforms=None,
     cache: bool = True,
+    jit="auto",
 ) -> Tuple[Dict[str, object], float]:
     """Same arguments and return value as the reference's ``nuts``: ``(samples, rate)`` where rate is the
     fraction of sampling iterations whose mean acceptance statistic exceeded 0.5 (nuts.py:341,353) and
@@ -87,7 +88,11 @@ def nuts(
     the pooled draws of all chains at the end of slow windows of doubling length, dual averaging restarted after every
     update.  ``transforms='auto'`` (extension, PROGRESS.md:119): parameters that are the value of a HalfNormal /
     Exponential / Gamma (Beta) term are sampled in log (logit) coordinates with the log-Jacobian added, which removes
-    the hard walls that freeze the reference's NUTS; draws come back in the model's own coordinates."""
+    the hard walls that freeze the reference's NUTS; draws come back in the model's own coordinates.
+
+    ``jit`` (pointwise-class models): 'auto' compiles kernels specialised to this model's term table with NVRTC when the
+    call runs >= 1024 chains (mlx_mcmc_b200/jit.py; ~3 s once per model, cached on disk), True forces it, False keeps the
+    generic interpreter kernels.  The draws are bit-identical either way."""
     if num_warmup == 0:
         raise ZeroDivisionError("division by zero")   # nuts.py:322-323
     if compat not in ("reference", "correct"):
@@ -105,7 +110,7 @@ def nuts(
     sched = _cabi.SCHED_SYNC if schedule == "sync" else _cabi.SCHED_ASYNC
     cmode = _cabi.COMPAT_REFERENCE if compat == "reference" else _cabi.COMPAT_CORRECT
     seed = philox_seed(key, 0)
-    model, st = prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, model, theta0, cache, transforms)
+    model, st = prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, model, theta0, cache, transforms, jit)
     st.da_state[:, 0] = 0.0                                           # H_bar
     st.da_state[:, 1] = 1.0                                           # eps_bar
     st.da_state[:, 2] = float(np.log(np.float32(10.0 * step_size)))   # mu, a float32 in the reference

@@ -316,23 +316,33 @@ def test_compact_and_general_pointwise_paths_agree_bit_for_bit(cuda, name):
     import mlx_mcmc_b200.core as mx
     from mlx_mcmc_b200.engine import compile_model
     fn, init, _ = W.ALL_SMALL[name](B.ns)
+    from mlx_mcmc_b200 import jit as J
     fast = compile_model(fn, init, cache=False)
     slow = compile_model(fn, init, cache=False, pointwise_path="general")
+    spec = compile_model(fn, init, cache=False)
+    assert J.specialize(spec, True) and spec.jit and spec.lib.b2m_model_has_module(spec.handle) == 1
     rng = np.random.default_rng(5)
     theta = fast.pack(init, 257) + torch.from_numpy(0.3 * rng.standard_normal((257, fast.D)).astype(np.float32)).cuda()
     for lanes in (1, 4):
         a, ga = fast.logp_grad(theta, lanes=lanes)
-        b, gb = slow.logp_grad(theta, lanes=lanes)
-        assert torch.equal(a, b) or torch.equal(torch.nan_to_num(a, nan=7.0), torch.nan_to_num(b, nan=7.0))
-        assert torch.equal(torch.nan_to_num(ga, nan=7.0), torch.nan_to_num(gb, nan=7.0))
+        for other in (slow, spec):      # general interpreter path; NVRTC-specialised kernels
+            b, gb = other.logp_grad(theta, lanes=lanes)
+            assert torch.equal(a, b) or torch.equal(torch.nan_to_num(a, nan=7.0), torch.nan_to_num(b, nan=7.0))
+            assert torch.equal(torch.nan_to_num(ga, nan=7.0), torch.nan_to_num(gb, nan=7.0))
     kw = dict(num_samples=40, num_warmup=30, num_chains=96, key=mx.random.key(3))
     if name != "t_vector_normal":           # hmc stores scalar parameters only in the reference; ours handles both
         sa, ra = B.hmc(fn, init, model=fast, **kw)
-        sb, rb = B.hmc(fn, init, model=slow, **kw)
-        assert ra == rb and all(np.array_equal(sa[k], sb[k], equal_nan=True) for k in sa)
+        for other in (slow, spec):
+            sb, rb = B.hmc(fn, init, model=other, **kw)
+            assert ra == rb and all(np.array_equal(sa[k], sb[k], equal_nan=True) for k in sa)
+        if name != "c5_ab_test":
+            ma, qa = B.metropolis_hastings(fn, init, num_samples=50, proposal_scale=0.05, num_chains=96, model=fast)
+            mb, qb = B.metropolis_hastings(fn, init, num_samples=50, proposal_scale=0.05, num_chains=96, model=spec)
+            assert qa == qb and all(np.array_equal(ma[k], mb[k], equal_nan=True) for k in ma)
     na, _ = B.nuts(fn, init, model=fast, **kw)
-    nb, _ = B.nuts(fn, init, model=slow, **kw)
-    assert all(np.array_equal(na[k], nb[k], equal_nan=True) for k in na)
+    for other in (slow, spec):
+        nb, _ = B.nuts(fn, init, model=other, **kw)
+        assert all(np.array_equal(na[k], nb[k], equal_nan=True) for k in na)
 
 
 def test_edge_shapes_empty_single_and_one_by_one(cuda):
