@@ -521,6 +521,13 @@ __device__ __forceinline__ void eval_term_c(const b2m_term &T, const SModel &sm,
 }
 
 #ifdef B2M_JIT
+// a constant of the term table whose VALUE the compiler cannot see (control flow on the integer fields still folds):
+// arithmetic on it runs on the device exactly as in the generic kernels, which keeps the two bit-identical
+__device__ __forceinline__ float jit_const(unsigned bits) {
+  float v;
+  asm("mov.b32 %0, %1;" : "=f"(v) : "r"(bits));
+  return v;
+}
 // the generated translation unit defines B2M_JIT_TERMS(F): one F(dist, length, weight, k0, k1, k2, x.kind, x.a, x.b, x.c,
 // p0.kind, p0.a, p0.b, p0.c, p1.kind, p1.a, p1.b, p1.c) per term of the traced model
 #define B2M_JIT_ONE_TERM(DIST, LEN, W, K0, K1, K2, XK, XA, XB, XC, AK, AA, AB, AC, BK, BA, BB, BC)                      \
