@@ -101,6 +101,11 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = lib_path()
+    dbg = os.environ.get("B2M_LIB")       # developer switch: the debug-assert build (python -m mlx_mcmc_b200.build --debug)
+    if dbg:
+        if not os.path.exists(dbg):
+            raise ImportError(f"B2M_LIB={dbg} does not exist")
+        path, build_if_missing = dbg, False
     if build_if_missing and not _build.is_current():
         try:
             _build.build()

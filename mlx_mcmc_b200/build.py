@@ -55,6 +55,31 @@ def is_current() -> bool:
         return f.read().strip() == _fingerprint()
 
 
+def build_debug() -> str:
+    """The same sources with -DB2M_DEBUG_ASSERTS (index / invariant asserts inside the kernels) into
+    csrc/_debug/libb200mcmc.so; selected for a process with B2M_LIB=<path> (tools/debug_asserts_smoke.py)."""
+    nvcc = _nvcc()
+    out_dir = os.path.join(CSRC, "_debug")
+    os.makedirs(out_dir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(out_dir, src.replace(".cu", ".o"))
+        r = subprocess.run([nvcc, *NVCC_FLAGS, "-DB2M_DEBUG_ASSERTS", "-c", os.path.join(CSRC, src), "-o", obj],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(compile_one, _sources()))
+    lib = os.path.join(out_dir, "libb200mcmc.so")
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, "-lcudart", "-ldl"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a and link libb200mcmc.so.  Returns the library path."""
     if not force and is_current():
@@ -100,4 +125,4 @@ def _build_locked(verbose: bool) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_debug() if "--debug" in sys.argv else build(force="--force" in sys.argv, verbose="-v" in sys.argv))

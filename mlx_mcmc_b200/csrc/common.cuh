@@ -18,6 +18,16 @@
 #endif
 #endif
 
+// Index / invariant checks inside the kernels, compiled in by `python -m mlx_mcmc_b200.build --debug` (-DB2M_DEBUG_ASSERTS):
+// compute-sanitizer is closed on the GPU pool, so the debug build carries its own bounds asserts (a failed one traps the
+// kernel and the next CUDA call returns cudaErrorAssert).  tools/debug_asserts_smoke.py runs every path on that build.
+#if defined(B2M_DEBUG_ASSERTS) && !defined(__CUDACC_RTC__)
+#include <assert.h>
+#define B2M_ASSERT(cond) assert(cond)
+#else
+#define B2M_ASSERT(cond) ((void)0)
+#endif
+
 namespace b2m {
 
 #ifndef __CUDACC_RTC__

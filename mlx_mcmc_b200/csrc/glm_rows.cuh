@@ -48,6 +48,7 @@ struct PackP {
 //   |z_n| = |y0_n - (X delta)_n| <= max|y0| + ||delta||_2 max_n ||X_n||_2      (Cauchy-Schwarz)
 __device__ __forceinline__ void pack16_row(const PackP &P, const float *__restrict__ th, int64_t row, int lane) {
   const bool live = th != nullptr;
+  B2M_ASSERT(row >= 0 && P.Dp % 64 == 0 && P.D <= P.Dp && P.beta_off + P.D <= P.Dtot);
   const int *tf = P.tf;
   float amax = 0.f, n2 = 0.f;
   if (live) {
@@ -130,6 +131,7 @@ struct FinishP {
 // of sigma analytically, then the prior terms (generic densities) added on top.
 __device__ __forceinline__ void finish_row(const FinishP &F, const SModel &sm, const float *__restrict__ th, int64_t c,
                                            int64_t c_batch, float *__restrict__ logp_out, float *__restrict__ gr, int lane) {
+  B2M_ASSERT(c >= 0 && c < F.Cp && F.g_splits >= 0 && F.n_tiles >= 1);
   const float *thu = th;                         // unconstrained row (chain rule below)
   if (F.tf) th = F.thc + c_batch * F.Dtot;       // the model's view (c_batch = row of the packed batch)
   const int Dtot = F.Dtot, D = F.D, Dp = F.Dp, beta_off = F.beta_off, sigma_param = F.sigma_param;

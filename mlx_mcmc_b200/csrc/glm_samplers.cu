@@ -547,6 +547,7 @@ __device__ __forceinline__ void nuts_leaf_post_dev(const b2m_nuts_args &A, const
   if (a1 != a1) a1 = ref_compat ? 1.0f : 0.0f;
   a1 = fminf(a1, 1.0f);
   const int v = W.v[c], i = W.leaf[c];
+  B2M_ASSERT(j >= 0 && j < A.max_tree_depth && i >= 0 && i < (1 << j) && (v == 1 || v == -1));
   if (lane == 0) {
     A.n_leaves[c] += 1;
     if (!s1) A.n_diverge[c] += 1;
@@ -797,9 +798,13 @@ static void nuts_layout(Arena &A, NutsBufs &W, int64_t C, int D, int MD) {
 // arithmetic are those of the synchronous kernels (the same device functions), so a chain's draws are the same up to
 // the batch-dependent rounding of the GLM contractions.
 __device__ __forceinline__ void nuts_tick_dev(const b2m_nuts_args &A, const NutsBufs &W, int D, int64_t c, int lane) {
+  B2M_ASSERT(c >= 0 && c < A.n_chains);
   const int st = W.state[c];
+  B2M_ASSERT(st >= 0 && st <= 2);
   if (st == 2) return;
   int it = W.iter[c];
+  B2M_ASSERT(it >= 0 && it < A.n_iter);
+  B2M_ASSERT(W.depth[c] >= 0 && W.depth[c] <= A.max_tree_depth);
   if (st == 0) {
     nuts_begin_dev(A, W, D, c, lane, it);
     __syncwarp();
@@ -912,6 +917,7 @@ __global__ void __launch_bounds__(32 * WPB) nuts_state_kernel(b2m_nuts_args A, N
   if (r < S.n_rows) {
     const int64_t row = S.row_base + r;
     const int64_t c = S.idx ? S.idx[row] : row;
+    B2M_ASSERT(c >= 0 && c < A.n_chains && row >= 0 && (S.peer || row < S.n_pad));
     if (S.do_finish) {
       finish_row(S.F, sm, W.fq + c * D, S.peer ? r : row, row, W.flp + c, W.fg + c * D, lane);
       __syncwarp();

@@ -374,6 +374,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     for (int t = group; t < n_tiles; t += n_groups) {
     B2M_DECODE_TILE(t)
     const int m = m0 + q * 32 + lane;
+    B2M_ASSERT(m >= 0 && (int64_t)m < E.Cp && nkb > 0);
     float acc[CW];
 #pragma unroll
     for (int j = 0; j < CW; ++j) acc[j] = 0.f;
@@ -468,6 +469,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       // scales are undone here (the ranks' scales differ); the owner adds the per-source slots in rank order.
       const int row0 = m0 + q * 32;
       const int owner = row0 / E.push_own;
+      B2M_ASSERT(owner >= 0 && owner < kMaxPeers && E.push_dst[owner] != nullptr && (row0 + 31) / E.push_own == owner);
       float *dst = E.push_dst[owner] + ((int64_t)E.push_rank * E.push_own + (row0 - owner * E.push_own)) * E.Dp + nb;
       const float ru = E.r_unscale ? E.r_unscale[m] : 1.0f;   // lane r: scale of row r of this warp's 32 rows
       float *scratch = scratch_base + (warp - 2) * (32 * 33);

@@ -33,7 +33,50 @@ class MCMC:
         sampler verbatim (mcmc.py:96,122,156,177), so e.g. ``step_size`` with ``method='metropolis'``
         raises TypeError exactly as there.  Extra keyword-only sampler options (``num_chains``,
         ``adapt``, ``compat``, ``return_torch`` ...) ride in ``kwargs`` too."""
-        self._single_chain = int(kwargs.get("num_chains", 1)) == 1
+        # keyword-only extensions for one-process-per-GPU runs under torchrun (the reference is single device):
+        #   device=i          run on cuda:i (default: the current device)
+        #   shard='chains'    this rank runs its block of the `num_chains` global chains; draws of all ranks are gathered
+        #   shard='obs'       GLM-class models: every rank holds a row shard of (X, y) and all chains (dist.py);
+        #                     with slice_state='peer' | 'nccl' the per-chain work is sliced over the ranks too
+        device = kwargs.pop("device", kwargs.pop("devices", None))
+        shard = kwargs.pop("shard", None)
+        if isinstance(device, (list, tuple)):
+            if len(device) != 1:
+                raise ValueError("one process drives one GPU: pass device=i (launch one process per GPU with torchrun)")
+            device = device[0]
+        if device is not None:
+            import torch
+            torch.cuda.set_device(int(device))
+        if shard not in (None, "chains", "obs"):
+            raise ValueError(f"Unknown shard mode: {shard}")
+        gather = None
+        if shard is not None:
+            from .. import dist as D_
+            rank, world = D_.rank_world()
+            total = int(kwargs.get("num_chains", 1))
+            if shard == "chains" and world > 1:
+                count, offset = D_.shard_chains(total, rank, world)
+                if count == 0:
+                    raise ValueError(f"rank {rank} would own no chains (num_chains={total}, world={world})")
+                kwargs["num_chains"], kwargs["chain_offset"] = count, offset
+                gather = (D_, count)
+            elif shard == "obs" and world > 1:
+                peer = total if kwargs.get("slice_state") in (True, "peer") else None
+                kwargs["model"] = D_.compile_obs_sharded(self.log_prob_fn, initial_params, peer_chains=peer)
+        self._single_chain = int(kwargs.get("num_chains", 1)) == 1 and gather is None
+        out = self._run_local(initial_params, num_samples, num_warmup, method, proposal_scale, random_seed, verbose, kwargs)
+        if gather is not None:
+            D_, count = gather
+            local = self.samples if count > 1 else {k: v[None] for k, v in self.samples.items()}
+            self.samples = D_.gather_draws(local, count)
+            import torch
+            dev = torch.device("cuda") if D_.td.get_backend() == "nccl" else None
+            tot = D_.reduce_stats({"acc": self.acceptance_rate * count, "n": count}, "sum", None, dev)
+            self.acceptance_rate = tot["acc"] / max(tot["n"], 1.0)
+            out = self.samples
+        return out
+
+    def _run_local(self, initial_params, num_samples, num_warmup, method, proposal_scale, random_seed, verbose, kwargs):
         if method in ('hmc', 'nuts'):
             if verbose:
                 print(f"\n{_RULE}\nB200-MCMC: {method.upper()} Sampling\n{_RULE}\n")

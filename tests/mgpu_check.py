@@ -42,6 +42,14 @@ def main():
     assert np.array_equal(sharded["rate"], whole["rate"]), "chain-sharded HMC draws differ from the single-GPU run"
     assert abs(rate - rate1) < 1e-12
     report["chains_hmc"] = "bit-equal"
+    # the same through the user-facing call: MCMC.run(..., shard='chains') gathers every rank's draws
+    mc = B.MCMC(fn)
+    got = mc.run(init, num_samples=40, num_warmup=60, method="hmc", step_size=0.1, num_leapfrog_steps=10, random_seed=5,
+                 num_chains=37, shard="chains", verbose=False)
+    ref1 = B.MCMC(fn).run(init, num_samples=40, num_warmup=60, method="hmc", step_size=0.1, num_leapfrog_steps=10,
+                          random_seed=5, num_chains=37, verbose=False)
+    assert got["rate"].shape == (37, 40) and np.array_equal(got["rate"], ref1["rate"]), "MCMC.run(shard='chains') differs"
+    report["mcmc_run_shard_chains"] = "bit-equal"
 
     # ---- 2. observation sharding: value + gradient
     fr, initr, mr = W.regression(B.ns, 6000, 48, seed=2)

@@ -196,6 +196,14 @@ def test_mcmc_errors_before_any_device_work():
         B.nuts(lambda p: B.Normal(0, 1).log_prob(p["x"]), {"x": 0.0}, num_warmup=0)
 
 
+def test_run_extension_keywords_are_validated_before_device_work():
+    m = B.MCMC(lambda p: B.Normal(0, 1).log_prob(p["x"]))
+    with pytest.raises(ValueError, match="shard"):
+        m.run({"x": 0.0}, method="nuts", shard="rows", verbose=False)
+    with pytest.raises(ValueError, match="one process drives one GPU"):
+        m.run({"x": 0.0}, method="nuts", devices=[0, 1], verbose=False)
+
+
 def test_sampler_option_validation_happens_on_the_host():
     fn, init = (lambda p: B.Normal(0, 1).log_prob(p["x"])), {"x": 0.0}
     with pytest.raises(ValueError, match="compat"):
