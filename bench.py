@@ -61,13 +61,17 @@ WORKLOADS = {
 METRIC = "leapfrog_grad_evals_per_sec"
 UNIT = "grad-evals/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-NCU_TRAFFIC = {"c4": {"bytes": 2.25e9 + 4.27e9, "source": "profiles/r01_tc_gemm_c4_v4_f16_ncu_summary.md (K5 0.64 GB read + 1.62 GB "
-                      "written, K6 4.13 GB read + 0.13 GB written)"}}
+NCU_TRAFFIC = {"c4": {"bytes": 0.591e9 + 1.616e9 + 3.966e9 + 0.127e9,
+                      "source": "profiles/r02_tc_gemm_c4_ncu_summary.md (K5 0.59 GB read + 1.62 GB written, K6 3.97 GB read + 0.13 GB "
+                                "written; tensor pipe active 85.1 % / 92.6 % of the elapsed cycles)"}}
 
 
 # issue-side evidence of the pointwise kernels from the committed ncu captures (profiles/): the bound of these paths
-PW_ISSUE = {"c2": {"source": "profiles/r01_hmc_kernel_c2_v2_ncu_summary.md", "issue_slots_busy_pct": 51.0, "warp_occupancy_pct": 20.0,
-                   "waves": 0.43, "registers": 64, "per_evaluation_setup_share_of_instructions": 0.657}}
+PW_ISSUE = {"c2": {"source": "profiles/r02_hmc_kernel_c2_specialised_ncu_summary.md",
+                   "specialised": {"issue_slots_busy_pct": 64.9, "ipc_per_sm": 2.41, "warp_occupancy_pct": 19.2, "waves": 0.49,
+                                   "registers": 72, "thread_instructions_per_grad_eval": 368},
+                   "interpreter": {"issue_slots_busy_pct": 50.1, "ipc_per_sm": 1.93, "warp_occupancy_pct": 20.4, "waves": 0.43,
+                                   "registers": 64, "thread_instructions_per_grad_eval": 625}}}
 
 
 # ----------------------------------------------------------------------------------------- clocks
