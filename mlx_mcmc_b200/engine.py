@@ -258,15 +258,32 @@ _MODEL_CACHE: "Dict[tuple, DeviceModel]" = {}
 _CACHE_SIZE = 4
 
 
+_FULL_FINGERPRINT_BYTES = 64 << 20
+
+
 def _array_fingerprint(a: np.ndarray) -> tuple:
+    """Content fingerprint of an observed array: 64 position-dependent wrapping sums over its 64-bit words (contiguous
+    chunks, one memory-bound pass, no dtype conversion).  Arrays up to 64 MB are summed completely; larger ones (the 400 MB
+    design matrix: a full pass would cost a tenth of a sampler call) through 1024 evenly spaced contiguous runs covering a
+    sixteenth of the words, plus the first and last megabyte and the buffer address -- new data, re-generated data,
+    rescaling and shuffles are all seen, an in-place edit of a handful of elements of a > 64 MB array may not be (pass
+    cache=False, or clear_model_cache(), after such an edit)."""
     b = np.ascontiguousarray(a)
     raw = b.view(np.uint8).reshape(-1)
-    n4 = raw.size // 4
-    words = raw[: n4 * 4].view(np.uint32)
-    # two position-dependent 64-bit sums over the raw words: any single changed element changes the first, a swap of
-    # two elements of different parity changes the second; memory-bound (tens of ms for the 400 MB design matrix)
-    return (b.shape, str(b.dtype), int(words.sum(dtype=np.uint64)), int(words[1::2].sum(dtype=np.uint64)),
-            bytes(raw[n4 * 4:]))
+    n8 = raw.size // 8
+    w = raw[: n8 * 8].view(np.uint64)
+    tail = bytes(raw[n8 * 8:])
+    extra = ()
+    if raw.size > _FULL_FINGERPRINT_BYTES:
+        extra = (int(b.ctypes.data), int(w[: 1 << 17].sum()), int(w[-(1 << 17):].sum()))
+        blk = w.size // 1024
+        runs = w[: blk * 1024].reshape(1024, blk)[:, : max(blk // 16, 1)].sum(axis=1)      # contiguous runs: no strided gather
+        return (b.shape, str(b.dtype), tuple(int(v) for v in runs), extra, tail)
+    if w.size == 0:
+        return (b.shape, str(b.dtype), tail)
+    bounds = np.linspace(0, w.size, 65).astype(np.int64)
+    sums = tuple(int(w[bounds[i]:bounds[i + 1]].sum()) for i in range(64))
+    return (b.shape, str(b.dtype), sums, extra, tail)
 
 
 def _trace_fingerprint(traced: TracedModel, extra: tuple) -> tuple:
