@@ -334,9 +334,7 @@ struct NutsBufs {
   int *fin;         // [C] finished an iteration in the current tick (pooled adaptation)
   int *live;        // [C] state != 2 (input of the compaction)
   int *n_done;      // device counter of finished chains
-  double *pool;     // [4] pooled adaptation: spare, spare, next iteration to apply, spare (peer: global finished count)
-  unsigned long long *pool_fx;   // [n_iter] pooled adaptation: sum over chains of alpha of iteration m, fixed point 2^-40
-  int *pool_cnt;                 // [n_iter] chains that have reported iteration m
+  double *pool;     // [4] pooled adaptation: sum of alpha, count, update index, spare
   const int *tf;    // constraint transforms of the model (draws are written constrained) or nullptr
 };
 
@@ -672,15 +670,7 @@ __device__ __forceinline__ void nuts_end_dev(const b2m_nuts_args &A, const NutsB
     W.lp[c] = W.clp[c];
     const double mean_alpha = W.alpha_sum[c] / fmax((double)W.alpha_cnt[c], 1.0);
     A.n_accept[c] += mean_alpha > 0.5 ? 1 : 0;
-    if (A.adapt == B2M_ADAPT_POOLED) {
-      W.alpha_it[c] = (float)mean_alpha;
-      if (W.pool_fx) {   // asynchronous schedules pool BY ITERATION: integer adds commute, so the sum does not depend on timing
-        const double a = (mean_alpha == mean_alpha) ? fmin(fmax(mean_alpha, 0.0), 1.0) : 0.0;
-        atomicAdd(&W.pool_fx[it], (unsigned long long)llrint(a * 1099511627776.0));
-        __threadfence();
-        atomicAdd(&W.pool_cnt[it], 1);
-      }
-    }
+    if (A.adapt == B2M_ADAPT_POOLED) W.alpha_it[c] = (float)mean_alpha;
     if (A.adapt == B2M_ADAPT_DUAL_AVERAGING) {
       double h_bar = A.da_state[c * 3 + 0], eps_bar = A.da_state[c * 3 + 1];
       const float mu = (float)A.da_state[c * 3 + 2];
@@ -774,7 +764,7 @@ __global__ void __launch_bounds__(1024) nuts_pool_adapt_kernel(b2m_nuts_args A, 
 }
 
 // carve the NUTS workspace (both schedules) out of the model's arena
-static void nuts_layout(Arena &A, NutsBufs &W, int64_t C, int D, int MD, int n_iter = 0) {
+static void nuts_layout(Arena &A, NutsBufs &W, int64_t C, int D, int MD) {
   const size_t cd = (size_t)C * D;
   float **vecs[] = {&W.g, &W.p0, &W.q_lo, &W.p_lo, &W.g_lo, &W.q_hi, &W.p_hi, &W.g_hi, &W.cq, &W.cg,
                     &W.fq, &W.fp, &W.fg, &W.sfq, &W.sfp, &W.scq, &W.scg};
@@ -795,7 +785,6 @@ static void nuts_layout(Arena &A, NutsBufs &W, int64_t C, int D, int MD, int n_i
   A.take(&W.state, C); A.take(&W.iter, C); A.take(&W.fin, C); A.take(&W.live, C);
   A.take(&W.n_done, 1);
   A.take(&W.pool, 4);
-  if (n_iter > 0) { A.take(&W.pool_fx, (size_t)n_iter); A.take(&W.pool_cnt, (size_t)n_iter); }
 }
 
 // ================================================================= NUTS, iteration-asynchronous lock-step
@@ -1031,37 +1020,55 @@ __global__ void __launch_bounds__(128) obs_signal_kernel(const float *__restrict
   if ((int)threadIdx.x < Q.nranks) st_release_sys(Q.gflag_peer[threadIdx.x], seq);
 }
 
+// Pooled dual averaging under the asynchronous schedule: acceptance statistics of the transitions that finished in
+// this tick are added (fixed order) to a pool; every n_chains completed transitions -- one per chain on average -- the
+// recurrences of nuts.py:298-310 advance once on the pool's mean and every chain gets the new step size for its next
+// transition.  `flush` applies what is left at the end of the call.
 __global__ void set_i64_kernel(long long *dst, const int *src) { *dst = (long long)*src; }
 
 __global__ void __launch_bounds__(1024) nuts_pool_async_kernel(b2m_nuts_args A, NutsBufs W, int flush) {
-  // Pooled dual averaging under the asynchronous schedules, pooled BY ITERATION: update m of the recurrences of
-  // nuts.py:298-310 is applied once all n_chains chains have reported the acceptance statistic of their iteration m
-  // (fixed-point sums accumulated by nuts_end_dev), on its mean -- the same sequence of updates as the synchronous
-  // schedule, whatever the tick timing; every chain receives the new step size for the transitions it starts afterwards.
-  (void)flush;
+  __shared__ double rs[1024];
+  __shared__ int rc[1024];
   __shared__ double eps_sh, hbar_sh, ebar_sh;
   __shared__ int updated;
   const int64_t C = A.n_chains;
+  double s = 0.0;
+  int n = 0;
+  for (int64_t c = threadIdx.x; c < C; c += 1024)
+    if (W.fin[c]) {
+      const float a = W.alpha_it[c];
+      s += (a == a) ? (double)a : 0.0;
+      ++n;
+      W.fin[c] = 0;
+    }
+  rs[threadIdx.x] = s;
+  rc[threadIdx.x] = n;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { rs[threadIdx.x] += rs[threadIdx.x + o]; rc[threadIdx.x] += rc[threadIdx.x + o]; }
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     updated = 0;
-    int m = (int)W.pool[2];
-    double h_bar = A.da_state[0], eps_bar = A.da_state[1], eps = A.step_size[0];
-    const float mu = (float)A.da_state[2];
-    while (m < A.n_iter && *reinterpret_cast<volatile int *>(&W.pool_cnt[m]) == (int)C) {
-      __threadfence();
-      const double mean_alpha = (double)W.pool_fx[m] / 1099511627776.0 / (double)C;
-      const double it = (double)((int64_t)(uint32_t)(A.iter_offset + m) - A.adapt_origin), eta = 1.0 / (it + 10.0);
+    double sum = W.pool[0] + rs[0], cnt = W.pool[1] + (double)rc[0];
+    if (cnt >= (double)C || (flush && cnt > 0.0)) {
+      const double mean_alpha = sum / cnt;
+      double h_bar = A.da_state[0], eps_bar = A.da_state[1];
+      const float mu = (float)A.da_state[2];
+      const double m = (double)((int64_t)(uint32_t)A.iter_offset - A.adapt_origin) + W.pool[2], eta = 1.0 / (m + 10.0);
       h_bar = (1.0 - eta) * h_bar + eta * (A.target_accept - mean_alpha);
-      float log_eps = __fsub_rn(mu, (float)((sqrt(it + 1.0) / 0.05) * h_bar));
+      float log_eps = __fsub_rn(mu, (float)((sqrt(m + 1.0) / 0.05) * h_bar));
       log_eps = fmaxf(fminf(log_eps, 10.0f), -10.0f);
-      eps = (double)expf(log_eps);
-      const double wgt = pow(it + 1.0, -0.75);
+      const double eps = (double)expf(log_eps);
+      const double wgt = pow(m + 1.0, -0.75);
       eps_bar = (double)expf((float)(wgt * log(eps) + (1.0 - wgt) * log(eps_bar)));
+      eps_sh = eps; hbar_sh = h_bar; ebar_sh = eps_bar;
+      W.pool[2] += 1.0;
+      sum = 0.0; cnt = 0.0;
       updated = 1;
-      ++m;
     }
-    W.pool[2] = (double)m;
-    eps_sh = eps; hbar_sh = h_bar; ebar_sh = eps_bar;
+    W.pool[0] = sum;
+    W.pool[1] = cnt;
   }
   __syncthreads();
   if (updated)
@@ -1076,18 +1083,13 @@ int glm_nuts_run_async(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   const int64_t C = a.n_chains;
   const int D = gm.Dtot, MD = a.max_tree_depth;
   NutsBufs W{};
-  const int n_pool = a.adapt == B2M_ADAPT_POOLED ? a.n_iter : 0;
   Arena probe;
-  nuts_layout(probe, W, C, D, MD, n_pool);
+  nuts_layout(probe, W, C, D, MD);
   if (int rc0 = arena_reserve(gm, probe.off)) return rc0;
   Arena real;
   real.base = gm.ws;
-  nuts_layout(real, W, C, D, MD, n_pool);
+  nuts_layout(real, W, C, D, MD);
   W.tf = gm.tf;
-  if (n_pool) {
-    B2M_CHECK_CUDA(cudaMemsetAsync(W.pool_fx, 0, sizeof(unsigned long long) * n_pool, st));
-    B2M_CHECK_CUDA(cudaMemsetAsync(W.pool_cnt, 0, sizeof(int) * n_pool, st));
-  }
 
   const int T = 32 * WPB;
   B2M_CHECK_CUDA(cudaMemsetAsync(W.state, 0, sizeof(int) * C, st));
@@ -1251,18 +1253,13 @@ int glm_nuts_run_fused(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     B2M_REQUIRE(a.inj_normal == nullptr && a.trace_doubling == nullptr, "slice_state = PEER: draw injection is not supported");
   }
   NutsBufs W{};
-  const int n_pool = a.adapt == B2M_ADAPT_POOLED ? a.n_iter : 0;
   Arena probe;
-  nuts_layout(probe, W, C, D, MD, n_pool);
+  nuts_layout(probe, W, C, D, MD);
   if (int rc0 = arena_reserve(gm, probe.off)) return rc0;
   Arena real;
   real.base = gm.ws;
-  nuts_layout(real, W, C, D, MD, n_pool);
+  nuts_layout(real, W, C, D, MD);
   W.tf = gm.tf;
-  if (n_pool) {
-    B2M_CHECK_CUDA(cudaMemsetAsync(W.pool_fx, 0, sizeof(unsigned long long) * n_pool, st));
-    B2M_CHECK_CUDA(cudaMemsetAsync(W.pool_cnt, 0, sizeof(int) * n_pool, st));
-  }
   if (!gm.blk_counter) {
     B2M_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(&gm.blk_counter), sizeof(unsigned) * 8));
     B2M_CHECK_CUDA(cudaMemset(gm.blk_counter, 0, sizeof(unsigned) * 8));
