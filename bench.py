@@ -448,13 +448,14 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
     leaves0 = int(st.n_leaves.sum().item())
     n0 = lib.b2m_launch_count()
     import ctypes
-    four = (ctypes.c_double * 4)()
-    lib.b2m_profile(1)          # CUDA events around every GEMM launch of the timed region, on the launching stream
+    ten = (ctypes.c_double * 10)()
+    lib.b2m_profile(1)          # CUDA events around every GEMM / state-kernel launch of the timed region, on the launching stream
     barrier()
     timed.run(one_step)
     barrier()
-    lib.b2m_profile_read(four)
+    lib.b2m_profile_read_ex(ten)
     lib.b2m_profile(0)
+    four = list(ten)[:4]
     launches = lib.b2m_launch_count() - n0
     leaves = int(st.n_leaves.sum().item()) - leaves0
     total_ms = timed.total_ms()
@@ -503,7 +504,8 @@ def bench_glm(torch, dist, B, lib, args, wl, wl_name, rank, world, local_rank, f
 
     out["roofline"] = glm_roofline(torch, four, leaves, N, D, C, total_ms, model, wl_name)
     both = out["roofline"]["avg_launch_ms"]["K5"] + out["roofline"]["avg_launch_ms"]["K6"]
-    out["issue"] = {"grad_evals_per_s_per_gpu": value / world, "lockstep_eval_ms": both, "nuts_step_ms": total_ms / args.steps}
+    out["issue"] = {"grad_evals_per_s_per_gpu": value / world, "lockstep_eval_ms": both, "nuts_step_ms": total_ms / args.steps,
+                    "state_kernel_ms_avg": ten[4] / max(ten[5], 1), "state_kernel_launches": int(ten[5])}
 
     log("roofline pass done")
     if full and not args.no_ess:
@@ -603,13 +605,14 @@ def bench_glm_strong(torch, dist, B, lib, args, wl, wl_name, rank, world, local_
     clocks.start()
     l0 = leaves_all()
     n0 = lib.b2m_launch_count()
-    four = (ctypes.c_double * 4)()
+    ten = (ctypes.c_double * 10)()
     lib.b2m_profile(1)
     barrier()
     timed.run(lambda: step(_cabi.SLICE_PEER))
     barrier()
-    lib.b2m_profile_read(four)
+    lib.b2m_profile_read_ex(ten)
     lib.b2m_profile(0)
+    four = list(ten)[:4]
     launches = lib.b2m_launch_count() - n0
     dl = leaves_all() - l0
     total_ms = timed.total_ms()
@@ -680,7 +683,11 @@ def bench_glm_strong(torch, dist, B, lib, args, wl, wl_name, rank, world, local_
     both = out["roofline"]["avg_launch_ms"]["K5"] + out["roofline"]["avg_launch_ms"]["K6"]
     ticks = out["roofline"]["launches_timed"] / 2 / args.steps
     out["issue"] = {"lockstep_eval_ms_gemms": both, "tick_ms": total_ms / args.steps / max(ticks, 1), "ticks_per_step": ticks,
-                    "non_gemm_ms_per_tick": total_ms / args.steps / max(ticks, 1) - both}
+                    "non_gemm_ms_per_tick": total_ms / args.steps / max(ticks, 1) - both,
+                    "state_kernel_ms_avg": ten[4] / max(ten[5], 1), "wait_kernel_ms_avg": ten[6] / max(ten[7], 1),
+                    "signal_kernel_ms_avg": ten[8] / max(ten[9], 1),
+                    "note": "rank 0, CUDA events around every launch: the state kernel's time includes its wait for the other ranks' "
+                            "gradient partials, the wait kernel's its wait for their packed rows (rank skew shows up there)"}
     return out
 
 

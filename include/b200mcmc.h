@@ -334,6 +334,9 @@ int b2m_diag_params(const float *mean, const float *var, const float *ess_ref, c
  * returns {K5 total ms, K5 launches, K6 total ms, K6 launches}. */
 int b2m_profile(int32_t enable);
 int b2m_profile_read(double *out4);
+/* the same plus the per-chain kernels of the fused NUTS loop: {total ms, launches} x {K5, K6, state kernel, peer wait kernel
+ * (includes waiting for the slowest rank's rows), peer signal kernel} */
+int b2m_profile_read_ex(double *out10);
 
 /* number of kernel launches this library has issued since load (bench.py's gpu_launches) */
 int64_t b2m_launch_count(void);

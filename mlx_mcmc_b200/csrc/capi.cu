@@ -194,6 +194,11 @@ int b2m_profile_read(double *out4) {
   return b2m::tc_profile_read(out4);
 }
 
+int b2m_profile_read_ex(double *out10) {
+  B2M_REQUIRE(out10 != nullptr, "b2m_profile_read_ex: NULL argument");
+  return b2m::tc_profile_read_n(out10, 5);
+}
+
 int b2m_struct_sizes(int32_t *out6) {
   out6[0] = (int32_t)sizeof(b2m_term);
   out6[1] = (int32_t)sizeof(b2m_operand);

@@ -140,6 +140,8 @@ int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st);
 bool tc_available();
 void tc_profile(bool enable);
 int tc_profile_read(double *out4);
+int tc_profile_read_n(double *out, int n_kinds);
+void prof_mark(int kind, cudaStream_t st);   // kinds 2 state, 3 peer wait, 4 peer signal: call before and after the launch
 int grad_splits(const GlmModel &g, int64_t Cp);
 
 int tc_gemm_grad_push(GlmModel &g, int64_t Cp, cudaStream_t st);   // K6 whose epilogue stores into the owners' windows

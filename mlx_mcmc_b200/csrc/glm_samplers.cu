@@ -1346,7 +1346,9 @@ int glm_nuts_run_fused(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
   };
   auto launch_state = [&](const StateP &S) {
     const unsigned grid = (unsigned)((S.n_pad + WPB - 1) / WPB);
+    prof_mark(2, st);
     nuts_state_kernel<<<grid, T, finish_smem(gm), st>>>(a, W, D, gm.prior, S);
+    prof_mark(2, st);
     ++g_launches;
   };
   // host side of the progress ring: {tick + 1, finished chains} of tick t lives in slot t % kProgRing
@@ -1403,17 +1405,21 @@ int glm_nuts_run_fused(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     const int64_t Cp = rows <= 128 ? 128 : (rows + 255) / 256 * 256;
     if (peer) {
       char *mine = pw.base[pw.rank];
+      prof_mark(3, st);
       obs_wait_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(
           reinterpret_cast<const unsigned long long *>(mine + pw.off_bflag), pw.nranks, seq,
           reinterpret_cast<int *>(mine + pw.off_err), reinterpret_cast<const float4 *>(mine + pw.off_meta), C, gm.y0max_bits,
           gm.x_rownorm_max, gm.weight, gm.inv_var, gm.a_unscale, gm.r_scale, gm.r_unscale,
           reinterpret_cast<const long long *>(mine + pw.off_done), h_prog, tick);
+      prof_mark(3, st);
       ++g_launches;
     }
     if ((rc = tc_gemm_resid(gm, Cp, st))) break;
     if (peer) {
       if ((rc = tc_gemm_grad_push(gm, Cp, st))) break;
+      prof_mark(4, st);
       obs_signal_kernel<<<(unsigned)((Cp + 127) / 128), 128, 0, st>>>(gm.ss_part, gm.Np / 128, Cp, Q, seq, gm.blk_counter + 1);
+      prof_mark(4, st);
       ++g_launches;
     } else {
       if ((rc = tc_gemm_grad(gm, Cp, st))) break;

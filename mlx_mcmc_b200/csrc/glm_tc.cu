@@ -428,7 +428,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           const float yj = __shfl_sync(0xffffffffu, yv[b], j);
           const float z = yj - (F16 ? acc[b * 32 + j] * a_un : acc[b * 32 + j]);
           ss = fmaf(z, z, ss);
-          scratch[lane * 33 + j] = z * ivw;
+          // F16: the row scale of R is applied here, by the thread that owns the row (same two multiplications, in the
+          // same order, as scaling after the transposition -- without a shuffle and two multiplies per stored pair)
+          scratch[lane * 33 + j] = F16 ? (z * ivw) * rs_lane : z * ivw;
         }
         __syncwarp();
         if (F16) {
@@ -441,8 +443,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           __half2 *rl = reinterpret_cast<__half2 *>(static_cast<__half *>(E.Rl) + off);
 #pragma unroll 8
           for (int r = 0; r < 32; r += 2) {
-            const float sc = __shfl_sync(0xffffffffu, rs_lane, r + hrow);
-            const float v0 = scratch[(r + hrow) * 33 + cl] * sc, v1 = scratch[(r + hrow) * 33 + cl + 1] * sc;
+            const float v0 = scratch[(r + hrow) * 33 + cl], v1 = scratch[(r + hrow) * 33 + cl + 1];
             const __half2 hi = __floats2half2_rn(v0, v1);
             const float2 hf = __half22float2(hi);
             rh[(int64_t)r * (E.Np / 2)] = hi;
@@ -575,7 +576,9 @@ int make_map_uncached(CUtensorMap *map, const void *base, int64_t rows, int64_t 
 // ---------------------------------------------------------------- per-launch timing (bench.py's roofline)
 struct Prof {
   bool on = false;
-  std::vector<cudaEvent_t> ev[2];   // [0] = K5 (residual epilogue), [1] = K6 (split-K gradient): start, stop, start, ...
+  // [0] = K5 (residual epilogue), [1] = K6 (gradient), [2] = NUTS state kernel, [3] = peer wait kernel, [4] = peer signal
+  // kernel: start, stop, start, ...
+  std::vector<cudaEvent_t> ev[5];
 } g_prof;
 
 template <int BLOCK_N, int MODE, int NCTA, bool F16>
@@ -657,6 +660,31 @@ void tc_profile(bool enable) {
     v.clear();
   }
   g_prof.on = enable;
+}
+
+// bracket one launch of kind 2..4 (the per-chain kernels of the fused NUTS loop) with events while profiling is on
+void prof_mark(int kind, cudaStream_t st) {
+  if (!g_prof.on || kind < 0 || kind >= 5) return;
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_prof.ev[kind].push_back(e);
+}
+
+// out = {total ms, launches} per kind, n_kinds of them, since tc_profile(true); synchronises the device
+int tc_profile_read_n(double *out, int n_kinds) {
+  B2M_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < n_kinds && k < 5; ++k) {
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < g_prof.ev[k].size(); i += 2) {
+      float t = 0.f;
+      B2M_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof.ev[k][i], g_prof.ev[k][i + 1]));
+      ms += t;
+    }
+    out[2 * k] = ms;
+    out[2 * k + 1] = (double)(g_prof.ev[k].size() / 2);
+  }
+  return 0;
 }
 
 // out4 = {K5 total ms, K5 launches, K6 total ms, K6 launches} since tc_profile(true); synchronises the device
