@@ -56,6 +56,8 @@ def hmc(
         raise ZeroDivisionError("division by zero")
     if adapt not in ("reference", "dual_averaging"):
         raise ValueError(f"Unknown adapt mode: {adapt}")
+    if adapt_mass_matrix and num_warmup < 20:
+        raise ValueError("adapt_mass_matrix=True needs num_warmup >= 20 (the metric is estimated in warm-up windows)")
     seed = philox_seed(key, 0)
     model, st = prepare(log_prob_fn, initial_params, num_chains, step_size, chain_offset, model, theta0, cache, transforms, jit)
     mode = _cabi.ADAPT_NONE

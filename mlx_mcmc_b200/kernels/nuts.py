@@ -107,6 +107,9 @@ def nuts(
         raise ValueError(f"Unknown schedule: {schedule}")
     if slice_state not in (False, True, "peer", "nccl"):
         raise ValueError(f"Unknown slice_state: {slice_state}")
+    if adapt_mass_matrix and (not adapt_step_size or num_warmup < 20):
+        raise ValueError("adapt_mass_matrix=True needs adapt_step_size=True and num_warmup >= 20 (the metric is estimated in "
+                         "warm-up windows and the step size re-adapted after every update)")
     sched = _cabi.SCHED_SYNC if schedule == "sync" else _cabi.SCHED_ASYNC
     cmode = _cabi.COMPAT_REFERENCE if compat == "reference" else _cabi.COMPAT_CORRECT
     seed = philox_seed(key, 0)
