@@ -529,7 +529,15 @@ def bench_glm_strong(torch, dist, B, lib, args, wl, wl_name, rank, world, local_
     ITERS = wl["iters"]
     if C % (128 * world) or C % 256:
         raise SystemExit(f"--scaling strong needs chains % (128 x ranks) == 0 and % 256 == 0 (got {C} on {world} ranks)")
-    fn, meta, model, st, mode = glm_setup(torch, B, wl, C, 0, seed, obs_sharded=True, peer=True)
+    exchange_note = None
+    try:
+        fn, meta, model, st, mode = glm_setup(torch, B, wl, C, 0, seed, obs_sharded=True, peer=True)
+        SLICE = _cabi.SLICE_PEER
+    except RuntimeError as e:       # the peer window could not be set up on this box (the error is raised on every rank):
+        log(f"peer window unavailable ({e}); timing the NCCL reduce-scatter form instead")      # say so, never silently
+        fn, meta, model, st, mode = glm_setup(torch, B, wl, C, 0, seed, obs_sharded=True, peer=False)
+        SLICE = _cabi.SLICE_NCCL
+        exchange_note = f"peer window unavailable on this box ({e}): NCCL reduce-scatter / all-gather per gradient"
     rows_local = next(int(a_.shape[0]) for a_ in model._arrays if a_.dim() == 2)   # this rank's rows of X
     it0 = [wl["adapt_iters"]]
     draws = torch.zeros((ITERS, C, D), dtype=torch.float32, device="cuda")
@@ -570,7 +578,7 @@ def bench_glm_strong(torch, dist, B, lib, args, wl, wl_name, rank, world, local_
     for t_, s_ in zip((st.theta, st.n_leaves, st.n_accept, st.n_diverge), saved):
         t_.copy_(s_)
     d2 = torch.zeros((1, C, D), device="cuda")
-    launch_nuts(st, 1, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, 10 ** 6, draws=d2, slice_state=_cabi.SLICE_PEER)
+    launch_nuts(st, 1, MD, _cabi.ADAPT_NONE, _cabi.COMPAT_CORRECT, 0.65, seed, 10 ** 6, draws=d2, slice_state=SLICE)
     peer_leaves = (st.n_leaves - saved[1]).sum().double().reshape(1)
     dist.all_reduce(d2)                                     # merge the slices (each rank wrote its own chains' rows)
     dist.all_reduce(peer_leaves)
@@ -599,7 +607,7 @@ def bench_glm_strong(torch, dist, B, lib, args, wl, wl_name, rank, world, local_
     timed = Timed(torch, args.steps)
     for _ in range(warm):
         timed.flush.fill_(1)
-        step(_cabi.SLICE_PEER)
+        step(SLICE)
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -608,7 +616,7 @@ def bench_glm_strong(torch, dist, B, lib, args, wl, wl_name, rank, world, local_
     ten = (ctypes.c_double * 10)()
     lib.b2m_profile(1)
     barrier()
-    timed.run(lambda: step(_cabi.SLICE_PEER))
+    timed.run(lambda: step(SLICE))
     barrier()
     lib.b2m_profile_read_ex(ten)
     lib.b2m_profile(0)
@@ -629,7 +637,7 @@ def bench_glm_strong(torch, dist, B, lib, args, wl, wl_name, rank, world, local_
     def api_call(k):
         return B.nuts(fn, host_init, num_samples=S_e2e, num_warmup=1, step_size=eps_host, max_tree_depth=MD,
                       adapt_step_size=False, key=mx.random.key(100 + k), num_chains=C, compat="correct", return_info=True,
-                      theta0=host_theta, model=model, slice_state="peer")
+                      theta0=host_theta, model=model, slice_state="peer" if SLICE == _cabi.SLICE_PEER else "nccl")
 
     api_call(0)
     barrier()
@@ -674,8 +682,9 @@ def bench_glm_strong(torch, dist, B, lib, args, wl, wl_name, rank, world, local_
            "config_extra": {"chains_total": C, "chains_advanced_per_gpu": C // world, "rows_per_gpu": rows_local,
                             "iters_per_step": ITERS, "mean_tree_depth": mean_depth,
                             "grad_evals_per_step_total": leaves_tot / args.steps, "adapted_step_size_median": eps_host,
-                            "exchange": "peer window: K6 epilogue -> owner's slot (NVLink stores), owner -> all: packed fp16 rows; "
-                                        f"{4 * C * D * (world - 1) / world / 1e6:.1f} MB out per rank per gradient, no NCCL in the loop"}}
+                            "exchange": exchange_note or (
+                                "peer window: K6 epilogue -> owner's slot (NVLink stores), owner -> all: packed fp16 rows; "
+                                f"{4 * C * D * (world - 1) / world / 1e6:.1f} MB out per rank per gradient, no NCCL in the loop")}}
     if rank != 0:
         return out
     out["roofline"] = glm_roofline(torch, four, leaves_tot, rows_local, D, C, total_ms, model, wl_name,

@@ -221,33 +221,54 @@ class PeerWindow:
         self.num_chains = int(num_chains)
         self.own = C.c_void_p()
         self.mapped = {}
-        nbytes = C.c_int64()
-        with torch.cuda.device(model.device):
-            _cabi.check(self.lib.b2m_model_peer_bytes(model.handle, self.num_chains, self.world, C.byref(nbytes)))
-            handle = (C.c_uint8 * 64)()
-            _cabi.check(self.lib.b2m_peer_alloc(nbytes.value, C.byref(self.own), handle))
+        nccl = td.get_backend(group) == "nccl"
+        dev = model.device
+
+        def agree(ok: bool, what: str, err=None):
+            """every rank learns whether the step worked everywhere: a failure is an error on ALL ranks, never a hang"""
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev if nccl else "cpu")
+            td.all_reduce(flag, op=td.ReduceOp.MIN, group=group)
+            if int(flag) == 0:
+                self.close(barrier=False)
+                raise RuntimeError(f"peer window: {what} failed on {'this rank: ' + str(err) if not ok else 'another rank'}")
+
+        nbytes, handle, err = C.c_int64(), (C.c_uint8 * 64)(), None
+        try:
+            with torch.cuda.device(dev):
+                _cabi.check(self.lib.b2m_model_peer_bytes(model.handle, self.num_chains, self.world, C.byref(nbytes)))
+                _cabi.check(self.lib.b2m_peer_alloc(nbytes.value, C.byref(self.own), handle))
+        except Exception as e:      # noqa: BLE001 -- reported on every rank by agree()
+            err = e
+        agree(err is None, "allocating the window / its CUDA IPC handle", err)
         self.bytes = nbytes.value
         mine = torch.tensor(list(handle), dtype=torch.uint8)
-        nccl = td.get_backend(group) == "nccl"
-        carrier = mine.to(model.device) if nccl else mine
+        carrier = mine.to(dev) if nccl else mine
         parts = [torch.zeros_like(carrier) for _ in range(self.world)]
         td.all_gather(parts, carrier, group=group)
         ptrs = (C.c_void_p * self.world)()
-        with torch.cuda.device(model.device):
-            for s in range(self.world):
-                if s == self.rank:
-                    ptrs[s] = self.own.value
-                    continue
-                raw = (C.c_uint8 * 64)(*parts[s].cpu().tolist())
-                p = C.c_void_p()
-                _cabi.check(self.lib.b2m_peer_open(raw, C.byref(p)))
-                self.mapped[s] = p
-                ptrs[s] = p.value
-            td.barrier(group=group)       # every window exists and is zeroed before anybody stores into it
-            _cabi.check(self.lib.b2m_model_peer_attach(model.handle, ptrs, self.world, self.rank, self.num_chains, self.bytes))
+        try:
+            with torch.cuda.device(dev):
+                for s in range(self.world):
+                    if s == self.rank:
+                        ptrs[s] = self.own.value
+                        continue
+                    raw = (C.c_uint8 * 64)(*parts[s].cpu().tolist())
+                    p = C.c_void_p()
+                    _cabi.check(self.lib.b2m_peer_open(raw, C.byref(p)))
+                    self.mapped[s] = p
+                    ptrs[s] = p.value
+        except Exception as e:      # noqa: BLE001
+            err = e
+        agree(err is None, "mapping the peers' windows (CUDA IPC / peer access)", err)    # also: every window exists and is zeroed
+        try:
+            with torch.cuda.device(dev):
+                _cabi.check(self.lib.b2m_model_peer_attach(model.handle, ptrs, self.world, self.rank, self.num_chains, self.bytes))
+        except Exception as e:      # noqa: BLE001
+            err = e
+        agree(err is None, "attaching the window to the model", err)
         model._peer = self
 
-    def close(self):
+    def close(self, barrier: bool = True):
         mapped, self.mapped = self.mapped, {}
         for p in mapped.values():
             try:
@@ -257,7 +278,7 @@ class PeerWindow:
         own, self.own = self.own, C.c_void_p()
         if own:
             try:
-                if td.is_initialized():
+                if barrier and td.is_initialized():
                     td.barrier(group=self.group)     # nobody still maps this window
                 self.lib.b2m_peer_free(own)
             except Exception:
