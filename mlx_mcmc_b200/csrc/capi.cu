@@ -2,6 +2,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -10,7 +11,7 @@
 namespace b2m {
 
 static thread_local std::string tl_error;
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 void set_error(const std::string &msg) { tl_error = msg; }
 
 int pick_lanes(const KModel &km, int64_t n_chains, int requested);
@@ -51,7 +52,15 @@ struct b2m_model {
   b2m::GlmModel glm;           // model_class == 1
   void *dev_prior_terms = nullptr;
   b2m::JitModule *jit = nullptr;   // per-model specialised kernels (b2m_model_attach_module), pointwise class
+  // A handle is NOT re-entrant: GLM-class models keep one workspace arena, one progress ring and one peer window per
+  // handle.  Entry points that use them take this lock without waiting; a second concurrent call on the same handle is an
+  // error (use one handle per thread / stream), never silent corruption.
+  std::mutex busy;
 };
+
+#define B2M_MODEL_GUARD(m)                                                                               \
+  std::unique_lock<std::mutex> _guard((m)->busy, std::try_to_lock);                                      \
+  B2M_REQUIRE(_guard.owns_lock(), "this model handle is in use by another call (handles are not re-entrant: one per thread)")
 
 using b2m::set_error;
 
@@ -151,7 +160,7 @@ extern "C" {
 
 const char *b2m_last_error(void) { return b2m::tl_error.c_str(); }
 int b2m_abi_version(void) { return B2M_ABI_VERSION; }
-int64_t b2m_launch_count(void) { return b2m::g_launches; }
+int64_t b2m_launch_count(void) { return b2m::g_launches.load(); }
 
 // Internal (not part of the public header): C[M,N] = A[M,K] . B[N,K]^T through the 3xTF32 tcgen05 kernel, with the
 // promotion interval and the set of partial products selectable, for accuracy experiments and tests.
@@ -346,6 +355,7 @@ int b2m_logp_grad(b2m_model *m, const float *theta, int64_t n_chains, float *log
   B2M_REQUIRE(m && theta && logp, "b2m_logp_grad: NULL argument");
   B2M_REQUIRE(n_chains > 0, "b2m_logp_grad: n_chains must be positive");
   B2M_REQUIRE(valid_lanes(lanes), "b2m_logp_grad: lanes must be 0 or a power of two <= 32");
+  B2M_MODEL_GUARD(m);
   if (m->model_class == 1)
     return b2m::glm_logp_grad(m->glm, theta, n_chains, logp, grad, static_cast<cudaStream_t>(stream), true);
   return b2m::launch_logp_grad(m->km, theta, n_chains, logp, grad, lanes, static_cast<cudaStream_t>(stream), m->jit);
@@ -442,6 +452,7 @@ int b2m_hmc_run(b2m_model *m, const b2m_hmc_args *a, void *stream) {
   B2M_REQUIRE(a->adapt >= B2M_ADAPT_NONE && a->adapt <= B2M_ADAPT_DUAL_AVERAGING, "b2m_hmc_run: bad adapt mode");
   B2M_REQUIRE(a->adapt != B2M_ADAPT_DUAL_AVERAGING || a->da_state, "b2m_hmc_run: dual averaging needs da_state");
   if (a->n_iter == 0) return 0;
+  B2M_MODEL_GUARD(m);
   if (m->model_class == 1) return b2m::glm_hmc_run(m->glm, *a, static_cast<cudaStream_t>(stream));
   return b2m::launch_hmc(m->km, *a, static_cast<cudaStream_t>(stream), m->jit);
 }
@@ -452,6 +463,7 @@ int b2m_mh_run(b2m_model *m, const b2m_mh_args *a, void *stream) {
   B2M_REQUIRE(a->theta && a->logp && a->n_accept, "b2m_mh_run: NULL state pointer");
   B2M_REQUIRE(valid_lanes(a->lanes), "b2m_mh_run: lanes must be 0 or a power of two <= 32");
   if (a->n_iter == 0) return 0;
+  B2M_MODEL_GUARD(m);
   if (m->model_class == 1) return b2m::glm_mh_run(m->glm, *a, static_cast<cudaStream_t>(stream));
   return b2m::launch_mh(m->km, *a, static_cast<cudaStream_t>(stream), m->jit);
 }
@@ -473,6 +485,7 @@ int b2m_nuts_run(b2m_model *m, const b2m_nuts_args *a, void *stream) {
                                                    a->schedule == B2M_SCHED_ASYNC),
               "b2m_nuts_run: slice_state needs an observation-sharded GLM-class model, the asynchronous schedule and no adaptation");
   if (a->n_iter == 0) return 0;
+  B2M_MODEL_GUARD(m);
   if (m->model_class == 1) return b2m::glm_nuts_run(m->glm, *a, static_cast<cudaStream_t>(stream));
   return b2m::launch_nuts(m->km, *a, static_cast<cudaStream_t>(stream), m->jit);
 }

@@ -3,6 +3,7 @@
 #ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 #endif
 
@@ -33,7 +34,7 @@ namespace b2m {
 #ifndef __CUDACC_RTC__
 // ---------------------------------------------------------------- error plumbing (host)
 void set_error(const std::string &msg);
-extern int64_t g_launches;
+extern std::atomic<int64_t> g_launches;   // kernel launches issued by this library (any thread)
 #endif
 
 #define B2M_CHECK_CUDA(expr)                                                                   \
