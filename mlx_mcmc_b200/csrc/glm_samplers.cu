@@ -879,9 +879,6 @@ struct StateP {
   unsigned long long *bflag_peer[kMaxPeers];  // &bflag[rank] in every rank's window
   long long *done_peer[kMaxPeers];            // &done[rank] in every rank's window
   int *err;                                   // in my window
-  // shared-memory staging of the chain's working vectors (see nuts_state_kernel): byte offset of the staging area
-  // inside the dynamic shared memory, or -1
-  int stage_off;
 };
 
 constexpr int kProgRing = 8;
@@ -921,44 +918,14 @@ __global__ void __launch_bounds__(32 * WPB) nuts_state_kernel(b2m_nuts_args A, N
     const int64_t row = S.row_base + r;
     const int64_t c = S.idx ? S.idx[row] : row;
     B2M_ASSERT(c >= 0 && c < A.n_chains && row >= 0 && (S.peer || row < S.n_pad));
-    if (S.stage_off >= 0 && S.do_tick_pack) {
-      // Staged tick.  A tick is a chain of ~15 DEPENDENT passes over the chain's working vectors (finish writes the
-      // gradient, the leaf's second half kick reads it, the subtree copies read what that wrote, the next half kick, the
-      // pack ...); through global memory every link costs an L2 round trip and the kernel is latency bound (half of a
-      // 79-us tick at 100 coefficients x 1024 chains; 0.09 of 0.63 ms at 8 ranks).  Here the seven vectors a tick works on
-      // -- leaf position / momentum / gradient and the four "subtree being assembled" vectors, which do not outlive the
-      // tick -- live in shared memory: the per-chain device functions run unchanged on pointers into it, the three
-      // persistent vectors are loaded once and written back once.  Same arithmetic, same order.
-      const int Dv = (D + 3) & ~3;
-      float *stg = reinterpret_cast<float *>(smem + S.stage_off) + (size_t)warp * 7 * Dv;
-      const size_t o = (size_t)c * D;
-      NutsBufs V = W;
-      V.fq = stg - o; V.fp = stg + Dv - o; V.fg = stg + 2 * Dv - o;
-      V.sfq = stg + 3 * Dv - o; V.sfp = stg + 4 * Dv - o; V.scq = stg + 5 * Dv - o; V.scg = stg + 6 * Dv - o;
-      vcopy(V.fq + o, W.fq + o, D, lane);
-      vcopy(V.fp + o, W.fp + o, D, lane);
-      if (!S.do_finish) vcopy(V.fg + o, W.fg + o, D, lane);
+    if (S.do_finish) {
+      finish_row(S.F, sm, W.fq + c * D, S.peer ? r : row, row, W.flp + c, W.fg + c * D, lane);
       __syncwarp();
-      if (S.do_finish) {
-        finish_row(S.F, sm, V.fq + o, S.peer ? r : row, row, W.flp + c, V.fg + o, lane);
-        __syncwarp();
-      }
-      nuts_tick_dev(A, V, D, c, lane);
+    }
+    if (S.do_tick_pack) {
+      nuts_tick_dev(A, W, D, c, lane);
       __syncwarp();
-      pack16_row(S.P, V.fq + o, row, lane);
-      vcopy(W.fq + o, V.fq + o, D, lane);
-      vcopy(W.fp + o, V.fp + o, D, lane);
-      vcopy(W.fg + o, V.fg + o, D, lane);
-    } else {
-      if (S.do_finish) {
-        finish_row(S.F, sm, W.fq + c * D, S.peer ? r : row, row, W.flp + c, W.fg + c * D, lane);
-        __syncwarp();
-      }
-      if (S.do_tick_pack) {
-        nuts_tick_dev(A, W, D, c, lane);
-        __syncwarp();
-        pack16_row(S.P, W.fq + c * D, row, lane);
-      }
+      pack16_row(S.P, W.fq + c * D, row, lane);
     }
   } else if (r < S.n_pad && S.do_tick_pack) {
     pack16_row(S.P, nullptr, S.row_base + r, lane);
@@ -1388,28 +1355,10 @@ int glm_nuts_run_fused(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     }
     return S;
   };
-  // shared-memory staging of the tick's working vectors: always when it is small (<= 40 KB per block), and up to the
-  // whole SM when the grid is so small that occupancy cannot hide the latency anyway (one or two blocks per SM)
-  const size_t fin_bytes = (finish_smem(gm) + 15) & ~size_t(15);
-  const size_t stage_bytes = sizeof(float) * 7 * (size_t)((D + 3) & ~3) * WPB;
-  bool attr_set = false;
-  auto launch_state = [&](StateP S) {
+  auto launch_state = [&](const StateP &S) {
     const unsigned grid = (unsigned)((S.n_pad + WPB - 1) / WPB);
-    const bool stage = S.do_tick_pack && (stage_bytes <= 40 * 1024 ||
-                                          (grid <= 148 && fin_bytes + stage_bytes <= 200 * 1024) ||
-                                          (grid <= 296 && 2 * (fin_bytes + stage_bytes) <= 220 * 1024));
-    S.stage_off = stage ? (int)fin_bytes : -1;
-    const size_t smem_bytes = fin_bytes + (stage ? stage_bytes : 0);
-    if (smem_bytes > 48 * 1024 && !attr_set) {
-      if (cudaFuncSetAttribute(nuts_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
-        set_error("NUTS fused schedule: cannot raise the state kernel's shared-memory limit");
-        rc = 2;
-        return;
-      }
-      attr_set = true;
-    }
     prof_mark(2, st);
-    nuts_state_kernel<<<grid, T, smem_bytes, st>>>(a, W, D, gm.prior, S);
+    nuts_state_kernel<<<grid, T, finish_smem(gm), st>>>(a, W, D, gm.prior, S);
     prof_mark(2, st);
     ++g_launches;
   };
