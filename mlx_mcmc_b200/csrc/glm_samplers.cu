@@ -31,8 +31,12 @@ __device__ __forceinline__ void normals4(uint64_t seed, uint64_t gchain, uint32_
 }
 
 // im = diag(M^-1) shared by all chains or nullptr (identity, the reference): p = z sqrt(m_d) ~ N(0, M)
-__device__ inline void fill_momentum(float *p, int D, const float *inj, uint64_t seed, uint64_t gchain, uint32_t giter,
-                                     uint4 w0, int lane, const float *__restrict__ im = nullptr) {
+// (__noinline__ on the vector helpers: the fused state kernel inlined ~35 copies of them into 24,000 instructions =
+// 390 KB of code, and with a handful of warps per SM the kernel was bound by instruction-cache misses -- ncu: "no
+// instruction" was the largest stall reason at the 1024-chain configuration.  They take plain pointers and scalars, so a
+// call costs a few dozen cycles against the ~500-cycle memory round trips they contain.)
+__device__ __noinline__ void fill_momentum(float *p, int D, const float *inj, uint64_t seed, uint64_t gchain, uint32_t giter,
+                                           uint4 w0, int lane, const float *__restrict__ im = nullptr) {
   if (inj) {
     for (int d = lane; d < D; d += 32) p[d] = im ? inj[d] / sqrtf(im[d]) : inj[d];
     return;
@@ -55,7 +59,7 @@ __device__ inline void fill_momentum(float *p, int D, const float *inj, uint64_t
   }
 }
 
-__device__ __forceinline__ float kinetic_w(const float *__restrict__ p, int D, int lane, const float *__restrict__ im = nullptr) {
+__device__ __noinline__ float kinetic_w(const float *__restrict__ p, int D, int lane, const float *__restrict__ im = nullptr) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   int d = lane;
   if (im) {   // 0.5 sum p_d^2 / m_d
@@ -341,7 +345,7 @@ struct NutsBufs {
 // One warp copies a [D] vector.  These kernels are pure HBM streaming with one warp per chain: with a scalar loop each
 // lane has a single 4-byte load in flight and the copy is latency bound (the v1 leaf kernels took 120-200 us for
 // ~300 MB of traffic); 16-byte accesses, four independent loads before the first store, put enough bytes in flight.
-__device__ __forceinline__ void vcopy(float *__restrict__ dst, const float *__restrict__ src, int D, int lane) {
+__device__ __noinline__ void vcopy(float *__restrict__ dst, const float *__restrict__ src, int D, int lane) {
   if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
     const float4 *__restrict__ s4 = reinterpret_cast<const float4 *>(src);
     float4 *__restrict__ d4 = reinterpret_cast<float4 *>(dst);
@@ -373,8 +377,8 @@ __device__ __forceinline__ void vcopy(float *__restrict__ dst, const float *__re
 }
 
 // continue-straight test of nuts.py:119-135 on [D] vectors (warp reduction)
-__device__ __forceinline__ bool straight_w(const float *q_lo, const float *q_hi, const float *p_lo, const float *p_hi,
-                                           int D, int lane) {
+__device__ __noinline__ bool straight_w(const float *q_lo, const float *q_hi, const float *p_lo, const float *p_hi,
+                                        int D, int lane) {
   float a = 0.f, b = 0.f;
 #pragma unroll 4
   for (int d = lane; d < D; d += 32) {
@@ -805,13 +809,10 @@ __device__ __forceinline__ void nuts_tick_dev(const b2m_nuts_args &A, const Nuts
   int it = W.iter[c];
   B2M_ASSERT(it >= 0 && it < A.n_iter);
   B2M_ASSERT(W.depth[c] >= 0 && W.depth[c] <= A.max_tree_depth);
-  if (st == 0) {
-    nuts_begin_dev(A, W, D, c, lane, it);
-    __syncwarp();
-    nuts_doubling_begin_dev(A, W, D, c, lane, it, 0);
-    __syncwarp();
-    if (lane == 0) W.state[c] = 1;
-  } else {
+  // one call site per step of the state machine (each is a few thousand instructions once inlined)
+  bool begin_transition = st == 0;
+  int begin_doubling = -1;                                  // depth of the doubling to start, or -1
+  if (st != 0) {
     const int j = W.depth[c];
     nuts_leaf_post_dev(A, W, D, c, lane, it, j);
     __syncwarp();
@@ -819,7 +820,7 @@ __device__ __forceinline__ void nuts_tick_dev(const b2m_nuts_args &A, const Nuts
       nuts_doubling_end_dev(A, W, D, c, lane, it, j);
       __syncwarp();
       if (W.s[c] && W.depth[c] < A.max_tree_depth) {
-        nuts_doubling_begin_dev(A, W, D, c, lane, it, W.depth[c]);
+        begin_doubling = W.depth[c];
       } else {                                             // the transition is over
         nuts_end_dev(A, W, D, c, lane, it);
         __syncwarp();
@@ -829,14 +830,20 @@ __device__ __forceinline__ void nuts_tick_dev(const b2m_nuts_args &A, const Nuts
           if (lane == 0) { W.state[c] = 2; W.live[c] = 0; atomicAdd(W.n_done, 1); }
           return;
         }
-        nuts_begin_dev(A, W, D, c, lane, it);
-        __syncwarp();
-        nuts_doubling_begin_dev(A, W, D, c, lane, it, 0);
+        begin_transition = true;
       }
-      __syncwarp();
     }
   }
-  __syncwarp();
+  if (begin_transition) {
+    nuts_begin_dev(A, W, D, c, lane, it);
+    __syncwarp();
+    begin_doubling = 0;
+    if (st == 0 && lane == 0) W.state[c] = 1;
+  }
+  if (begin_doubling >= 0) {
+    nuts_doubling_begin_dev(A, W, D, c, lane, it, begin_doubling);
+    __syncwarp();
+  }
   nuts_leaf_pre_dev(A, W, D, c, lane);
 }
 
@@ -904,7 +911,6 @@ __device__ __forceinline__ void spin_until(const unsigned long long *flag, unsig
 
 __global__ void __launch_bounds__(32 * WPB) nuts_state_kernel(b2m_nuts_args A, NutsBufs W, int D, KModel prior, StateP S) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ int last_block;
   SModel sm;
   sm.n_terms = 0;
   if (S.do_finish && S.F.has_prior) model_to_smem(prior, smem, sm);
@@ -931,25 +937,27 @@ __global__ void __launch_bounds__(32 * WPB) nuts_state_kernel(b2m_nuts_args A, N
     pack16_row(S.P, nullptr, S.row_base + r, lane);
   }
   if (!S.do_tick_pack) return;
-  // the last block to get here publishes the tick
+  // the last WARP to get here publishes the tick (no block-wide barrier: a warp whose chain closes a transition must
+  // not hold up its three neighbours -- barrier stalls were as large as the memory stalls at 1024 chains)
   if (S.peer) __threadfence_system(); else __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  __syncwarp();
+  int last_warp = 0;
+  if (lane == 0) {
     const unsigned prev = atomicAdd(S.blk_counter, 1u);
-    last_block = prev == gridDim.x - 1;
-    if (last_block) *S.blk_counter = 0;
+    last_warp = prev == gridDim.x * WPB - 1;
+    if (last_warp) *S.blk_counter = 0;
   }
-  __syncthreads();
-  if (!last_block) return;
+  last_warp = __shfl_sync(0xffffffffu, last_warp, 0);
+  if (!last_warp) return;
   __threadfence();
   const long long n_done = *reinterpret_cast<volatile int *>(W.n_done);
   if (S.peer) {
-    if ((int)threadIdx.x < S.nranks) {
-      *reinterpret_cast<volatile long long *>(S.done_peer[threadIdx.x]) = n_done;
+    if (lane < S.nranks) {
+      *reinterpret_cast<volatile long long *>(S.done_peer[lane]) = n_done;
       __threadfence_system();
-      st_release_sys(S.bflag_peer[threadIdx.x], S.seq);
+      st_release_sys(S.bflag_peer[lane], S.seq);
     }
-  } else if (threadIdx.x == 0 && S.h_prog) {
+  } else if (lane == 0 && S.h_prog) {
     volatile long long *slot = S.h_prog + 2 * (S.tick % kProgRing);
     slot[1] = n_done;
     __threadfence_system();
