@@ -390,3 +390,27 @@ def test_peer_window_layout_is_what_the_header_documents():
     assert lib.b2m_model_peer_bytes(None, 4096, 8, ctypes.byref(n)) != 0
     assert b"NULL" in lib.b2m_last_error()
     assert lib.b2m_options_size() == ctypes.sizeof(_cabi.ModelOptions)
+
+
+def test_specialised_kernels_compile_with_nvrtc_on_the_cpu_box():
+    """mlx_mcmc_b200/jit.py: the translation unit generated for a traced model compiles with NVRTC for sm_100a (no GPU
+    needed to compile) and exports the four entry points b2m_model_attach_module looks up; ineligible models are refused."""
+    from mlx_mcmc_b200 import jit as J
+    if not J.available():
+        pytest.skip("cuda-python / NVRTC not importable here")
+    fn, init, _ = W.c2_event_rate(B.ns)
+    tr = B.trace(fn, init)
+    assert J.eligible(tr) and J.dmax_for(tr.D) == 2
+    src = J.generate_source(tr, tr.transform_codes())
+    assert "#define B2M_JIT_HAS_TF 1" in src and src.count("  F(") == len(tr.terms)
+    assert "jit_const(0x" in src                      # constants travel as opaque bit patterns (bit-identity with the interpreter)
+    cubin = J.compile_cubin(src)
+    assert cubin[:4] == b"\x7fELF" and len(cubin) > 10000
+    for name in (b"b2m_jit_logp_grad", b"b2m_jit_hmc", b"b2m_jit_mh", b"b2m_jit_nuts"):
+        assert name in cubin
+    assert J.compile_cubin(src) is cubin              # memory cache
+    fr, ir, _ = W.t_regression_small(B.ns)
+    assert not J.eligible(B.trace(fr, ir))            # GLM class: the tensor-core path, not these kernels
+    affine = B.trace(lambda p: mx.sum(B.Normal(p["a"] + p["b"] * mx.array(np.arange(4.0)), 1.0).log_prob(mx.array(np.ones(4)))),
+                     {"a": 0.0, "b": 0.0})
+    assert not J.eligible(affine)                     # affine operands keep the interpreter kernels
