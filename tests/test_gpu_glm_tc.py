@@ -1,6 +1,7 @@
 """GPU: the tcgen05 contractions (K5/K6) in both operand encodings -- 3xTF32 ("tc") and 3xFP16 with power-of-two
 operand scaling ("tc16", the default when the data's dynamic range allows it) -- against float64 and against the
 fp32 SIMT path."""
+import ctypes
 import math
 import os
 
@@ -9,6 +10,7 @@ import pytest
 import torch
 
 import mlx_mcmc_b200 as B
+from mlx_mcmc_b200 import _cabi
 from mlx_mcmc_b200 import workloads as W
 from mlx_mcmc_b200.engine import compile_model
 
@@ -174,3 +176,70 @@ def test_fp16_encoding_handles_column_scales_and_falls_back_on_outliers(cuda):
     assert wide.glm_path == "tc"
     lp2, g2 = wide.logp_grad(torch.from_numpy(theta).cuda())
     assert torch.isfinite(lp2).all() and torch.isfinite(g2).all()
+
+
+# ------------------------------------------------------------------------------------------------ concurrent K5 || K6 launch
+def _knob(name, value):
+    assert _cabi.load().b2m_tuning_set(name.encode(), int(value)) == 0
+
+
+@pytest.mark.parametrize("n,d,c,slab,ring", [(30000, 256, 512, 2, 3), (50000, 500, 1024, 3, 2), (26000, 200, 300, 1, 4)])
+def test_concurrent_launch_matches_separate_launches_and_float64(cuda, n, d, c, slab, ring):
+    """tc_gemm_fused_kernel (half of the CTA pairs run K5, the other half K6 a slab behind, residuals in an L2 ring)
+    against the two separate launches of the same arithmetic and against float64; repeatable bit for bit.  The slab
+    partials are added in slab order instead of register promotion + split-K, so the two agree to float32 rounding."""
+    tc, meta = _model("tc16", n, d, seed=n + d)
+    rng = np.random.default_rng(2)
+    theta = (meta.beta_true[None, :] + 0.1 * rng.standard_normal((c, d))).astype(np.float32)
+    t = torch.from_numpy(theta).cuda()
+    lp64, g64 = _float64(meta, theta)
+    try:
+        _knob("fuse", 0)
+        lp_s, g_s = tc.logp_grad(t)
+        _knob("fuse", 2); _knob("fuse_slab", slab); _knob("fuse_ring", ring)
+        lib, four = _cabi.load(), (ctypes.c_double * 4)()
+        lib.b2m_profile(1)
+        lp_f, g_f = tc.logp_grad(t)
+        lp_f2, g_f2 = tc.logp_grad(t)
+        lib.b2m_profile_read(four)
+        lib.b2m_profile(0)
+        assert four[1] == 2 and four[3] == 0            # two launches, each covering K5 and K6 (no separate K6 launch)
+    finally:
+        _knob("fuse", 0); _knob("fuse_slab", 0); _knob("fuse_ring", 0)
+    assert torch.equal(lp_f, lp_f2) and torch.equal(g_f, g_f2)
+    gs = float(np.max(np.abs(g64)))
+    assert torch.equal(lp_f, lp_s)                       # K5 is the same arithmetic in both launch shapes
+    assert float((g_f - g_s).abs().max()) / gs < 2e-6
+    for lp, g in ((lp_f, g_f), (lp_s, g_s)):
+        assert np.max(np.abs(lp.cpu().numpy() - lp64) / np.abs(lp64)) < 1e-5
+        assert np.max(np.abs(g.cpu().numpy() - g64)) / gs < 1e-5
+    print(f"n={n} d={d} c={c}: fused vs separate {float((g_f - g_s).abs().max()) / gs:.2e}, "
+          f"fused vs float64 {np.max(np.abs(g_f.cpu().numpy() - g64)) / gs:.2e}")
+
+
+def test_c4_full_batch_concurrent_launch_within_1e5_of_float64(c4):
+    """The shape the concurrent launch exists for (B2M_TC_FUSE=1): all 4096 chains of BASELINE.json's Target configuration
+    (residual operand 1.6 GB).  Against float64 on the device and against the separate launches."""
+    model, meta, X64, y64 = c4
+    if model.glm_path != "tc16":
+        pytest.skip("the concurrent launch exists for the fp16 encoding")
+    gen = torch.Generator(device="cuda").manual_seed(13)
+    base = torch.from_numpy(meta.beta_true).cuda()[None, :]
+    theta = (base + 0.003 * torch.randn(4096, 1000, device="cuda", generator=gen)).contiguous()
+    lp_s, g_s = model.logp_grad(theta)                  # default: two launches
+    try:
+        _knob("fuse", 1)                                # the concurrent launch, chosen for shapes of this size
+        lp, g = model.logp_grad(theta)
+        lp2, g2 = model.logp_grad(theta)
+    finally:
+        _knob("fuse", 0)
+    assert torch.equal(lp, lp2) and torch.equal(g, g2) and torch.equal(lp, lp_s)
+    e_lp = e_g = e_chain = 0.0
+    for i in range(0, 4096, 1024):                      # float64 arbiter in four slices (3.3 GB of residuals each)
+        lp64, g64 = _float64_gpu(X64, y64, theta[i:i + 1024])
+        e_lp = max(e_lp, float(((lp[i:i + 1024].double() - lp64).abs() / lp64.abs()).max()))
+        e_g = max(e_g, float((g[i:i + 1024].double() - g64).abs().max() / g64.abs().max()))
+        e_chain = max(e_chain, float(((g[i:i + 1024].double() - g64).abs().amax(1) / g64.abs().amax(1)).max()))
+    d_sep = float((g - g_s).abs().max() / g_s.abs().max())
+    print(f"C4 4096 chains, concurrent launch: logp {e_lp:.2e} grad {e_g:.2e} per-chain {e_chain:.2e}; vs separate {d_sep:.2e}")
+    assert e_lp < 1e-5 and e_g < 1e-5 and e_chain < 1e-5 and d_sep < 2e-6

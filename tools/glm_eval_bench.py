@@ -17,7 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=100000)
 ap.add_argument("--d", type=int, default=1000)
 ap.add_argument("--chains", type=int, default=4096)
-ap.add_argument("--path", default="tc")
+ap.add_argument("--path", default="auto")
 ap.add_argument("--check", type=int, default=64)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--spread", type=float, default=0.01)
@@ -52,8 +52,22 @@ for _ in range(args.reps):
     torch.cuda.synchronize()
     times.append(a.elapsed_time(b))
 ms = float(np.median(times))
+# GEMM-only time of the same calls: CUDA events inside the library around every K5 / K6 launch (one entry when the two run
+# as the concurrent launch)
+import ctypes
+from mlx_mcmc_b200 import _cabi
+lib = _cabi.load()
+four = (ctypes.c_double * 4)()
+lib.b2m_profile(1)
+for _ in range(args.reps):
+    lp, g = model.logp_grad(t)
+lib.b2m_profile_read(four)
+lib.b2m_profile(0)
+k5 = four[0] / max(four[1], 1)
+k6 = four[2] / max(four[3], 1)
 flops = 4.0 * args.n * args.d * args.chains
-out = {"where": args.where, "n": args.n, "d": args.d, "chains": args.chains, "path": args.path, "ms_per_eval": ms, "all_ms": times,
+out = {"glm_path": model.glm_path, "gemm_ms": {"K5": k5, "K6": k6, "both": k5 + k6, "fused": four[3] == 0},
+       "knobs": {k: v for k, v in os.environ.items() if k.startswith("B2M_TC_")}, "where": args.where, "n": args.n, "d": args.d, "chains": args.chains, "path": args.path, "ms_per_eval": ms, "all_ms": times,
        "useful_tflops": flops / ms / 1e9, "grad_evals_per_s": args.chains / ms * 1e3,
        "logical_GBps": 4.0 * args.n * args.d * args.chains / ms / 1e6}
 if args.check:
