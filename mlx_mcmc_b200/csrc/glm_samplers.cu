@@ -909,7 +909,7 @@ __device__ __forceinline__ void spin_until(const unsigned long long *flag, unsig
   }
 }
 
-__global__ void __launch_bounds__(32 * WPB) nuts_state_kernel(b2m_nuts_args A, NutsBufs W, int D, KModel prior, StateP S) {
+__global__ void __launch_bounds__(32 * WPB, 7) nuts_state_kernel(b2m_nuts_args A, NutsBufs W, int D, KModel prior, StateP S) {
   extern __shared__ __align__(16) unsigned char smem[];
   SModel sm;
   sm.n_terms = 0;
@@ -1460,6 +1460,7 @@ int glm_nuts_run_fused(GlmModel &gm, const b2m_nuts_args &a, cudaStream_t st) {
     B2M_CHECK_CUDA(cudaMemcpy(&herr, pw.base[pw.rank] + pw.off_err, sizeof(int), cudaMemcpyDeviceToHost));
     B2M_REQUIRE(herr == 0, "NUTS peer exchange: a flag wait timed out");
   }
+  B2M_REQUIRE(!(gm.h_fz_err && *gm.h_fz_err), "concurrent K5 || K6 launch: a dependency wait timed out (results are invalid)");
   return 0;
 }
 

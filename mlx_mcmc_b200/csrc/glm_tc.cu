@@ -448,6 +448,14 @@ tc_gemm_body(const CUtensorMap &tmAh, const CUtensorMap &tmAl, const CUtensorMap
     float acc[CW];
 #pragma unroll
     for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+    bool turn_ok = true;
+    if (FUSED && !RESID && zs > 0) {
+      // K6 role: has the previous slab's partial of this output tile been added?  Sampled now, off the critical path
+      // (the tile that passes the turn on started a whole round of tiles earlier); the epilogue only waits if not.
+      int ok = 0;
+      if (lane == 0) ok = ld_acquire_gpu(E.fz_turn + mp_ * E.fz_tn6 + nt) >= zs * NCTA * NUM_EPI_WARPS;
+      turn_ok = __shfl_sync(0xffffffffu, ok, 0) != 0;
+    }
     for (int ch = 0; ch < n_chunks; ++ch, ++gch) {
       const int buf = gch & 1;
       mbar_wait(&tmem_full[buf], (gch >> 1) & 1);
@@ -582,31 +590,37 @@ tc_gemm_body(const CUtensorMap &tmAh, const CUtensorMap &tmAl, const CUtensorMap
       // overwrites the ring slot.  Row segments of 128 bytes through the transposition scratch.  Every address receives
       // its additions one slab after the other (the turn is passed on only after a gpu-scope fence), so the rounding is
       // that of a sequential sum.
-      if (zs > 0) {
+      if (zs > 0 && !turn_ok) {   // (the counter was already sampled when the tile began: normally nothing to wait for)
         if (lane == 0) spin_ge(E.fz_turn + mp_ * E.fz_tn6 + nt, zs * NCTA * NUM_EPI_WARPS, E.fz_err, E.fz_err_host);
         __syncwarp();
       }
       float *g = E.Gpart + (int64_t)(m0 + q * 32) * E.Dp + nb;
       float *scratch = scratch_base + (warp - 2) * (32 * 33);
+      // after the transposition a lane takes four adjacent columns of rows rr, rr + 4, ...: one 16-byte reduction (or store)
+      // per lane, four whole 128-byte row segments per warp instruction; scratch reads are conflict free (bank = rr + cc + k)
+      const int rr = lane >> 3, cc = (lane & 7) * 4;
 #pragma unroll
       for (int b = 0; b < CW / 32; ++b) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = acc[b * 32 + j];
         __syncwarp();
-        float *gp = g + b * 32 + lane;
-        if (zs > 0) {
-          // reductions performed at L2, no value returned: a load + add + store per row exposed one L2 / DRAM round trip
-          // per row to the promotion warps (measured: the K6 role ran 3.5x slower than its MMAs)
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r)
-            asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(gp + (int64_t)r * E.Dp), "f"(scratch[r * 33 + lane]) : "memory");
-        } else {
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) gp[(int64_t)r * E.Dp] = scratch[r * 33 + lane];
+        float *gp = g + b * 32 + cc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rr + 4 * i;
+          const float v0 = scratch[r * 33 + cc], v1 = scratch[r * 33 + cc + 1], v2 = scratch[r * 33 + cc + 2], v3 = scratch[r * 33 + cc + 3];
+          float *dst = gp + (int64_t)r * E.Dp;
+          if (zs > 0) {
+            // reductions performed at L2, no value returned: a load + add + store per row exposed one L2 / DRAM round trip
+            // per row to the promotion warps (measured: the K6 role ran 3.5x slower than its MMAs)
+            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+          } else {
+            *reinterpret_cast<float4 *>(dst) = make_float4(v0, v1, v2, v3);
+          }
         }
         __syncwarp();
       }
-      __threadfence();
+      // one arrival per warp; lane 0's fence is cumulative over the warp's reductions (ordered before it by the barrier)
       __syncwarp();
       if (lane == 0) {
         __threadfence();
