@@ -117,12 +117,13 @@ struct GlmModel {
 //   B2M_TC_GROUPS_RESID / B2M_TC_GROUPS_GRAD  persistent CTA groups, B2M_TC_CHUNK_RESID / B2M_TC_CHUNK_GRAD promotion
 //   interval in k-blocks, B2M_TC_PAIR=0 single-CTA kernels, B2M_TC_L2_HINTS=1 L2 eviction-policy hints on the TMA loads of
 //   the separate kernels (measured: no gain, off by default)
+//   B2M_TC_K6_ORDER=0 K6 tiles with the pair row fastest (round-1 order) instead of the column tile
 //   B2M_TC_FUSE=0 (default) separate K5 / K6 launches; 1 the concurrent launch for large fp16-encoded problems (a fifth
 //   of the DRAM traffic, ~10-20 % slower: DESIGN.md 4.2), 2 whenever the shape allows; B2M_TC_FUSE_SLAB 256-observation
 //   tiles per slab of the concurrent launch, B2M_TC_FUSE_RING slabs in the residual ring, B2M_TC_FUSE_GROUPS5 CTA pairs given to K5,
 //   B2M_TC_FUSE_HINTS5 / B2M_TC_FUSE_HINTS6 eviction-policy codes (A | B << 2; 0 none, 1 evict_first, 2 evict_last)
 struct Tuning {
-  int groups_resid = 0, groups_grad = 0, chunk_resid = 0, chunk_grad = 0, pair = 1, l2_hints = 0;
+  int groups_resid = 0, groups_grad = 0, chunk_resid = 0, chunk_grad = 0, pair = 1, l2_hints = 0, k6_order = 1;
   int fuse = 0, fuse_slab = 0, fuse_ring = 0, fuse_groups5 = 0, fuse_hints5 = -1, fuse_hints6 = -1;
 };
 const Tuning &tuning();

@@ -254,6 +254,7 @@ struct EpiParams {
   // it a few launches late because it reads the counter without draining the stream)
   const int *skip_flag;
   int skip_target;
+  int nt_fast;    // K6 tile order: column tile fastest (see the tile loop); 0 = pair row fastest (B2M_TC_K6_ORDER=0)
   int l2_hints;   // CTA-pair kernels: L2 eviction-policy codes of the TMA loads, A | B << 2 (see l2_policy)
   // FUSED (concurrent K5 || K6, tc_gemm_fused_kernel): the residual operand is a ring of `fz_ring` slabs of `fz_slab`
   // 256-observation tiles, [Cp, fz_pitch] halves; fz_ready[pair row][slab] counts the epilogue warps of K5 tiles that
@@ -305,12 +306,19 @@ tc_gemm_body(const CUtensorMap &tmAh, const CUtensorMap &tmAl, const CUtensorMap
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta = NCTA == 2 ? cluster_ctarank() : 0u;   // rank inside the CTA pair; 0 = leader (issues the MMAs)
-  // Persistent tile loop: CTA group g (a CTA, or a pair) takes tiles g, g + G, g + 2G, ...  Tile t = (pair-row
-  // t % Tm, column tile (t / Tm) % Tn, K split t / (Tm Tn)): neighbours in time share the B tile.  Barriers and TMEM
+  // Persistent tile loop: CTA group g (a CTA, or a pair) takes tiles g, g + G, g + 2G, ...  K5: tile t = (pair-row
+  // t % Tm, observation tile t / Tm) -- the sixteen pairs on one observation tile share the B tile (design matrix rows),
+  // the A operand (packed positions, 16 MB) lives in L2.  K6: tile t = (column tile t % Tn, pair-row (t / Tn) % Tm, K split
+  // t / (Tm Tn)) -- the Tn neighbours share the A tile, which is the big stream there (the residual operand: 1.6 GB per
+  // evaluation at C4 against 0.4 GB of transposed design matrix); with the pair row fastest the Tn readers of one residual
+  // tile were 16 tiles apart, often in different rounds of the 74 pairs, and the tile came from DRAM more than once.  Barriers and TMEM
   // are set up once; the producer and the MMA issuer run ahead into the next tile while the promotion warps are
   // still in the epilogue of the previous one (both TMEM chunk buffers are free by then).
 #define B2M_DECODE_TILE(t)                                                         \
-  const int mp_ = (t) % Tm, r_ = (t) / Tm, nt = r_ % Tn, zs = r_ / Tn;             \
+  const bool ntf_ = !RESID && E.nt_fast;                                           \
+  const int mp_ = ntf_ ? ((t) / Tn) % Tm : (t) % Tm;                               \
+  const int nt = ntf_ ? (t) % Tn : ((t) / Tm) % Tn;                                \
+  const int zs = (t) / (Tm * Tn);                                                  \
   const int m0 = (mp_ * NCTA + (int)cta) * BLOCK_M, n0 = nt * BLOCK_N;             \
   const int kb0 = zs * k_blocks_per_split;                                         \
   const int kb1 = min(kb0 + k_blocks_per_split, k_blocks_total);                   \
@@ -891,6 +899,7 @@ static Tuning &tuning_storage() {
     x.chunk_grad = geti("B2M_TC_CHUNK_GRAD", 0);
     x.pair = geti("B2M_TC_PAIR", 1);
     x.l2_hints = geti("B2M_TC_L2_HINTS", 0);
+    x.k6_order = geti("B2M_TC_K6_ORDER", 1);
     x.fuse = geti("B2M_TC_FUSE", 0);
     x.fuse_slab = geti("B2M_TC_FUSE_SLAB", 0);
     x.fuse_ring = geti("B2M_TC_FUSE_RING", 0);
@@ -908,7 +917,7 @@ int tuning_set(const char *name, int value) {
   Tuning &t = tuning_storage();
   struct { const char *n; int *p; } tab[] = {
       {"groups_resid", &t.groups_resid}, {"groups_grad", &t.groups_grad}, {"chunk_resid", &t.chunk_resid},
-      {"chunk_grad", &t.chunk_grad}, {"pair", &t.pair}, {"l2_hints", &t.l2_hints}, {"fuse", &t.fuse},
+      {"chunk_grad", &t.chunk_grad}, {"pair", &t.pair}, {"l2_hints", &t.l2_hints}, {"k6_order", &t.k6_order}, {"fuse", &t.fuse},
       {"fuse_slab", &t.fuse_slab}, {"fuse_ring", &t.fuse_ring}, {"fuse_groups5", &t.fuse_groups5},
       {"fuse_hints5", &t.fuse_hints5}, {"fuse_hints6", &t.fuse_hints6}};
   for (auto &e : tab)
@@ -990,6 +999,7 @@ int tc_gemm_grad(GlmModel &g, int64_t Cp, cudaStream_t st) {
   E.Gpart = g.G; E.Cp = Cp; E.Dp = g.Dp;
   E.skip_flag = g.skip_flag; E.skip_target = g.skip_target;
   E.l2_hints = tuning().l2_hints ? (1 | 2 << 2) : 0;   // A (residual stream): evict_first, B (transposed design matrix): evict_last
+  E.nt_fast = tuning().k6_order;
   dim3 grid((unsigned)(Cp / BLOCK_M), g.Dp / bn, (unsigned)((kb_total + kb_per - 1) / kb_per));
   g.g_splits = (int)grid.z;
   const int ck = tuning().chunk_grad > 0 ? tuning().chunk_grad : (f16 ? DEFAULT_CHUNK_KB / 2 : DEFAULT_CHUNK_KB);
@@ -1072,6 +1082,7 @@ static int tc_gemm_fused(GlmModel &g, int64_t Cp, const FusePlan &P, cudaStream_
   E5.fz_err = err_dev; E5.fz_err_host = g.h_fz_err;
   EpiParams E6 = E5;
   E6.Gpart = g.G; E6.Dp = g.Dp;
+  E6.nt_fast = T.k6_order;
   // K5: A = packed positions (16 MB, re-read for every observation tile) -> evict_last, B = design matrix, read once while
   // the sixteen pair rows are on the tile -> evict_first.  K6: no hints (the ring and the slab of the transposed matrix are
   // re-read within a slab time and then dead).
@@ -1143,6 +1154,7 @@ int tc_gemm_grad_push(GlmModel &g, int64_t Cp, cudaStream_t st) {
   EpiParams E{};
   E.Cp = Cp; E.Dp = g.Dp;
   E.l2_hints = tuning().l2_hints ? (1 | 2 << 2) : 0;
+  E.nt_fast = tuning().k6_order;
   E.push_own = (int)w.own; E.push_rank = w.rank;
   for (int s = 0; s < w.nranks; ++s) E.push_dst[s] = reinterpret_cast<float *>(w.base[s] + w.off_g);
   E.r_unscale = g.r_unscale; E.inv_col_scale = g.inv_col_scale;
