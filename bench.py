@@ -61,9 +61,11 @@ WORKLOADS = {
 METRIC = "leapfrog_grad_evals_per_sec"
 UNIT = "grad-evals/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-NCU_TRAFFIC = {"c4": {"bytes": 0.591e9 + 1.616e9 + 3.966e9 + 0.127e9,
-                      "source": "profiles/r02_tc_gemm_c4_ncu_summary.md (K5 0.59 GB read + 1.62 GB written, K6 3.97 GB read + 0.13 GB "
-                                "written; tensor pipe active 85.1 % / 92.6 % of the elapsed cycles)"}}
+NCU_TRAFFIC = {"c4": {"bytes": 0.564e9 + 1.616e9 + 3.281e9 + 0.126e9,
+                      "source": "profiles/r02_tc_gemm_c4_ncu_summary.md, later capture (K5 0.56 GB read + 1.62 GB written, K6 3.28 GB read + "
+                                "0.13 GB written with the column-tile-fastest tile order; tensor pipe active 92.6 % / 92.6 % of the "
+                                "elapsed cycles; the opt-in concurrent K5 || K6 launch moves 1.09 GB: "
+                                "profiles/r02_tc_gemm_fused_c4_ncu_summary.md)"}}
 
 
 # issue-side evidence of the pointwise kernels from the committed ncu captures (profiles/): the bound of these paths
