@@ -340,7 +340,8 @@ int b2m_profile_read_ex(double *out10);
 
 /* Experiments and tests only (no reference counterpart): set one launch-shape knob of the GLM contractions for this process,
  * e.g. ("fuse", 0) = the separate K5 / K6 launches (default), ("fuse", 1) = the concurrent K5 || K6 launch for large
- * problems, ("fuse", 2) = whenever the shape allows, ("fuse_slab", t), ("fuse_ring", r), ("l2_hints", 0|1).  The same knobs are read once from B2M_TC_* environment
+ * problems, ("fuse", 2) = whenever the shape allows, ("fuse_slab", t), ("fuse_ring", r), ("l2_hints", 0|1), ("k6_order", 0|1:
+ * pair row / column tile fastest in K6's persistent tile loop).  The same knobs are read once from B2M_TC_* environment
  * variables at load.  Returns non-zero for an unknown name.  Results never depend on a knob beyond float32 rounding. */
 int b2m_tuning_set(const char *name, int32_t value);
 

@@ -61,7 +61,7 @@ def test_committed_round2_lines_have_the_contract_keys():
     """the one-GPU line and the 8-GPU strong-scaling line of round 2 (profiles/), as the driver would parse them"""
     with open(os.path.join(ROOT, "profiles", "r02_bench_default_v6.json")) as f:
         one = json.loads(f.read())
-    with open(os.path.join(ROOT, "profiles", "r02_bench_c4_n8_strong.json")) as f:
+    with open(os.path.join(ROOT, "profiles", "r02_bench_c4_n8_strong_v2.json")) as f:
         eight = json.loads(f.read())
     for line in (one, eight):
         _check_common(line)
