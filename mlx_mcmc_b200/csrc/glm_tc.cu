@@ -99,10 +99,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   // and was 7 % of the K5 stall samples
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// L2 eviction policies for the TMA loads.  K6 streams the 1.6 GB residual operand once per column tile past the 0.4 GB
-// transposed design matrix that sixteen row tiles re-read: without hints the stream evicts the matrix (ncu: L2 hit rate
-// 63 %, 3.97 GB of DRAM reads for 2.05 GB of operands).  A operand of K6 -> evict_first, B operand -> evict_last;
-// K5's small A operand (the packed positions, re-read by every column tile) -> evict_last.
+// L2 eviction policies for the TMA loads (opt-in, B2M_TC_L2_HINTS=1).  K6 streams the 1.6 GB residual operand past the 0.4 GB
+// transposed design matrix that sixteen row tiles re-read, and reads 3.1-4.0 GB from DRAM for 2.05 GB of operands.  Hints
+// (K6: A -> evict_first, B -> evict_last; K5: its small, re-read A operand -> evict_last) were measured and did not help
+// (K5 + K6 3.63 ms with, 3.42-3.51 ms without); what did was the tile order (column tile fastest, see the tile loop).
 // code: 1 = evict_first, 2 = evict_last (0 = no hint: the plain load is issued instead)
 __device__ __forceinline__ uint64_t l2_policy(int code) {
   uint64_t p;
@@ -357,8 +357,7 @@ tc_gemm_body(const CUtensorMap &tmAh, const CUtensorMap &tmAl, const CUtensorMap
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // K5: A = packed positions (small, re-read by every column tile) -> keep; K6: A = residual stream -> evict first,
-      // B = transposed design matrix (re-read by every row tile) -> keep
+      // eviction-policy codes of the two operands (0 = plain load), set by the launcher
       const int code_a = E.l2_hints & 3, code_b = (E.l2_hints >> 2) & 3;
       const uint64_t pol_a = l2_policy(code_a), pol_b = l2_policy(code_b);
       for (int t = group; t < n_tiles; t += n_groups) {
